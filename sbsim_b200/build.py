@@ -1,0 +1,47 @@
+"""Builds libsbx.so in-tree with nvcc for sm_100a (cross-compiles without a GPU)."""
+
+from __future__ import annotations
+
+import os
+import subprocess
+import sys
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+SRC = os.path.join(_HERE, "csrc", "sbx_api.cu")
+DEPS = [SRC, os.path.join(_HERE, "csrc", "sbx_kernels.cuh"),
+        os.path.join(_HERE, "csrc", "sbx_device.cuh"),
+        os.path.join(os.path.dirname(_HERE), "include", "sbx.h")]
+OUT = os.path.join(_HERE, "lib", "libsbx.so")
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
+    # one IEEE rounding per fp32/fp64 op, as the reference's eager arithmetic has
+    "-fmad=false", "-prec-div=true", "-prec-sqrt=true",
+    "-shared", "-Xcompiler", "-fPIC",
+]
+
+
+def needs_build() -> bool:
+  if not os.path.exists(OUT):
+    return True
+  t = os.path.getmtime(OUT)
+  return any(os.path.getmtime(d) > t for d in DEPS)
+
+
+def build(force: bool = False, verbose: bool = False) -> str:
+  if not force and not needs_build():
+    return OUT
+  os.makedirs(os.path.dirname(OUT), exist_ok=True)
+  nvcc = os.environ.get("NVCC", "nvcc")
+  cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+  res = subprocess.run(cmd, capture_output=True, text=True)
+  if res.returncode != 0:
+    sys.stderr.write(res.stdout + res.stderr)
+    raise RuntimeError("nvcc failed building libsbx.so")
+  if verbose:
+    sys.stderr.write(res.stderr)
+  return OUT
+
+
+if __name__ == "__main__":
+  print(build(force="--force" in sys.argv, verbose="-v" in sys.argv))

@@ -1,0 +1,683 @@
+// libsbx.so: C ABI (include/sbx.h) over the sm_100a kernels in sbx_kernels.cuh.
+//
+// Host-side design
+//   * The handle owns every device allocation (state, static plan data,
+//     exogenous tables); callers pass only I/O buffers.
+//   * All envs of a handle share one clock, so step_count / time_index /
+//     episode_ended and the thermostats' "previous timestamp" (which the
+//     reference never resets, vav.py:98) are host integers.
+//   * Resident path: one kernel launch per env step.  Streaming path: HVAC
+//     prologue, one launch per Jacobi sweep with a pinned-memory convergence
+//     poll, zone reduction, epilogue.
+//   * sbx_step_host stages through pinned buffers so that host<->device copies
+//     are asynchronous DMA on the handle's stream.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <new>
+#include <string>
+
+#include "../../include/sbx.h"
+#include "sbx_kernels.cuh"
+
+using namespace sbx;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct DevBuf {
+  void* p = nullptr;
+  size_t bytes = 0;
+};
+
+}  // namespace
+
+struct sbx_env {
+  sbx_config cfg;
+  int device = 0;
+  int D = 0;
+  int path = SBX_PATH_STREAMING;
+  int V = 1;
+  int n_sms = 0;
+  int resident_ctas_per_sm = 0;
+  size_t resident_smem = 0;
+  Params P;
+  // host-level episode state
+  int step_count = 0, time_index = 0, episode_ended = 0, reset_called = 0;
+  int therm_seen = 0, prev_comfort = 0;
+  uint8_t* h_comfort = nullptr;  // host copy of the comfort table (for prev_comfort)
+  // device allocations
+  DevBuf all[64];
+  int n_all = 0;
+  int64_t device_bytes = 0;
+  int64_t launches = 0;
+  int64_t env_steps = 0;
+  CarryStore* carry = nullptr;
+  float* gather = nullptr;       // [B,H,W] staging for download of T (streaming path)
+  double* fd_ambient = nullptr;
+  double* fd_convection = nullptr;
+  double* d_obs_mean = nullptr;
+  double* d_obs_var = nullptr;
+  double* d_hist_bins = nullptr;
+  // I/O staging for the *_host calls
+  float* d_action = nullptr;
+  float* d_obs = nullptr;
+  float* d_reward = nullptr;
+  int32_t* d_step_type = nullptr;
+  float* d_discount = nullptr;
+  float* h_action = nullptr;     // pinned
+  float* h_obs = nullptr;
+  float* h_reward = nullptr;
+  int32_t* h_step_type = nullptr;
+  float* h_discount = nullptr;
+  int32_t* h_n_active = nullptr; // pinned
+  cudaStream_t stream = nullptr; // handle-owned stream for *_host calls and uploads
+  std::string err;
+};
+
+namespace {
+
+int fail(sbx_handle h, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (h) h->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CUDA_TRY(h, expr)                                                              \
+  do {                                                                                 \
+    cudaError_t e__ = (expr);                                                          \
+    if (e__ != cudaSuccess)                                                            \
+      return fail(h, SBX_E_CUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e__), \
+                  __FILE__, __LINE__);                                                 \
+  } while (0)
+
+template <typename T>
+int dev_alloc(sbx_handle h, T** out, size_t count, bool zero = true) {
+  void* p = nullptr;
+  const size_t bytes = (count ? count : 1) * sizeof(T);
+  cudaError_t e = cudaMalloc(&p, bytes);
+  if (e != cudaSuccess)
+    return fail(h, SBX_E_NOMEM, "cudaMalloc(%zu bytes) failed: %s", bytes, cudaGetErrorString(e));
+  if (zero) {
+    e = cudaMemset(p, 0, bytes);
+    if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
+  }
+  if (h->n_all >= 64) return fail(h, SBX_E_INVALID, "too many allocations");
+  h->all[h->n_all].p = p;
+  h->all[h->n_all].bytes = bytes;
+  ++h->n_all;
+  h->device_bytes += (int64_t)bytes;
+  *out = reinterpret_cast<T*>(p);
+  return SBX_OK;
+}
+
+int obs_dim(const sbx_config& c) {
+  int d = 9 + 3 + 7;
+  if (c.obs_mode == SBX_OBS_RAW) d += 3 * c.n_zones;
+  else d += c.n_hist_bins[0] + c.n_hist_bins[1] + c.n_hist_bins[2];
+  return d;
+}
+
+int validate(const sbx_config& c) {
+  if (c.abi_version != SBX_ABI_VERSION) return fail(nullptr, SBX_E_INVALID, "abi_version %d != %d", c.abi_version, SBX_ABI_VERSION);
+  if (c.n_envs < 1 || c.height < 1 || c.width < 1) return fail(nullptr, SBX_E_INVALID, "n_envs/height/width must be >= 1");
+  if (c.n_zones < 1 || c.n_zones > 254) return fail(nullptr, SBX_E_INVALID, "n_zones must be in [1, 254]");
+  if (c.n_plans != 1 && c.n_plans != c.n_envs) return fail(nullptr, SBX_E_INVALID, "n_plans must be 1 or n_envs");
+  if (c.n_weather != 1 && c.n_weather != c.n_envs) return fail(nullptr, SBX_E_INVALID, "n_weather must be 1 or n_envs");
+  if (c.n_reset != 0 && c.n_reset != 1 && c.n_reset != c.n_envs) return fail(nullptr, SBX_E_INVALID, "n_reset must be 0, 1 or n_envs");
+  if (c.n_occ_zones != 1 && c.n_occ_zones != c.n_zones) return fail(nullptr, SBX_E_INVALID, "n_occ_zones must be 1 or n_zones");
+  if (c.episode_steps < 0 || c.n_table_steps < c.episode_steps + 2) return fail(nullptr, SBX_E_INVALID, "n_table_steps must be >= episode_steps + 2");
+  if (c.n_actions < 0 || c.n_actions > SBX_MAX_ACTIONS) return fail(nullptr, SBX_E_INVALID, "n_actions must be in [0, %d]", SBX_MAX_ACTIONS);
+  for (int i = 0; i < c.n_actions; ++i)
+    if (c.action_target[i] < 0 || c.action_target[i] > 2) return fail(nullptr, SBX_E_INVALID, "bad action_target[%d]", i);
+  if (c.obs_mode != SBX_OBS_RAW && c.obs_mode != SBX_OBS_HISTOGRAM) return fail(nullptr, SBX_E_INVALID, "bad obs_mode");
+  if (c.obs_mode == SBX_OBS_HISTOGRAM)
+    for (int f = 0; f < 3; ++f)
+      if (c.n_hist_bins[f] < 1 || c.n_hist_bins[f] > SBX_MAX_HIST_BINS) return fail(nullptr, SBX_E_INVALID, "n_hist_bins[%d] out of range", f);
+  if (c.iteration_limit < 1) return fail(nullptr, SBX_E_INVALID, "iteration_limit must be >= 1");
+  if (!(c.time_step_sec > 0.f)) return fail(nullptr, SBX_E_INVALID, "time_step_sec must be > 0");
+  if (c.discount_factor <= 0 || c.discount_factor > 1) return fail(nullptr, SBX_E_INVALID, "Discount factor must be in (0,1]");  // environment.py:446
+  if (c.ahu_init_cooling_setpoint <= c.ahu_init_heating_setpoint) return fail(nullptr, SBX_E_INVALID, "cooling_air_temp_setpoint must greater than heating_air_temp_setpoint");  // air_handler.py:62-66
+  if (c.max_productivity_personhour_usd <= c.min_productivity_personhour_usd) return fail(nullptr, SBX_E_INVALID, "max productivity must exceed min productivity");
+  return SBX_OK;
+}
+
+void fill_params(sbx_handle h) {
+  const sbx_config& c = h->cfg;
+  Params& p = h->P;
+  p.B = c.n_envs; p.H = c.height; p.W = c.width; p.Z = c.n_zones;
+  p.n_plans = c.n_plans; p.n_weather = c.n_weather; p.n_reset = c.n_reset;
+  p.n_occ_zones = c.n_occ_zones; p.T_rows = c.n_table_steps;
+  p.obs_mode = c.obs_mode; p.D = h->D; p.n_actions = c.n_actions;
+  for (int i = 0; i < SBX_MAX_ACTIONS; ++i) {
+    p.action_target[i] = c.action_target[i];
+    // `agent_ratio * output_range + min` with np.float32 agent_ratio: the Python
+    // floats are cast to fp32 first (NEP 50 weak scalars).
+    p.action_min[i] = (float)c.action_min[i];
+    p.action_range[i] = (float)(c.action_max[i] - c.action_min[i]);
+  }
+  for (int f = 0; f < 3; ++f) p.n_hist_bins[f] = c.obs_mode == SBX_OBS_HISTOGRAM ? c.n_hist_bins[f] : 0;
+  p.dt = c.time_step_sec; p.z = c.floor_height_m; p.threshold = c.convergence_threshold;
+  p.iteration_limit = c.iteration_limit;
+  p.comfort_heat = c.comfort_heat; p.comfort_cool = c.comfort_cool;
+  p.eco_heat = c.eco_heat; p.eco_cool = c.eco_cool;
+  p.ahu_r = c.ahu_recirculation; p.ahu_init_heat = c.ahu_init_heating_setpoint;
+  p.ahu_init_cool = c.ahu_init_cooling_setpoint; p.ahu_dp = c.ahu_fan_differential_pressure;
+  p.ahu_eff = c.ahu_fan_efficiency; p.ahu_max_flow = c.ahu_max_air_flow_rate;
+  p.boiler_init_sp = c.boiler_init_setpoint; p.boiler_head = c.boiler_pump_head;
+  p.boiler_eff = c.boiler_pump_efficiency; p.boiler_heat_rate = c.boiler_heating_rate;
+  p.boiler_cool_rate = c.boiler_cooling_rate;
+  {  // compute_thermal_dissipation_rate boiler.py:309-320
+    const double r1 = c.boiler_tank_radius, r2 = r1 + c.boiler_insulation_thickness;
+    const double conduction = log(r2 / r1) / c.boiler_insulation_conductivity;
+    const double convection = 1.0 / c.boiler_convection_coefficient / r2;
+    p.boiler_diss_factor = c.boiler_tank_length * 2.0 * M_PI / (conduction + convection);
+  }
+  p.boiler_capacity = c.boiler_water_capacity;
+  p.vav_max_flow = c.vav_max_air_flow_rate; p.vav_max_reheat = c.vav_reheat_max_water_flow_rate;
+  p.pmax = c.max_productivity_personhour_usd; p.pmin = c.min_productivity_personhour_usd;
+  p.emax = c.max_electricity_rate; p.gmax = c.max_natural_gas_rate;
+  p.delta = c.productivity_midpoint_delta; p.stiff = c.productivity_decay_stiffness;
+  p.wu = c.productivity_weight; p.wv = c.energy_cost_weight; p.ww = c.carbon_emission_weight;
+  p.gas_carbon = c.gas_carbon_rate;
+  p.discount = c.discount_factor; p.occ_norm = c.occupancy_normalization_constant;
+  p.episode_steps = c.episode_steps;
+  p.fd_only = 0;
+}
+
+// launch helpers --------------------------------------------------------------
+
+int pre_post_smem(const sbx_handle h, int warps) {
+  return warps * (3 * h->cfg.n_zones + 64 + h->cfg.n_zones) * (int)sizeof(double);
+}
+
+int launch_check(sbx_handle h, const char* what) {
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(e));
+  ++h->launches;
+  return SBX_OK;
+}
+
+int launch_zone_reduce(sbx_handle h, cudaStream_t st) {
+  const Params& p = h->P;
+  CUDA_TRY(h, cudaMemsetAsync(p.zone_sum, 0, sizeof(double) * (size_t)p.B * (p.Z + 1), st));
+  const StreamTiling tl = stream_tiling(p.H, p.W, h->V);
+  const unsigned grid = (unsigned)((size_t)tl.tiles * p.B);
+  if (h->V == 4) k_zone_reduce<4><<<grid, kStreamThreads, 0, st>>>(p);
+  else k_zone_reduce<1><<<grid, kStreamThreads, 0, st>>>(p);
+  return launch_check(h, "k_zone_reduce");
+}
+
+int launch_post(sbx_handle h, cudaStream_t st, int is_reset) {
+  const Params& p = h->P;
+  const int wpb = 4;
+  const unsigned grid = (unsigned)((p.B + wpb - 1) / wpb);
+  k_post<<<grid, wpb * 32, pre_post_smem(h, wpb), st>>>(p, h->carry, is_reset);
+  return launch_check(h, "k_post");
+}
+
+// Streaming Jacobi loop: one launch per sweep + convergence poll.
+int run_stream_sweeps(sbx_handle h, cudaStream_t st) {
+  const Params& p = h->P;
+  const unsigned gb = (unsigned)((p.B + 255) / 256);
+  k_activate<<<gb, 256, 0, st>>>(p);
+  if (int rc = launch_check(h, "k_activate")) return rc;
+  const StreamTiling tl = stream_tiling(p.H, p.W, h->V);
+  const unsigned grid = (unsigned)((size_t)tl.tiles * p.B);
+  for (int k = 1; k <= p.iteration_limit; ++k) {
+    if (h->V == 4) k_sweep<4><<<grid, kStreamThreads, 0, st>>>(p, k);
+    else k_sweep<1><<<grid, kStreamThreads, 0, st>>>(p, k);
+    if (int rc = launch_check(h, "k_sweep")) return rc;
+    CUDA_TRY(h, cudaMemsetAsync(p.n_active, 0, sizeof(int32_t), st));
+    k_check<<<gb, 256, 0, st>>>(p, k);
+    if (int rc = launch_check(h, "k_check")) return rc;
+    CUDA_TRY(h, cudaMemcpyAsync(h->h_n_active, p.n_active, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    if (*h->h_n_active == 0) break;
+  }
+  return SBX_OK;
+}
+
+int run_resident(sbx_handle h, cudaStream_t st) {
+  const Params& p = h->P;
+  if (h->V == 4) k_resident_step<4><<<p.B, kResidentThreads, h->resident_smem, st>>>(p);
+  else k_resident_step<1><<<p.B, kResidentThreads, h->resident_smem, st>>>(p);
+  return launch_check(h, "k_resident_step");
+}
+
+int do_reset(sbx_handle h, float* obs, float* reward, int32_t* step_type, float* discount,
+             cudaStream_t st) {
+  Params& p = h->P;
+  p.fd_only = 0;
+  p.time_index = 0; p.step_count = 0;
+  p.therm_seen = h->therm_seen; p.prev_comfort = h->prev_comfort;
+  p.action = nullptr; p.obs = obs; p.reward = reward; p.step_type = step_type; p.discount_out = discount;
+  const unsigned gb = (unsigned)((p.B + 255) / 256);
+  k_reset_state<<<gb, 256, 0, st>>>(p);
+  if (int rc = launch_check(h, "k_reset_state")) return rc;
+  const size_t total = (size_t)p.B * p.H * p.W;
+  const unsigned gt = (unsigned)((total + 256 * 8 - 1) / (256 * 8));
+  k_reset_temp<<<gt > 0 ? gt : 1, 256, 0, st>>>(p);
+  if (int rc = launch_check(h, "k_reset_temp")) return rc;
+  if (int rc = launch_zone_reduce(h, st)) return rc;
+  if (int rc = launch_post(h, st, 1)) return rc;
+  h->step_count = 0; h->time_index = 0; h->episode_ended = 0; h->reset_called = 1;
+  return SBX_OK;
+}
+
+int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_t* step_type,
+            float* discount, cudaStream_t st) {
+  if (!h->reset_called) return fail(h, SBX_E_STATE, "sbx_step before sbx_reset");
+  if (h->episode_ended) return fail(h, SBX_E_STATE, "episode has ended; call sbx_reset (environment.py:1252)");
+  if (h->cfg.n_actions > 0 && !action) return fail(h, SBX_E_INVALID, "action is NULL");
+  if (h->time_index + 1 >= h->cfg.n_table_steps) return fail(h, SBX_E_STATE, "time index %d beyond the exogenous tables (%d rows)", h->time_index + 1, h->cfg.n_table_steps);
+  Params& p = h->P;
+  p.fd_only = 0;
+  p.time_index = h->time_index; p.step_count = h->step_count;
+  p.therm_seen = h->therm_seen; p.prev_comfort = h->prev_comfort;
+  p.action = action; p.obs = obs; p.reward = reward; p.step_type = step_type; p.discount_out = discount;
+  if (h->path == SBX_PATH_RESIDENT) {
+    if (int rc = run_resident(h, st)) return rc;
+  } else {
+    const int wpb = 4;
+    const unsigned grid = (unsigned)((p.B + wpb - 1) / wpb);
+    k_pre<<<grid, wpb * 32, pre_post_smem(h, wpb), st>>>(p, h->carry);
+    if (int rc = launch_check(h, "k_pre")) return rc;
+    if (int rc = run_stream_sweeps(h, st)) return rc;
+    if (int rc = launch_zone_reduce(h, st)) return rc;
+    if (int rc = launch_post(h, st, 0)) return rc;
+  }
+  // host mirror of Thermostat._previous_timestamp (thermostat.py:147) and of the
+  // episode counters (environment.py:1313, 1358-1359)
+  h->therm_seen = 1;
+  h->prev_comfort = h->h_comfort ? h->h_comfort[h->time_index] : 0;
+  const bool ended = h->step_count >= h->cfg.episode_steps;
+  h->episode_ended = ended ? 1 : 0;
+  if (!ended) ++h->step_count;
+  ++h->time_index;
+  h->env_steps += h->cfg.n_envs;
+  return SBX_OK;
+}
+
+struct FieldInfo {
+  void* ptr;
+  size_t bytes;
+  bool writable;
+};
+
+}  // namespace
+
+extern "C" {
+
+const char* sbx_last_error(sbx_handle h) { return h ? h->err.c_str() : g_create_error.c_str(); }
+
+int sbx_abi_info(int32_t* abi_version, size_t* config_bytes, size_t* info_bytes) {
+  if (abi_version) *abi_version = SBX_ABI_VERSION;
+  if (config_bytes) *config_bytes = sizeof(sbx_config);
+  if (info_bytes) *info_bytes = sizeof(sbx_info);
+  return SBX_OK;
+}
+
+int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
+  if (!cfg || !out) return fail(nullptr, SBX_E_INVALID, "null argument");
+  *out = nullptr;
+  if (int rc = validate(*cfg)) return rc;
+  sbx_handle h = new (std::nothrow) sbx_env();
+  if (!h) return fail(nullptr, SBX_E_NOMEM, "out of host memory");
+  h->cfg = *cfg;
+  h->device = device;
+  h->D = obs_dim(*cfg);
+  auto bail = [&](int rc) {
+    g_create_error = h->err;
+    sbx_destroy(h);
+    return rc;
+  };
+  {
+    cudaError_t e = cudaSetDevice(device);
+    if (e != cudaSuccess) { fail(h, SBX_E_CUDA, "cudaSetDevice(%d) failed: %s", device, cudaGetErrorString(e)); return bail(SBX_E_CUDA); }
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, device);
+    if (e != cudaSuccess) { fail(h, SBX_E_CUDA, "cudaGetDeviceProperties failed: %s", cudaGetErrorString(e)); return bail(SBX_E_CUDA); }
+    h->n_sms = prop.multiProcessorCount;
+    if (prop.major < 10) { fail(h, SBX_E_CUDA, "libsbx is built for sm_100a; device %d is sm_%d%d", device, prop.major, prop.minor); return bail(SBX_E_CUDA); }
+  }
+  const sbx_config& c = h->cfg;
+  const size_t B = c.n_envs, Z = c.n_zones, N = (size_t)c.height * c.width, T = c.n_table_steps;
+  h->V = (c.width % 4 == 0) ? 4 : 1;
+
+  // path selection
+  const ResidentLayout L = resident_layout((int)N, (int)Z);
+  int max_optin = 0;
+  cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+  const bool fits = L.total <= (size_t)max_optin && (c.width / h->V) <= kResidentThreads * 64;
+  if (c.kernel_path == SBX_PATH_RESIDENT && !fits) {
+    fail(h, SBX_E_INVALID, "resident path needs %zu B of shared memory per CTA; device allows %d", L.total, max_optin);
+    return bail(SBX_E_INVALID);
+  }
+  h->path = (c.kernel_path == SBX_PATH_AUTO) ? (fits ? SBX_PATH_RESIDENT : SBX_PATH_STREAMING) : c.kernel_path;
+  h->resident_smem = L.total;
+  if (h->path == SBX_PATH_RESIDENT) {
+    cudaError_t e;
+    if (h->V == 4) e = cudaFuncSetAttribute(k_resident_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    else e = cudaFuncSetAttribute(k_resident_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (e != cudaSuccess) { fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return bail(SBX_E_CUDA); }
+    int nb = 0;
+    if (h->V == 4) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_resident_step<4>, kResidentThreads, L.total);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb, k_resident_step<1>, kResidentThreads, L.total);
+    h->resident_ctas_per_sm = nb;
+  }
+
+  Params& p = h->P;
+  memset(&p, 0, sizeof(p));
+  fill_params(h);
+#define ALLOC(field, type, count)                                           \
+  do {                                                                      \
+    type* tmp__ = nullptr;                                                  \
+    if (int rc = dev_alloc<type>(h, &tmp__, (count))) return bail(rc);      \
+    field = tmp__;                                                          \
+  } while (0)
+  ALLOC(p.desc, uint16_t, (size_t)c.n_plans * N);
+  ALLOC(p.material, double, (size_t)c.n_plans * 9);
+  ALLOC(p.cv_size, double, (size_t)c.n_plans);
+  ALLOC(p.zone_ncv, int32_t, (size_t)c.n_plans * Z);
+  ALLOC(p.zone_ndiff, int32_t, (size_t)c.n_plans * Z);
+  ALLOC(p.obs_zone_order, int32_t, (size_t)c.n_plans * Z);
+  ALLOC(p.reset_temps, float, (size_t)c.n_reset * N);
+  ALLOC(p.initial_temp, float, B);
+  ALLOC(p.ambient, double, (size_t)c.n_weather * T);
+  ALLOC(p.convection, double, (size_t)c.n_weather);
+  ALLOC(p.comfort, uint8_t, T);
+  ALLOC(p.comfort_soon, uint8_t, T);
+  ALLOC(p.occ_reward, double, T * c.n_occ_zones);
+  ALLOC(p.occ_obs, int32_t, T);
+  ALLOC(p.price_e, double, T);
+  ALLOC(p.carbon_e, double, T);
+  ALLOC(p.price_g, double, T);
+  ALLOC(p.time_feat, double, T * 4);
+  ALLOC(h->d_obs_mean, double, SBX_N_DEVICE_FIELDS);
+  ALLOC(h->d_obs_var, double, SBX_N_DEVICE_FIELDS);
+  ALLOC(h->d_hist_bins, double, 3 * SBX_MAX_HIST_BINS);
+  const int n_tbuf = h->path == SBX_PATH_RESIDENT ? 1 : 3;
+  for (int i = 0; i < n_tbuf; ++i) ALLOC(p.tbuf[i], float, B * N);
+  for (int i = n_tbuf; i < 3; ++i) p.tbuf[i] = p.tbuf[0];
+  ALLOC(p.cur, uint8_t, B);
+  ALLOC(p.zone_mean, float, B * Z);
+  ALLOC(p.global_mean, float, B);
+  ALLOC(p.qcv, float, B * Z);
+  ALLOC(p.qcv_next, float, B * Z);
+  ALLOC(p.therm_mode, uint8_t, B * Z);
+  ALLOC(p.ahu_heat_sp, double, B);
+  ALLOC(p.ahu_cool_sp, double, B);
+  ALLOC(p.boiler_sp, double, B);
+  ALLOC(p.boiler_tank, double, B * 3);
+  ALLOC(p.pre_zone_mean, float, B * Z);
+  ALLOC(p.diag, double, B * SBX_DIAG_N);
+  ALLOC(p.q_zone, double, B * Z);
+  ALLOC(p.zone_supply, double, B * Z);
+  ALLOC(p.n_sweeps, int32_t, B);
+  ALLOC(p.max_delta_bits, uint32_t, B);
+  ALLOC(p.max_delta, float, B);
+  ALLOC(p.zone_sum, double, B * (Z + 1));
+  ALLOC(p.active, uint8_t, B);
+  ALLOC(p.n_active, int32_t, 1);
+  ALLOC(p.sweeps_total, unsigned long long, 1);
+  ALLOC(h->carry, CarryStore, B);
+  ALLOC(h->fd_ambient, double, B);
+  ALLOC(h->fd_convection, double, B);
+  ALLOC(h->d_action, float, B * (c.n_actions > 0 ? c.n_actions : 1));
+  ALLOC(h->d_obs, float, B * h->D);
+  ALLOC(h->d_reward, float, B);
+  ALLOC(h->d_step_type, int32_t, B);
+  ALLOC(h->d_discount, float, B);
+#undef ALLOC
+  p.obs_mean = h->d_obs_mean; p.obs_var = h->d_obs_var; p.hist_bins = h->d_hist_bins;
+  p.obs_inv_std = nullptr;
+  p.fd_ambient = h->fd_ambient; p.fd_convection = h->fd_convection;
+  {
+    cudaError_t e = cudaMemcpy(h->d_obs_mean, c.obs_mean, sizeof(c.obs_mean), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_obs_var, c.obs_variance, sizeof(c.obs_variance), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaMemcpy(h->d_hist_bins, c.hist_bins, sizeof(c.hist_bins), cudaMemcpyHostToDevice);
+    if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_action, sizeof(float) * B * (c.n_actions > 0 ? c.n_actions : 1));
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_obs, sizeof(float) * B * h->D);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_reward, sizeof(float) * B);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_step_type, sizeof(int32_t) * B);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_discount, sizeof(float) * B);
+    if (e == cudaSuccess) e = cudaMallocHost(&h->h_n_active, sizeof(int32_t));
+    if (e != cudaSuccess) { fail(h, SBX_E_CUDA, "host-side setup failed: %s", cudaGetErrorString(e)); return bail(SBX_E_CUDA); }
+  }
+  h->h_comfort = new (std::nothrow) uint8_t[T]();
+  if (!h->h_comfort) { fail(h, SBX_E_NOMEM, "out of host memory"); return bail(SBX_E_NOMEM); }
+  *out = h;
+  return SBX_OK;
+}
+
+int sbx_destroy(sbx_handle h) {
+  if (!h) return SBX_OK;
+  cudaSetDevice(h->device);
+  cudaDeviceSynchronize();
+  for (int i = 0; i < h->n_all; ++i) cudaFree(h->all[i].p);
+  if (h->gather) cudaFree(h->gather);
+  cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward);
+  cudaFreeHost(h->h_step_type); cudaFreeHost(h->h_discount); cudaFreeHost(h->h_n_active);
+  if (h->stream) cudaStreamDestroy(h->stream);
+  delete[] h->h_comfort;
+  delete h;
+  return SBX_OK;
+}
+
+int sbx_get_info(sbx_handle h, sbx_info* out) {
+  if (!h || !out) return fail(h, SBX_E_INVALID, "null argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  memset(out, 0, sizeof(*out));
+  out->obs_dim = h->D;
+  out->kernel_path = h->path;
+  out->n_sms = h->n_sms;
+  out->resident_ctas_per_sm = h->resident_ctas_per_sm;
+  out->device_bytes = h->device_bytes;
+  out->kernel_launches = h->launches;
+  unsigned long long sw = 0;
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  CUDA_TRY(h, cudaMemcpy(&sw, h->P.sweeps_total, sizeof(sw), cudaMemcpyDeviceToHost));
+  out->sweeps_total = (int64_t)sw;
+  out->env_steps_total = h->env_steps;
+  out->step_count = h->step_count;
+  out->episode_ended = h->episode_ended;
+  out->time_index = h->time_index;
+  return SBX_OK;
+}
+
+static int field_info(sbx_handle h, int field, FieldInfo* fi) {
+  const sbx_config& c = h->cfg;
+  const Params& p = h->P;
+  const size_t B = c.n_envs, Z = c.n_zones, N = (size_t)c.height * c.width, T = c.n_table_steps;
+#define F(id, ptr_, count, type, w) case id: fi->ptr = (void*)(ptr_); fi->bytes = (size_t)(count) * sizeof(type); fi->writable = w; return SBX_OK
+  switch (field) {
+    F(SBX_F_PLAN_DESC, p.desc, (size_t)c.n_plans * N, uint16_t, true);
+    F(SBX_F_PLAN_MATERIAL, p.material, (size_t)c.n_plans * 9, double, true);
+    F(SBX_F_PLAN_CV_SIZE, p.cv_size, c.n_plans, double, true);
+    F(SBX_F_ZONE_NCV, p.zone_ncv, (size_t)c.n_plans * Z, int32_t, true);
+    F(SBX_F_ZONE_NDIFF, p.zone_ndiff, (size_t)c.n_plans * Z, int32_t, true);
+    F(SBX_F_OBS_ZONE_ORDER, p.obs_zone_order, (size_t)c.n_plans * Z, int32_t, true);
+    F(SBX_F_RESET_TEMPS, p.reset_temps, (size_t)c.n_reset * N, float, true);
+    F(SBX_F_INITIAL_TEMP, p.initial_temp, B, float, true);
+    F(SBX_F_AMBIENT, p.ambient, (size_t)c.n_weather * T, double, true);
+    F(SBX_F_CONVECTION, p.convection, c.n_weather, double, true);
+    F(SBX_F_COMFORT, p.comfort, T, uint8_t, true);
+    F(SBX_F_COMFORT_SOON, p.comfort_soon, T, uint8_t, true);
+    F(SBX_F_OCC_REWARD, p.occ_reward, T * c.n_occ_zones, double, true);
+    F(SBX_F_OCC_OBS, p.occ_obs, T, int32_t, true);
+    F(SBX_F_PRICE_ELEC, p.price_e, T, double, true);
+    F(SBX_F_CARBON_ELEC, p.carbon_e, T, double, true);
+    F(SBX_F_PRICE_GAS, p.price_g, T, double, true);
+    F(SBX_F_TIME_FEATURES, p.time_feat, T * 4, double, true);
+    F(SBX_F_TEMP, p.tbuf[0], B * N, float, true);
+    F(SBX_F_ZONE_MEAN, p.zone_mean, B * Z, float, true);
+    F(SBX_F_GLOBAL_MEAN, p.global_mean, B, float, true);
+    F(SBX_F_Q_CV, p.qcv, B * Z, float, true);
+    F(SBX_F_THERMOSTAT_MODE, p.therm_mode, B * Z, uint8_t, true);
+    F(SBX_F_AHU_HEATING_SP, p.ahu_heat_sp, B, double, true);
+    F(SBX_F_AHU_COOLING_SP, p.ahu_cool_sp, B, double, true);
+    F(SBX_F_BOILER_SP, p.boiler_sp, B, double, true);
+    F(SBX_F_BOILER_TANK, p.boiler_tank, B * 3, double, true);
+    F(SBX_F_N_SWEEPS, p.n_sweeps, B, int32_t, false);
+    F(SBX_F_MAX_DELTA, p.max_delta, B, float, false);
+    F(SBX_F_STEP_DIAG, p.diag, B * SBX_DIAG_N, double, false);
+    F(SBX_F_Q_ZONE, p.q_zone, B * Z, double, false);
+    F(SBX_F_ZONE_SUPPLY_TEMP, p.zone_supply, B * Z, double, false);
+    F(SBX_F_PRE_ZONE_MEAN, p.pre_zone_mean, B * Z, float, false);
+    default: break;
+  }
+#undef F
+  return fail(h, SBX_E_INVALID, "unknown field %d", field);
+}
+
+int sbx_upload(sbx_handle h, int field, const void* src, size_t nbytes) {
+  if (!h || !src) return fail(h, SBX_E_INVALID, "null argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (field == SBX_F_THERMOSTAT_PREV) {
+    if (nbytes != 2 * sizeof(int32_t)) return fail(h, SBX_E_INVALID, "field %d needs %zu bytes, got %zu", field, 2 * sizeof(int32_t), nbytes);
+    const int32_t* v = (const int32_t*)src;
+    h->therm_seen = v[0] != 0; h->prev_comfort = v[1] != 0;
+    return SBX_OK;
+  }
+  if (field == SBX_F_EPISODE) {
+    if (nbytes != 4 * sizeof(int32_t)) return fail(h, SBX_E_INVALID, "field %d needs %zu bytes, got %zu", field, 4 * sizeof(int32_t), nbytes);
+    const int32_t* v = (const int32_t*)src;
+    if (v[1] < 0 || v[1] >= h->cfg.n_table_steps) return fail(h, SBX_E_INVALID, "time_index %d outside the tables", v[1]);
+    h->step_count = v[0]; h->time_index = v[1]; h->episode_ended = v[2] != 0; h->reset_called = v[3] != 0;
+    return SBX_OK;
+  }
+  FieldInfo fi;
+  if (int rc = field_info(h, field, &fi)) return rc;
+  if (!fi.writable) return fail(h, SBX_E_INVALID, "field %d is read-only", field);
+  if (nbytes != fi.bytes) return fail(h, SBX_E_INVALID, "field %d needs %zu bytes, got %zu", field, fi.bytes, nbytes);
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  CUDA_TRY(h, cudaMemcpy(fi.ptr, src, nbytes, cudaMemcpyHostToDevice));
+  if (field == SBX_F_TEMP) CUDA_TRY(h, cudaMemset(h->P.cur, 0, h->cfg.n_envs));
+  if (field == SBX_F_COMFORT) memcpy(h->h_comfort, src, nbytes);
+  return SBX_OK;
+}
+
+int sbx_download(sbx_handle h, int field, void* dst, size_t nbytes) {
+  if (!h || !dst) return fail(h, SBX_E_INVALID, "null argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (field == SBX_F_THERMOSTAT_PREV) {
+    if (nbytes != 2 * sizeof(int32_t)) return fail(h, SBX_E_INVALID, "field %d needs %zu bytes, got %zu", field, 2 * sizeof(int32_t), nbytes);
+    int32_t* v = (int32_t*)dst;
+    v[0] = h->therm_seen; v[1] = h->prev_comfort;
+    return SBX_OK;
+  }
+  if (field == SBX_F_EPISODE) {
+    if (nbytes != 4 * sizeof(int32_t)) return fail(h, SBX_E_INVALID, "field %d needs %zu bytes, got %zu", field, 4 * sizeof(int32_t), nbytes);
+    int32_t* v = (int32_t*)dst;
+    v[0] = h->step_count; v[1] = h->time_index; v[2] = h->episode_ended; v[3] = h->reset_called;
+    return SBX_OK;
+  }
+  FieldInfo fi;
+  if (int rc = field_info(h, field, &fi)) return rc;
+  if (nbytes != fi.bytes) return fail(h, SBX_E_INVALID, "field %d needs %zu bytes, got %zu", field, fi.bytes, nbytes);
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  if (field == SBX_F_TEMP && h->path != SBX_PATH_RESIDENT) {
+    if (!h->gather) {
+      cudaError_t e = cudaMalloc((void**)&h->gather, fi.bytes);
+      if (e != cudaSuccess) return fail(h, SBX_E_NOMEM, "cudaMalloc(%zu) failed: %s", fi.bytes, cudaGetErrorString(e));
+    }
+    const size_t total = fi.bytes / sizeof(float);
+    const unsigned g = (unsigned)((total + 256 * 8 - 1) / (256 * 8));
+    k_gather_temp<<<g > 0 ? g : 1, 256>>>(h->P, h->gather);
+    if (int rc = launch_check(h, "k_gather_temp")) return rc;
+    CUDA_TRY(h, cudaMemcpy(dst, h->gather, nbytes, cudaMemcpyDeviceToHost));
+    return SBX_OK;
+  }
+  CUDA_TRY(h, cudaMemcpy(dst, fi.ptr, nbytes, cudaMemcpyDeviceToHost));
+  return SBX_OK;
+}
+
+int sbx_reset(sbx_handle h, float* obs, float* reward, int32_t* step_type, float* discount, void* stream) {
+  if (!h) return fail(h, SBX_E_INVALID, "null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return do_reset(h, obs, reward, step_type, discount, (cudaStream_t)stream);
+}
+
+int sbx_step(sbx_handle h, const float* action, float* obs, float* reward, int32_t* step_type,
+             float* discount, void* stream) {
+  if (!h) return fail(h, SBX_E_INVALID, "null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  return do_step(h, action, obs, reward, step_type, discount, (cudaStream_t)stream);
+}
+
+static int copy_out(sbx_handle h, float* obs, float* reward, int32_t* step_type, float* discount) {
+  const size_t B = h->cfg.n_envs;
+  cudaStream_t st = h->stream;
+  // pinned staging keeps the copies asynchronous DMA; one sync at the end
+  if (obs) CUDA_TRY(h, cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * B * h->D, cudaMemcpyDeviceToHost, st));
+  if (reward) CUDA_TRY(h, cudaMemcpyAsync(h->h_reward, h->d_reward, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+  if (step_type) CUDA_TRY(h, cudaMemcpyAsync(h->h_step_type, h->d_step_type, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
+  if (discount) CUDA_TRY(h, cudaMemcpyAsync(h->h_discount, h->d_discount, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  if (obs) memcpy(obs, h->h_obs, sizeof(float) * B * h->D);
+  if (reward) memcpy(reward, h->h_reward, sizeof(float) * B);
+  if (step_type) memcpy(step_type, h->h_step_type, sizeof(int32_t) * B);
+  if (discount) memcpy(discount, h->h_discount, sizeof(float) * B);
+  return SBX_OK;
+}
+
+int sbx_reset_host(sbx_handle h, float* obs, float* reward, int32_t* step_type, float* discount) {
+  if (!h) return fail(h, SBX_E_INVALID, "null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  if (int rc = do_reset(h, h->d_obs, h->d_reward, h->d_step_type, h->d_discount, h->stream)) return rc;
+  return copy_out(h, obs, reward, step_type, discount);
+}
+
+int sbx_step_host(sbx_handle h, const float* action, float* obs, float* reward, int32_t* step_type,
+                  float* discount) {
+  if (!h) return fail(h, SBX_E_INVALID, "null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t B = h->cfg.n_envs;
+  const int A = h->cfg.n_actions;
+  if (A > 0) {
+    if (!action) return fail(h, SBX_E_INVALID, "action is NULL");
+    memcpy(h->h_action, action, sizeof(float) * B * A);
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_action, h->h_action, sizeof(float) * B * A, cudaMemcpyHostToDevice, h->stream));
+  }
+  if (int rc = do_step(h, h->d_action, h->d_obs, h->d_reward, h->d_step_type, h->d_discount, h->stream)) return rc;
+  return copy_out(h, obs, reward, step_type, discount);
+}
+
+int sbx_fd_step(sbx_handle h, const double* ambient, const double* convection) {
+  if (!h || !ambient || !convection) return fail(h, SBX_E_INVALID, "null argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  const size_t B = h->cfg.n_envs;
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  CUDA_TRY(h, cudaMemcpy(h->fd_ambient, ambient, sizeof(double) * B, cudaMemcpyHostToDevice));
+  CUDA_TRY(h, cudaMemcpy(h->fd_convection, convection, sizeof(double) * B, cudaMemcpyHostToDevice));
+  Params& p = h->P;
+  p.fd_only = 1;
+  p.time_index = 0;
+  p.action = nullptr; p.obs = nullptr; p.reward = nullptr; p.step_type = nullptr; p.discount_out = nullptr;
+  int rc;
+  if (h->path == SBX_PATH_RESIDENT) rc = run_resident(h, h->stream);
+  else rc = run_stream_sweeps(h, h->stream);
+  p.fd_only = 0;
+  if (rc) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SBX_OK;
+}
+
+int sbx_sync(sbx_handle h) {
+  if (!h) return fail(h, SBX_E_INVALID, "null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  return SBX_OK;
+}
+
+}  // extern "C"

@@ -1,0 +1,650 @@
+// Device-side building blocks of libsbx: the per-CV Jacobi update and the
+// per-building HVAC / observation / reward algebra.
+//
+// Arithmetic contract
+//   * The diffusion update reproduces TFSimulator.update_temperature_estimates
+//     (/root/reference/smart_control/simulator/tf_simulator.py:757-853) with the
+//     SAME fp32 operation order, one IEEE rounding per op, no FMA contraction
+//     (__fmul_rn/__fadd_rn/__fdiv_rn and -fmad=false), so the temperature field
+//     is bit-identical to the reference's eager-TF arithmetic.  Terms that are
+//     exactly +0 for a class (0 conductivity / 0 convection on a side) are
+//     skipped only where x + 0 == x makes that exact.
+//   * Device scalars (thermostat, VAV, AHU, boiler, reward, normalisation) are
+//     evaluated in fp64 like the reference's Python floats, and rounded to fp32
+//     at the points where the reference stores them in proto `float` fields.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/sbx.h"
+
+namespace sbx {
+
+constexpr int kNumMaterials = 3;
+constexpr int kNumCombos = SBX_CV_NUM_CLASSES * kNumMaterials;
+constexpr int kMaxZones = 255;
+
+// thermostat modes (thermostat.py:63-66)
+constexpr int kOff = 0, kHeat = 1, kCool = 2, kPassiveCool = 3;
+
+constexpr double kAirHeatCapacity = 1006.0;    // utils/constants.py:21
+constexpr double kWaterHeatCapacity = 4180.0;  // utils/constants.py:22
+constexpr double kWaterDensity = 1000.0;       // utils/constants.py:46
+constexpr double kGravity = 9.8;               // utils/constants.py:47
+
+// Coefficients of one (class, material) combination; tf_simulator.py:791-798,
+// 669-690.  k1 pairs with T(i,j+1), k3 with T(i,j-1) (shift semantics of
+// tf_simulator.py:459-472, 636-640), k2 with T(i+1,j), k4 with T(i-1,j).
+struct Combo {
+  float k1, k3, k2, k4;
+  float hl_t, hr_t, hb_t, ha_t;  // T_inf * h on the left/right/bottom/top side
+  float vz, uz, den, cm;         // cm = ((((rho*U)*V)*c)*z)*c
+};
+
+// Everything a kernel needs; passed by value.
+struct Params {
+  // sizes
+  int B, H, W, Z, n_plans, n_weather, n_reset, n_occ_zones, T_rows;
+  int obs_mode, D, n_actions;
+  int action_target[SBX_MAX_ACTIONS];
+  float action_min[SBX_MAX_ACTIONS], action_range[SBX_MAX_ACTIONS];
+  int n_hist_bins[3];
+  // physics
+  float dt, z, threshold;
+  int iteration_limit;
+  // schedule
+  double comfort_heat, comfort_cool, eco_heat, eco_cool;
+  // devices
+  double ahu_r, ahu_init_heat, ahu_init_cool, ahu_dp, ahu_eff, ahu_max_flow;
+  double boiler_init_sp, boiler_head, boiler_eff, boiler_heat_rate, boiler_cool_rate;
+  double boiler_diss_factor;  // L*2*pi / (ln(r2/r1)/k_ins + 1/(h*r2))  boiler.py:309-320
+  double boiler_capacity;
+  double vav_max_flow, vav_max_reheat;
+  // reward
+  double pmax, pmin, emax, gmax, delta, stiff, wu, wv, ww, gas_carbon;
+  double discount, occ_norm;
+  // static per plan
+  const uint16_t* desc;      // [P,H,W]
+  const double* material;    // [P,3,3]
+  const double* cv_size;     // [P]
+  const int32_t* zone_ncv;   // [P,Z]
+  const int32_t* zone_ndiff; // [P,Z]
+  const int32_t* obs_zone_order;  // [P,Z]
+  const float* reset_temps;  // [n_reset,H,W]
+  const float* initial_temp; // [B]
+  // tables
+  const double* ambient;     // [Wn,T]
+  const double* convection;  // [Wn]
+  const uint8_t* comfort;    // [T]
+  const uint8_t* comfort_soon;
+  const double* occ_reward;  // [T,Zo]
+  const int32_t* occ_obs;    // [T]
+  const double* price_e;
+  const double* carbon_e;
+  const double* price_g;
+  const double* time_feat;   // [T,4]
+  const double* obs_mean;    // [15]
+  const double* obs_inv_std; // unused slot kept for layout clarity
+  const double* obs_var;     // [15]
+  const double* hist_bins;   // [3,SBX_MAX_HIST_BINS]
+  // state
+  float* tbuf[3];
+  uint8_t* cur;              // [B] which tbuf holds building.temp
+  float* zone_mean;          // [B,Z]
+  float* global_mean;        // [B]
+  float* qcv;                // [B,Z] heat per diffuser CV used by THIS step's solve
+  float* qcv_next;           // [B,Z] produced by this step's VAV outputs
+  uint8_t* therm_mode;       // [B,Z]
+  double* ahu_heat_sp;
+  double* ahu_cool_sp;
+  double* boiler_sp;
+  double* boiler_tank;       // [B,3]
+  // transients / diagnostics
+  float* pre_zone_mean;      // [B,Z]
+  double* diag;              // [B,SBX_DIAG_N]
+  double* q_zone;            // [B,Z]
+  double* zone_supply;       // [B,Z]
+  int32_t* n_sweeps;         // [B]
+  uint32_t* max_delta_bits;  // [B] fp32 bits of the running max (non-negative => uint order)
+  float* max_delta;          // [B] last completed sweep's max
+  double* zone_sum;          // [B,Z+1] streaming path; slot Z = whole grid
+  uint8_t* active;           // [B]
+  int32_t* n_active;         // [1]
+  unsigned long long* sweeps_total;  // [1]
+  // sbx_fd_step: solve only, ambient / convection given per env
+  int fd_only;
+  const double* fd_ambient;     // [B]
+  const double* fd_convection;  // [B]
+  // per call
+  int time_index;            // s: this step simulates [t_s, t_s + dt)
+  int step_count;
+  int episode_steps;
+  int therm_seen, prev_comfort;
+  const float* action;       // [B,A]
+  float* obs;                // [B,D]
+  float* reward;
+  int32_t* step_type;
+  float* discount_out;
+};
+
+__device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+__device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+__device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
+
+__device__ __forceinline__ int desc_class(uint32_t d) { return d & SBX_DESC_CLASS_MASK; }
+__device__ __forceinline__ int desc_material(uint32_t d) { return (d >> SBX_DESC_MATERIAL_SHIFT) & 3; }
+__device__ __forceinline__ int desc_zone(uint32_t d) { return (d >> SBX_DESC_ZONE_SHIFT) & 0xFF; }
+
+// Builds the coefficient set of one (class, material); every line mirrors one
+// TF op of tf_simulator.py (line numbers in comments).
+__device__ inline Combo make_combo(int cls, const double* mat /*k,c,rho*/, double dx,
+                                   float z, float dt, float h, float t_inf) {
+  // get_cv_dimension_tensors :304-321 -- fp64 product stored to an fp32 array
+  double hs = 1.0, vs = 1.0;
+  bool sl = false, sr = false, st = false, sb = false;
+  switch (cls) {
+    case SBX_CV_EDGE_TOP: vs = 0.5; st = true; break;
+    case SBX_CV_EDGE_BOTTOM: vs = 0.5; sb = true; break;
+    case SBX_CV_EDGE_LEFT: hs = 0.5; sl = true; break;
+    case SBX_CV_EDGE_RIGHT: hs = 0.5; sr = true; break;
+    case SBX_CV_CORNER_TL: hs = vs = 0.5; st = sl = true; break;
+    case SBX_CV_CORNER_TR: hs = vs = 0.5; st = sr = true; break;
+    case SBX_CV_CORNER_BL: hs = vs = 0.5; sb = sl = true; break;
+    case SBX_CV_CORNER_BR: hs = vs = 0.5; sb = sr = true; break;
+    default: break;
+  }
+  const float u = (float)(dx * hs);
+  const float v = (float)(dx * vs);
+  const float kf = (float)mat[0];
+  const float c = (float)mat[1];
+  const float rho = (float)mat[2];
+  const float kl = sl ? 0.f : kf, kr = sr ? 0.f : kf;   // :421-450
+  const float kt = st ? 0.f : kf, kb = sb ? 0.f : kf;
+  const float hl = sl ? h : 0.f, hr = sr ? h : 0.f;     // :354-392
+  const float ht = st ? h : 0.f, hb = sb ? h : 0.f;
+  Combo o;
+  o.uz = mul(z, u);                                     // :791
+  o.vz = mul(z, v);                                     // :792
+  o.k1 = fdiv(kl, u);                                   // :795
+  o.k3 = fdiv(kr, u);                                   // :796
+  o.k2 = fdiv(kb, v);                                   // :797
+  o.k4 = fdiv(kt, v);                                   // :798
+  float d1 = add(o.k1, o.k3);                           // :669
+  d1 = add(d1, hl);                                     // :670
+  d1 = add(d1, hr);                                     // :671
+  d1 = mul(o.vz, d1);                                   // :672
+  float d2 = add(o.k2, o.k4);                           // :675
+  d2 = add(d2, hb);                                     // :676
+  d2 = add(d2, ht);                                     // :677
+  d2 = mul(o.uz, d2);                                   // :678
+  float d3 = mul(rho, u);                               // :681
+  d3 = mul(d3, v);                                      // :682
+  d3 = mul(d3, c);                                      // :683
+  d3 = mul(z, d3);                                      // :684
+  d3 = mul(d3, c);                                      // :685
+  o.cm = d3;
+  d3 = fdiv(d3, dt);                                    // :686
+  o.den = add(add(d1, d2), d3);                         // :689-690
+  o.hl_t = mul(t_inf, hl);                              // :725
+  o.hr_t = mul(t_inf, hr);                              // :726
+  o.ha_t = mul(t_inf, ht);                              // :727
+  o.hb_t = mul(t_inf, hb);                              // :728
+  return o;
+}
+
+// Fills `tab[kNumCombos]` (shared memory) cooperatively.
+__device__ inline void build_combo_table(Combo* tab, const Params& p, int plan, int b,
+                                         float h, float t_inf, int tid, int nthreads) {
+  const double* mat = p.material + (size_t)plan * 9;
+  const double dx = p.cv_size[plan];
+  for (int i = tid; i < kNumCombos; i += nthreads) {
+    const int cls = i / kNumMaterials, m = i % kNumMaterials;
+    tab[i] = make_combo(cls, mat + m * 3, dx, p.z, p.dt, h, t_inf);
+  }
+}
+
+// Interior-class coefficients of the three materials, kept in registers.
+struct Fast {
+  float kq[kNumMaterials], den[kNumMaterials], cm[kNumMaterials];
+  float vz;
+};
+
+__device__ inline Fast load_fast(const Combo* tab) {
+  Fast f;
+#pragma unroll
+  for (int m = 0; m < kNumMaterials; ++m) {
+    const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + m];
+    f.kq[m] = c.k1;
+    f.den[m] = c.den;
+    f.cm[m] = c.cm;
+  }
+  f.vz = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
+  return f;
+}
+
+__device__ __forceinline__ float sel3(const float (&a)[kNumMaterials], int m) {
+  return m == 0 ? a[0] : (m == 1 ? a[1] : a[2]);
+}
+
+// thermal-mass coefficient cm of a CV (for the n3 term)
+__device__ __forceinline__ float cv_cm(uint32_t d, const Combo* tab, const Fast& f) {
+  const int cls = desc_class(d), m = desc_material(d);
+  return cls == SBX_CV_INTERIOR ? sel3(f.cm, m) : tab[cls * kNumMaterials + m].cm;
+}
+
+// One CV update (tf_simulator.py:719-754, 843, 847-849).
+//   t_jp = T(i,j+1), t_jm = T(i,j-1), t_im = T(i-1,j), t_ip = T(i+1,j)
+//   n3 = ((cm * T_prev) / dt)   precomputed (:743-749)
+//   q  = input_q at this CV (0 unless it is a diffuser)
+__device__ __forceinline__ float cv_update(uint32_t d, float t_jp, float t_jm, float t_im,
+                                           float t_ip, float n3, float q, float t_inf,
+                                           const Combo* tab, const Fast& f) {
+  const int cls = desc_class(d);
+  const int m = desc_material(d);
+  if (cls == SBX_CV_INTERIOR) {
+    const float kq = sel3(f.kq, m);
+    // (((k1*Tl)+(k3*Tr))+0)+0 ; the h terms are exactly +0 for this class
+    float n1 = add(mul(kq, t_jp), mul(kq, t_jm));       // :719-720, 731
+    n1 = mul(f.vz, n1);                                 // :734
+    float n2 = add(mul(kq, t_ip), mul(kq, t_im));       // :721-722, 737
+    n2 = mul(f.vz, n2);                                 // :740 (uz == vz for interior)
+    float num = add(add(add(n1, n2), n3), q);           // :752-754
+    return fdiv(num, sel3(f.den, m));                   // :843
+  }
+  if (cls == SBX_CV_EXTERIOR) return t_inf;             // :847-849
+  const Combo c = tab[cls * kNumMaterials + m];
+  float n1 = add(mul(c.k1, t_jp), mul(c.k3, t_jm));
+  n1 = add(n1, c.hl_t);                                 // :732
+  n1 = add(n1, c.hr_t);                                 // :733
+  n1 = mul(c.vz, n1);
+  float n2 = add(mul(c.k2, t_ip), mul(c.k4, t_im));
+  n2 = add(n2, c.hb_t);                                 // :738
+  n2 = add(n2, c.ha_t);                                 // :739
+  n2 = mul(c.uz, n2);
+  float num = add(add(add(n1, n2), n3), q);
+  return fdiv(num, c.den);
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// ---------------------------------------------------------------------------
+// HVAC / observation / reward: executed by ONE WARP per building, lanes over
+// zones for the per-zone algebra, lane 0 for the sequential device sums (the
+// reference accumulates zone by zone in dict order, simulator_flexible_floor_plan.py:165-183).
+// `sh` is per-building scratch in shared memory: 3*Z + 64 doubles.
+// ---------------------------------------------------------------------------
+
+struct PreOut {
+  double supply_air, ahu_flow, boiler_flow, return_water;
+  int ahu_count, boiler_count;
+  double ahu_heat_sp, ahu_cool_sp, boiler_sp;
+};
+
+__device__ inline double f32r(double v) { return (double)(float)v; }
+
+// AirHandler.get_supply_air_temp air_handler.py:204-233
+__device__ inline double mixed_air(const Params& p, double recirc, double amb) {
+  return p.ahu_r * recirc + (1 - p.ahu_r) * amb;
+}
+__device__ inline double supply_air(double mixed, double heat_sp, double cool_sp) {
+  if (mixed > cool_sp) return cool_sp;
+  if (mixed < heat_sp) return heat_sp;
+  return mixed;
+}
+
+// setup_step_sim + set_action + the VAV/AHU/boiler part of execute_step_sim.
+// Everything here depends only on PRE-step temperatures (Q4/Q5 of SURVEY.md
+// Appendix B), so it runs before the diffusion solve.
+__device__ inline PreOut hvac_pre(const Params& p, int b, int plan, int lane,
+                                  const float* zone_mean /*[Z] pre-step*/, float global_mean,
+                                  double* sh /*3*Z*/) {
+  const int Z = p.Z;
+  const int s = p.time_index;
+  const bool comfort_now = p.comfort[s] != 0;
+  const double w_heat = comfort_now ? p.comfort_heat : p.eco_heat;
+  const double w_cool = comfort_now ? p.comfort_cool : p.eco_cool;
+  const int32_t* ncv = p.zone_ncv + (size_t)plan * Z;
+  const int32_t* ndiff = p.zone_ndiff + (size_t)plan * Z;
+
+  // --- actions: BoundedActionNormalizer.setpoint_value in fp32 (NumPy weak
+  // scalar promotion keeps the np.float32 action's dtype), then proto float.
+  double heat_sp = p.ahu_heat_sp[b], cool_sp = p.ahu_cool_sp[b], boiler_sp = p.boiler_sp[b];
+  // thermostats run BEFORE the action is applied (simulator_building.py:209)
+  // but do not read any action-settable attribute, so order is immaterial here.
+  for (int i = 0; i < p.n_actions; ++i) {
+    const float a = p.action[(size_t)b * p.n_actions + i];
+    const float ratio = fdiv(add(a, 1.0f), 2.0f);       // bounded_action_normalizer.py:93-94
+    const float v = add(mul(ratio, p.action_range[i]), p.action_min[i]);  // :97-98
+    const int tgt = p.action_target[i];
+    if (tgt == SBX_ACT_BOILER_SETPOINT) boiler_sp = (double)v;
+    else if (tgt == SBX_ACT_AHU_COOLING_SETPOINT) cool_sp = (double)v;
+    else heat_sp = (double)v;
+  }
+
+  const double amb = p.ambient[(size_t)(p.n_weather == 1 ? 0 : b) * p.T_rows + s];
+  const double mixed = mixed_air(p, (double)global_mean, amb);
+  const double sup = supply_air(mixed, heat_sp, cool_sp);
+
+  double* sh_flow = sh;
+  double* sh_reheat = sh + Z;
+  double* sh_zs = sh + 2 * Z;
+  for (int zi = lane; zi < Z; zi += 32) {
+    double flow = 0, reheat = 0, zs = 0;
+    if (ncv[zi] > 0) {
+      const double zt = (double)zone_mean[zi];
+      int mode = p.therm_mode[(size_t)b * Z + zi];
+      // Thermostat.update thermostat.py:114-148
+      const double mid = 0.5 * (w_cool - w_heat) + w_heat;
+      auto default_control = [&](int m) {               // :76-112
+        if (zt < w_heat) return kHeat;
+        if (zt > w_cool) return kCool;
+        if (zt < mid && m == kHeat) return kHeat;
+        if (zt > mid && m == kCool) return kCool;
+        return kOff;
+      };
+      if (comfort_now) mode = default_control(mode);
+      else if (p.therm_seen && p.prev_comfort) mode = kPassiveCool;
+      else if (mode == kPassiveCool && zt > w_heat) mode = kPassiveCool;
+      else mode = default_control(mode);
+      p.therm_mode[(size_t)b * Z + zi] = (uint8_t)mode;
+      // Vav.update_settings vav.py:230-243
+      const double damper = (mode == kHeat || mode == kCool) ? 1.0 : 0.1;
+      const double valve = (mode == kHeat) ? 1.0 : 0.0;
+      // Vav.output vav.py:168-217, 245-264 (input water = boiler SETPOINT)
+      reheat = valve * p.vav_max_reheat;
+      flow = damper * p.vav_max_flow;
+      const double heat_diff = kAirHeatCapacity * flow - kWaterHeatCapacity * reheat;
+      const double water_heat = boiler_sp * kWaterHeatCapacity * reheat;
+      zs = (sup * heat_diff + water_heat) / flow / kAirHeatCapacity;
+      const double q = flow * kAirHeatCapacity * (zs - zt);
+      p.q_zone[(size_t)b * Z + zi] = q;
+      p.zone_supply[(size_t)b * Z + zi] = zs;
+      // apply_thermal_power_zone building.py:873-889: power * (1/n_diffusers)
+      const int nd = ndiff[zi];
+      p.qcv_next[(size_t)b * Z + zi] = nd > 0 ? (float)(q * (1.0 / (double)nd)) : 0.f;
+      sh_zs[zi] = valve;  // stash valve; zs kept in zone_supply
+    } else {
+      p.qcv_next[(size_t)b * Z + zi] = 0.f;
+      p.q_zone[(size_t)b * Z + zi] = 0.0;
+      p.zone_supply[(size_t)b * Z + zi] = 0.0;
+      sh_zs[zi] = 0.0;
+    }
+    sh_flow[zi] = flow;
+    sh_reheat[zi] = reheat;
+    p.pre_zone_mean[(size_t)b * Z + zi] = zone_mean[zi];
+  }
+  __syncwarp();
+  PreOut o;
+  o.supply_air = sup;
+  o.ahu_heat_sp = heat_sp;
+  o.ahu_cool_sp = cool_sp;
+  o.boiler_sp = boiler_sp;
+  o.ahu_flow = 0; o.boiler_flow = 0; o.return_water = 0; o.ahu_count = 0; o.boiler_count = 0;
+  if (lane == 0) {
+    double af = 0, bf = 0, num = 0, den = 0;
+    int ac = 0, bc = 0;
+    for (int zi = 0; zi < Z; ++zi) {
+      if (ncv[zi] <= 0) continue;
+      if (sh_flow[zi] > 0) {                            // air_handler.py:254-268
+        af += sh_flow[zi];
+        if (af > p.ahu_max_flow) af = p.ahu_max_flow;
+        ++ac;
+      }
+      if (sh_reheat[zi] > 0) { bf += sh_reheat[zi]; ++bc; }  // boiler.py:219-231
+      const double valve = sh_zs[zi];                   // simulator.py:373-381
+      num += valve * p.zone_supply[(size_t)b * Z + zi];
+      den += valve;
+    }
+    o.ahu_flow = af; o.boiler_flow = bf; o.ahu_count = ac; o.boiler_count = bc;
+    o.return_water = num / (den + 1e-6);
+    p.ahu_heat_sp[b] = heat_sp;
+    p.ahu_cool_sp[b] = cool_sp;
+    p.boiler_sp[b] = boiler_sp;
+    double* dg = p.diag + (size_t)b * SBX_DIAG_N;
+    dg[SBX_DIAG_SUPPLY_AIR_TEMP] = sup;
+    dg[SBX_DIAG_AHU_FLOW] = af;
+    dg[SBX_DIAG_BOILER_FLOW] = bf;
+    dg[SBX_DIAG_RETURN_WATER] = o.return_water;
+  }
+  // broadcast lane 0's sums
+  o.ahu_flow = __shfl_sync(0xffffffffu, o.ahu_flow, 0);
+  o.boiler_flow = __shfl_sync(0xffffffffu, o.boiler_flow, 0);
+  o.return_water = __shfl_sync(0xffffffffu, o.return_water, 0);
+  o.ahu_count = __shfl_sync(0xffffffffu, o.ahu_count, 0);
+  o.boiler_count = __shfl_sync(0xffffffffu, o.boiler_count, 0);
+  __syncwarp();
+  return o;
+}
+
+// state carried from hvac_pre to hvac_post through global memory in the
+// streaming path (the two run in different kernels there)
+struct Carry {
+  double ahu_flow, boiler_flow, return_water;
+  int ahu_count, boiler_count;
+};
+
+// StandardScoreObservationNormalizer._normalize_one observation_normalizer.py:68-92
+// on a proto-float value, result stored to a proto float again.
+__device__ inline float normalize(const Params& p, int field, double native) {
+  const double v = f32r(native);
+  const double var = p.obs_var[field];
+  if (var > 0.0) return (float)((v - p.obs_mean[field]) / sqrt(var));
+  return 0.f;
+}
+
+// Observation pack + reward.  `post_zone_mean` / `post_global_mean` are the
+// fresh (post-solve) means; `is_reset` selects the restart TimeStep of
+// Environment._reset (environment.py:1165-1212).
+__device__ inline void hvac_post(const Params& p, int b, int plan, int lane, bool is_reset,
+                                 const float* pre_zone_mean, const float* post_zone_mean,
+                                 float post_global_mean, const Carry& cy, double* sh /*3*Z*/) {
+  const int Z = p.Z;
+  const int s1 = is_reset ? 0 : p.time_index + 1;   // timestamp index of the observation
+  const int32_t* ncv = p.zone_ncv + (size_t)plan * Z;
+  const double amb1 = p.ambient[(size_t)(p.n_weather == 1 ? 0 : b) * p.T_rows + s1];
+  const double heat_sp = p.ahu_heat_sp[b], cool_sp = p.ahu_cool_sp[b];
+  const double boiler_sp = p.boiler_sp[b];
+  float* obs = p.obs ? p.obs + (size_t)b * p.D : nullptr;
+
+  // ---- observation (environment.py:873-985) ----
+  // Boiler.supply_water_temperature_sensor is stateful (boiler.py:146-217) and is
+  // read BEFORE the reward is computed (environment.py:1297-1306).
+  double tank = p.boiler_tank[(size_t)b * 3 + 0];
+  double tank_dt = p.boiler_tank[(size_t)b * 3 + 1];
+  double last_dur = p.boiler_tank[(size_t)b * 3 + 2];
+  if (lane == 0) {
+    if (is_reset) {
+      // after Boiler.reset(): temperature == setpoint, so _adjust_temperature is
+      // the identity whatever the (possibly negative) duration is.
+      tank = boiler_sp; tank_dt = 0.0; last_dur = 0.0;
+    } else {
+      last_dur = (double)p.dt;                          // obs_ts - action_ts
+      if (p.boiler_cool_rate > 0.0 && p.boiler_heat_rate > 0.0) {
+        const double begin = tank;
+        if (boiler_sp > begin) tank = fmin(begin + p.boiler_heat_rate * last_dur / 60.0, boiler_sp);
+        else if (boiler_sp < begin) tank = fmax(begin - p.boiler_cool_rate * last_dur / 60.0, boiler_sp);
+        else tank = boiler_sp;
+        tank_dt = tank - begin;
+      } else {
+        tank = boiler_sp;
+      }
+    }
+    p.boiler_tank[(size_t)b * 3 + 0] = tank;
+    p.boiler_tank[(size_t)b * 3 + 1] = tank_dt;
+    p.boiler_tank[(size_t)b * 3 + 2] = last_dur;
+    if (obs) {
+      const double fan_pct = cy.ahu_flow / p.ahu_max_flow;    // air_handler.py:246-248
+      obs[0] = normalize(p, 0, (double)cy.ahu_count);         // cooling_request_count
+      obs[1] = normalize(p, 1, p.ahu_dp);                     // differential_pressure_setpoint
+      obs[2] = normalize(p, 2, fan_pct);                      // discharge_fan_speed_percentage_command
+      obs[3] = normalize(p, 3, (1.0 - p.ahu_r) * cy.ahu_flow);  // outside_air_flowrate_sensor
+      obs[4] = normalize(p, 4, amb1);                         // outside_air_temperature_sensor
+      obs[5] = normalize(p, 5, cool_sp);
+      obs[6] = normalize(p, 6, cy.ahu_flow);                  // supply_air_flowrate_sensor
+      obs[7] = normalize(p, 7, heat_sp);
+      obs[8] = normalize(p, 8, fan_pct);                      // supply_fan_speed_percentage_command
+      obs[9] = normalize(p, 9, (double)cy.boiler_count);      // heating_request_count
+      obs[10] = normalize(p, 10, boiler_sp);                  // supply_water_setpoint
+      obs[11] = normalize(p, 11, tank);                       // supply_water_temperature_sensor
+    }
+  }
+  // per-VAV fields: damper, flow setpoint, cached zone temperature (vav.py:54-64;
+  // the cached temperature is the PRE-step mean, 0 after reset -- SURVEY Q4/Q25)
+  int n_hist_total = 0;
+  if (obs) {
+    if (p.obs_mode == SBX_OBS_RAW) {
+      const int32_t* order = p.obs_zone_order + (size_t)plan * Z;
+      for (int slot = lane; slot < Z; slot += 32) {
+        const int zi = order[slot];
+        float v0 = 0.f, v1 = 0.f, v2 = 0.f;
+        if (zi >= 0 && ncv[zi] > 0) {
+          double damper = 0.1, ztemp = 0.0;
+          if (!is_reset) {
+            const int mode = p.therm_mode[(size_t)b * Z + zi];
+            damper = (mode == kHeat || mode == kCool) ? 1.0 : 0.1;
+            ztemp = (double)pre_zone_mean[zi];
+          }
+          v0 = normalize(p, 12, damper);
+          v1 = normalize(p, 13, p.vav_max_flow);
+          v2 = normalize(p, 14, ztemp);
+        }
+        obs[12 + slot * 3 + 0] = v0;
+        obs[12 + slot * 3 + 1] = v1;
+        obs[12 + slot * 3 + 2] = v2;
+      }
+      n_hist_total = 3 * Z;
+    } else {
+      // HistogramReducer (histogram_reducer.py:136-146, 411-433): clip to the bin
+      // range, np.histogram with the last edge duplicated, divide by the count.
+      // Lanes cooperate per measurement through shared counters.
+      float* cnt = reinterpret_cast<float*>(sh + 3 * Z);  // 64 doubles = room for 3*SBX_MAX_HIST_BINS floats
+      const int total_bins = p.n_hist_bins[0] + p.n_hist_bins[1] + p.n_hist_bins[2];
+      for (int i = lane; i < total_bins; i += 32) cnt[i] = 0.f;
+      __syncwarp();
+      int base = 0;
+      float nz = 0.f;
+      for (int f = 0; f < 3; ++f) {
+        const int nb = p.n_hist_bins[f];
+        const double* bins = p.hist_bins + f * SBX_MAX_HIST_BINS;
+        for (int zi = lane; zi < Z; zi += 32) {
+          if (ncv[zi] <= 0) continue;
+          double native;
+          if (f == 0) {
+            int mode = p.therm_mode[(size_t)b * Z + zi];
+            native = is_reset ? 0.1 : ((mode == kHeat || mode == kCool) ? 1.0 : 0.1);
+          } else if (f == 1) {
+            native = p.vav_max_flow;
+          } else {
+            native = is_reset ? 0.0 : (double)pre_zone_mean[zi];
+          }
+          double v = (double)normalize(p, 12 + f, native);
+          v = fmin(fmax(v, bins[0]), bins[nb - 1]);
+          int k = 0;  // number of edges <= v, minus 1
+          for (int e = 1; e < nb; ++e) k += (bins[e] <= v) ? 1 : 0;
+          atomicAdd(&cnt[base + k], 1.0f);
+          if (f == 0) nz += 1.f;
+        }
+        base += nb;
+      }
+      __syncwarp();
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
+      for (int i = lane; i < total_bins; i += 32) obs[12 + i] = fdiv(cnt[i], nz);
+      __syncwarp();
+      n_hist_total = total_bins;
+    }
+    if (lane == 0) {
+      float* o = obs + 12 + n_hist_total;
+      const double* tf = p.time_feat + (size_t)s1 * 4;
+      o[0] = (float)tf[0]; o[1] = (float)tf[1]; o[2] = (float)tf[2]; o[3] = (float)tf[3];
+      o[4] = (float)p.comfort[s1];
+      o[5] = (float)p.comfort_soon[s1];
+      o[6] = (float)(((double)p.occ_obs[s1] - p.occ_norm) / (p.occ_norm + 1));  // environment.py:952-956
+    }
+  }
+  if (is_reset) {
+    if (lane == 0) {
+      if (p.reward) p.reward[b] = 0.f;
+      if (p.step_type) p.step_type[b] = SBX_STEP_FIRST;
+      if (p.discount_out) p.discount_out[b] = 1.f;
+    }
+    return;
+  }
+
+  // ---- reward (setpoint_energy_carbon_regret.py:142-291) ----
+  const bool comfort1 = p.comfort[s1] != 0;
+  const double w_heat = f32r(comfort1 ? p.comfort_heat : p.eco_heat);
+  const double w_cool = f32r(comfort1 ? p.comfort_cool : p.eco_cool);
+  const double dts = (double)p.dt;
+  double prod = 0.0, occ_sum = 0.0;
+  for (int zi = lane; zi < Z; zi += 32) {
+    if (ncv[zi] <= 0) continue;
+    const double occ = f32r(p.occ_reward[(size_t)s1 * p.n_occ_zones + (p.n_occ_zones == 1 ? 0 : zi)]);
+    const double t = (double)post_zone_mean[zi];
+    const double x0low = w_heat - p.delta, x0high = w_cool + p.delta;
+    double pr;                                          // base:83-123
+    if (t < w_heat) pr = p.pmax / (1.0 + exp(-p.stiff * (t - x0low)));
+    else if (t > w_cool) pr = p.pmax * (1.0 - 1.0 / (1.0 + exp(-p.stiff * (t - x0high))));
+    else pr = p.pmax;
+    prod += pr * occ * dts / 3600.0;
+    occ_sum += occ;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    prod += __shfl_xor_sync(0xffffffffu, prod, o);
+    occ_sum += __shfl_xor_sync(0xffffffffu, occ_sum, o);
+  }
+  if (lane == 0) {
+    // RewardInfo (simulator_flexible_floor_plan.py:238-283), each field -> proto float
+    const double blower = f32r(cy.ahu_flow * p.ahu_dp / p.ahu_eff
+                               + cy.ahu_flow * (1.0 - p.ahu_r) * p.ahu_dp / p.ahu_eff);
+    const double mixed1 = mixed_air(p, (double)post_global_mean, amb1);
+    const double sup1 = supply_air(mixed1, heat_sp, cool_sp);
+    const double ac = f32r(cy.ahu_flow * kAirHeatCapacity * (sup1 - mixed1));
+    const double rw = cy.return_water;
+    const double sw = boiler_sp > rw ? boiler_sp : rw;  // boiler.py:244-250
+    double gas = kWaterHeatCapacity * cy.boiler_flow * (sw - rw);
+    gas += p.boiler_diss_factor * (sw - amb1);          // boiler.py:275-320
+    if (last_dur > 0) gas += kWaterHeatCapacity * p.boiler_capacity * tank_dt / last_dur;
+    gas = f32r(gas);
+    const double pump = f32r(cy.boiler_flow * kWaterDensity * kGravity * p.boiler_head / p.boiler_eff);
+
+    const double max_p = p.pmax * occ_sum * dts / 3600.0;
+    const double min_p = p.pmin * occ_sum * dts / 3600.0;
+    const double actual = fmax(prod, min_p);
+    const double regret = occ_sum > 0.0 ? (actual - min_p) / (max_p - min_p) - 1.0 : 0.0;
+    const double e_rate = fmin(blower + fabs(ac) + pump, p.emax);
+    const double g_rate = fmin(gas, p.gmax);
+    const double pe = p.price_e[s1], ce = p.carbon_e[s1], pg = p.price_g[s1];
+    const double cost_e = pe * fabs(e_rate) * dts, cost_e_max = pe * fabs(p.emax) * dts;
+    const double carb_e = ce * fabs(e_rate) * dts, carb_e_max = ce * fabs(p.emax) * dts;
+    const double g_pos = g_rate < 0.0 ? 0.0 : g_rate;
+    const double cost_g = pg * (g_pos * dts), cost_g_max = pg * (p.gmax * dts);
+    const double carb_g = p.gas_carbon * (g_pos * dts), carb_g_max = p.gas_carbon * (p.gmax * dts);
+    const double n_cost = (cost_e + cost_g) / (cost_e_max + cost_g_max);
+    const double n_carbon = (carb_e + carb_g) / (carb_e_max + carb_g_max);
+    const double raw = regret * p.wu - n_cost * p.wv - n_carbon * p.ww;
+    const float value = (float)(raw / (p.wu + p.wv + p.ww));
+    const bool ended = p.step_count >= p.episode_steps;  // environment.py:1365-1368
+    if (p.reward) p.reward[b] = value;
+    if (p.step_type) p.step_type[b] = ended ? SBX_STEP_LAST : SBX_STEP_MID;
+    if (p.discount_out) p.discount_out[b] = ended ? 0.f : (float)p.discount;
+    double* dg = p.diag + (size_t)b * SBX_DIAG_N;
+    dg[SBX_DIAG_BLOWER_W] = blower;
+    dg[SBX_DIAG_AC_W] = ac;
+    dg[SBX_DIAG_GAS_W] = gas;
+    dg[SBX_DIAG_PUMP_W] = pump;
+    dg[SBX_DIAG_REGRET] = regret;
+    dg[SBX_DIAG_NORM_COST] = n_cost;
+    dg[SBX_DIAG_NORM_CARBON] = n_carbon;
+    dg[SBX_DIAG_TOTAL_OCC] = occ_sum;
+    dg[SBX_DIAG_PRODUCTIVITY] = actual;
+  }
+}
+
+}  // namespace sbx

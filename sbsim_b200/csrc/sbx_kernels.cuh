@@ -1,0 +1,615 @@
+// Kernels of libsbx (sm_100a).
+//
+//  k_resident_step   one CTA per building, the whole env step in ONE launch:
+//                    TMA bulk load of the temperature grid + descriptor into
+//                    shared memory, HVAC prologue, Jacobi sweeps to convergence
+//                    entirely on chip, zone reductions, observation + reward
+//                    epilogue, TMA bulk store of the new grid.
+//  k_sweep           streaming path (grids that do not fit an SM, e.g. the
+//                    744x1004 calibrated plan): one Jacobi sweep per launch,
+//                    128-bit coalesced row loads, rolling 3-row register window,
+//                    horizontal neighbours by warp shuffle, per-building max|dT|.
+//  k_zone_reduce     segmented zone sums + whole-grid sum (fp64 accumulators).
+//  k_pre / k_post    HVAC prologue / observation+reward epilogue, warp per building.
+#pragma once
+
+#include "sbx_device.cuh"
+
+namespace sbx {
+
+constexpr int kResidentThreads = 512;
+constexpr int kStreamThreads = 256;
+constexpr int kStreamRowsPerWarp = 8;
+
+template <int V>
+struct Vec;
+template <>
+struct Vec<4> {
+  using F = float4;
+  using D = uint2;  // 4 x u16
+};
+template <>
+struct Vec<1> {
+  using F = float;
+  using D = uint16_t;
+};
+
+template <int V>
+__device__ __forceinline__ void load_f(const float* p, float (&o)[V]) {
+  if constexpr (V == 4) {
+    const float4 v = *reinterpret_cast<const float4*>(p);
+    o[0] = v.x; o[1] = v.y; o[2] = v.z; o[3] = v.w;
+  } else {
+    o[0] = *p;
+  }
+}
+template <int V>
+__device__ __forceinline__ void store_f(float* p, const float (&o)[V]) {
+  if constexpr (V == 4) {
+    *reinterpret_cast<float4*>(p) = make_float4(o[0], o[1], o[2], o[3]);
+  } else {
+    *p = o[0];
+  }
+}
+template <int V>
+__device__ __forceinline__ void load_d(const uint16_t* p, uint32_t (&o)[V]) {
+  if constexpr (V == 4) {
+    const uint2 v = *reinterpret_cast<const uint2*>(p);
+    o[0] = v.x & 0xFFFFu; o[1] = v.x >> 16; o[2] = v.y & 0xFFFFu; o[3] = v.y >> 16;
+  } else {
+    o[0] = *p;
+  }
+}
+template <int V>
+__device__ __forceinline__ void fill(float (&o)[V], float v) {
+#pragma unroll
+  for (int e = 0; e < V; ++e) o[e] = v;
+}
+
+__device__ __forceinline__ double env_ambient(const Params& p, int b, int s) {
+  return p.fd_only ? p.fd_ambient[b]
+                   : p.ambient[(size_t)(p.n_weather == 1 ? 0 : b) * p.T_rows + s];
+}
+__device__ __forceinline__ double env_convection(const Params& p, int b) {
+  return p.fd_only ? p.fd_convection[b] : p.convection[p.n_weather == 1 ? 0 : b];
+}
+
+// ---------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy helpers (cp.async.bulk -> SASS UBLKCP)
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t phase) {
+  uint32_t done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(phase)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src, uint32_t bytes,
+                                            uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+  asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_wait() {
+  asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+}
+
+// ---------------------------------------------------------------------------
+// resident path
+// ---------------------------------------------------------------------------
+
+struct ResidentLayout {
+  size_t off_a, off_b, off_n3, off_desc, off_tab, off_qcv, off_bins, off_scratch, off_wmax,
+      off_zpre, off_zpost, off_bar, total;
+};
+
+__host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z) {
+  ResidentLayout L;
+  auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  size_t o = 0;
+  L.off_a = o; o = al(o + (size_t)n_cv * 4);
+  L.off_b = o; o = al(o + (size_t)n_cv * 4);
+  L.off_n3 = o; o = al(o + (size_t)n_cv * 4);
+  L.off_desc = o; o = al(o + (size_t)n_cv * 2);
+  L.off_tab = o; o = al(o + sizeof(Combo) * kNumCombos);
+  L.off_qcv = o; o = al(o + (size_t)(Z + 1) * 4);
+  L.off_bins = o; o = al(o + (size_t)(Z + 1) * 8);
+  L.off_scratch = o; o = al(o + (size_t)(3 * Z + 64) * 8);
+  L.off_wmax = o; o = al(o + 2 * 32 * 4);
+  L.off_zpre = o; o = al(o + (size_t)Z * 4);
+  L.off_zpost = o; o = al(o + (size_t)Z * 4);
+  L.off_bar = o; o = al(o + 16);
+  L.total = o;
+  return L;
+}
+
+// Accumulates V consecutive CVs into per-zone shared bins (fp64) + grid total.
+template <int V>
+__device__ __forceinline__ void zone_accumulate(const float (&t)[V], const uint32_t (&d)[V],
+                                                double* bins, double& total) {
+  int z0 = desc_zone(d[0]);
+  double run = 0.0;
+#pragma unroll
+  for (int e = 0; e < V; ++e) {
+    const int z = desc_zone(d[e]);
+    total += (double)t[e];
+    if (z != z0) {
+      if (z0 != SBX_ZONE_NONE) atomicAdd(&bins[z0], run);
+      z0 = z;
+      run = 0.0;
+    }
+    run += (double)t[e];
+  }
+  if (z0 != SBX_ZONE_NONE) atomicAdd(&bins[z0], run);
+}
+
+template <int V>
+__global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int b = blockIdx.x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  constexpr int NT = kResidentThreads, NW = NT / 32;
+  const int H = p.H, W = p.W, Z = p.Z;
+  const int n_cv = H * W;
+  const int plan = p.n_plans == 1 ? 0 : b;
+  const ResidentLayout L = resident_layout(n_cv, Z);
+  float* bufA = reinterpret_cast<float*>(smem + L.off_a);
+  float* bufB = reinterpret_cast<float*>(smem + L.off_b);
+  float* n3p = reinterpret_cast<float*>(smem + L.off_n3);
+  uint16_t* dsc = reinterpret_cast<uint16_t*>(smem + L.off_desc);
+  Combo* tab = reinterpret_cast<Combo*>(smem + L.off_tab);
+  float* qcv = reinterpret_cast<float*>(smem + L.off_qcv);
+  double* bins = reinterpret_cast<double*>(smem + L.off_bins);
+  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);
+  float* wmax = reinterpret_cast<float*>(smem + L.off_wmax);
+  float* zpre = reinterpret_cast<float*>(smem + L.off_zpre);
+  float* zpost = reinterpret_cast<float*>(smem + L.off_zpost);
+  uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
+
+  float* gT = p.tbuf[0] + (size_t)b * n_cv;
+  const uint16_t* gD = p.desc + (size_t)plan * n_cv;
+  const bool use_tma = (n_cv % 8) == 0;
+
+  // ---- stage 0: start the bulk loads ---------------------------------------
+  if (use_tma) {
+    if (tid == 0) {
+      mbar_init(bar, 1);
+      mbar_expect_tx(bar, (uint32_t)(n_cv * 4 + n_cv * 2));
+      tma_load_1d(bufA, gT, (uint32_t)(n_cv * 4), bar);
+      tma_load_1d(dsc, gD, (uint32_t)(n_cv * 2), bar);
+    }
+  } else {
+    for (int i = tid; i < n_cv; i += NT) {
+      bufA[i] = gT[i];
+      dsc[i] = gD[i];
+    }
+  }
+
+  // ---- stage 1: HVAC prologue (warp 0) while the copies are in flight -------
+  const double amb_d = env_ambient(p, b, p.time_index);
+  const float t_inf = (float)amb_d;                       // tf_simulator.py:785
+  const float h = (float)env_convection(p, b);
+  Carry cy = {0, 0, 0, 0, 0};
+  if (warp == 0) {
+    for (int zi = lane; zi < Z; zi += 32) {
+      zpre[zi] = p.zone_mean[(size_t)b * Z + zi];
+      qcv[zi] = p.qcv[(size_t)b * Z + zi];
+    }
+    __syncwarp();
+    if (!p.fd_only) {
+      PreOut o = hvac_pre(p, b, plan, lane, zpre, p.global_mean[b], scratch);
+      cy.ahu_flow = o.ahu_flow; cy.boiler_flow = o.boiler_flow;
+      cy.return_water = o.return_water;
+      cy.ahu_count = o.ahu_count; cy.boiler_count = o.boiler_count;
+    }
+  } else if (warp == 1) {
+    build_combo_table(tab, p, plan, b, h, t_inf, lane, 32);
+  } else if (warp == 2) {
+    for (int i = lane; i <= Z; i += 32) bins[i] = 0.0;
+  }
+  __syncthreads();
+  if (use_tma) mbar_wait(bar, 0);
+  const Fast fast = load_fast(tab);
+
+  // ---- stage 2: n3 = (cm * T_prev) / dt  (tf_simulator.py:743-749) ----------
+  const int n_items = n_cv / V;
+  for (int it = tid; it < n_items; it += NT) {
+    float t[V], o[V];
+    uint32_t d[V];
+    load_f<V>(bufA + it * V, t);
+    load_d<V>(dsc + it * V, d);
+#pragma unroll
+    for (int e = 0; e < V; ++e) o[e] = fdiv(mul(cv_cm(d[e], tab, fast), t[e]), p.dt);
+    store_f<V>(n3p + it * V, o);
+  }
+  __syncthreads();
+
+  // ---- stage 3: Jacobi sweeps to convergence (simulator.py:348-364) ---------
+  float* in = bufA;
+  float* out = bufB;
+  const int wq = W / V;
+  int k = 0;
+  float md = 0.f;
+  const int limit = p.iteration_limit;
+  while (k < limit) {
+    ++k;
+    float lmax = 0.f;
+    int r = tid / wq, q = tid - r * wq;
+    const int dr = NT / wq, dq = NT - dr * wq;
+    for (int it = tid; it < n_items; it += NT) {
+      const int base = it * V;
+      float c[V], up[V], dn[V], n3v[V], o[V];
+      uint32_t d[V];
+      load_f<V>(in + base, c);
+      load_d<V>(dsc + base, d);
+      load_f<V>(n3p + base, n3v);
+      if (r > 0) load_f<V>(in + base - W, up); else fill<V>(up, t_inf);       // :642-644
+      if (r < H - 1) load_f<V>(in + base + W, dn); else fill<V>(dn, t_inf);   // :646
+      const float left = q > 0 ? in[base - 1] : t_inf;                        // :638-640
+      const float right = q < wq - 1 ? in[base + V] : t_inf;                  // :636
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float t_jm = e == 0 ? left : c[e - 1];
+        const float t_jp = e == V - 1 ? right : c[e + 1];
+        const float qv = (d[e] & SBX_DESC_DIFFUSER) ? qcv[desc_zone(d[e])] : 0.f;
+        o[e] = cv_update(d[e], t_jp, t_jm, up[e], dn[e], n3v[e], qv, t_inf, tab, fast);
+        lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));                     // :851-853
+      }
+      store_f<V>(out + base, o);
+      r += dr; q += dq;
+      if (q >= wq) { q -= wq; ++r; }
+    }
+    lmax = warp_max(lmax);
+    if (lane == 0) wmax[(k & 1) * 32 + warp] = lmax;
+    __syncthreads();
+    md = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) md = fmaxf(md, wmax[(k & 1) * 32 + w]);
+    float* tmp = in; in = out; out = tmp;
+    if (md <= p.threshold) break;                                             // simulator.py:362
+  }
+  // `in` now holds building.temp for the next step (simulator.py:369)
+
+  // ---- stage 4: write back + zone reductions + epilogue ---------------------
+  if (use_tma) {
+    if (tid == 0) tma_store_1d(gT, in, (uint32_t)(n_cv * 4));
+  } else {
+    for (int i = tid; i < n_cv; i += NT) gT[i] = in[i];
+  }
+  if (tid == 0) {
+    p.n_sweeps[b] = k;
+    p.max_delta[b] = md;
+    if (!p.fd_only) atomicAdd(p.sweeps_total, (unsigned long long)k);
+  }
+  if (!p.fd_only) {
+    double total = 0.0;
+    for (int it = tid; it < n_items; it += NT) {
+      float t[V];
+      uint32_t d[V];
+      load_f<V>(in + it * V, t);
+      load_d<V>(dsc + it * V, d);
+      zone_accumulate<V>(t, d, bins, total);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+    if (lane == 0) atomicAdd(&bins[Z], total);
+    __syncthreads();
+    if (warp == 0) {
+      const int32_t* ncv = p.zone_ncv + (size_t)plan * Z;
+      for (int zi = lane; zi < Z; zi += 32) {
+        const int n = ncv[zi];
+        const float m = n > 0 ? (float)(bins[zi] / (double)n) : 0.f;
+        zpost[zi] = m;
+        p.zone_mean[(size_t)b * Z + zi] = m;
+        p.qcv[(size_t)b * Z + zi] = p.qcv_next[(size_t)b * Z + zi];  // input_q for the next solve
+      }
+      const float gmean = (float)(bins[Z] / (double)n_cv);
+      if (lane == 0) p.global_mean[b] = gmean;
+      __syncwarp();
+      hvac_post(p, b, plan, lane, false, zpre, zpost, gmean, cy, scratch);
+    }
+  }
+  if (use_tma && tid == 0) tma_store_wait();
+}
+
+// ---------------------------------------------------------------------------
+// streaming path
+// ---------------------------------------------------------------------------
+
+struct StreamTiling {
+  int tiles_x, tiles_y, tiles;
+};
+__host__ __device__ inline StreamTiling stream_tiling(int H, int W, int V) {
+  StreamTiling t;
+  const int tile_w = 32 * V;
+  const int tile_h = (kStreamThreads / 32) * kStreamRowsPerWarp;
+  t.tiles_x = (W + tile_w - 1) / tile_w;
+  t.tiles_y = (H + tile_h - 1) / tile_h;
+  t.tiles = t.tiles_x * t.tiles_y;
+  return t;
+}
+
+__device__ __forceinline__ void sweep_buffers(int cur, int k, int& in, int& out) {
+  const int s0 = (cur + 1) % 3, s1 = (cur + 2) % 3;
+  in = k == 1 ? cur : ((k & 1) == 0 ? s0 : s1);
+  out = (k & 1) ? s0 : s1;
+}
+
+// One Jacobi sweep of every still-active building.  Sweep index k is 1-based.
+template <int V>
+__global__ void __launch_bounds__(kStreamThreads) k_sweep(const Params p, const int k) {
+  __shared__ Combo tab[kNumCombos];
+  __shared__ float qcv[kMaxZones + 1];
+  const StreamTiling tl = stream_tiling(p.H, p.W, V);
+  const int b = blockIdx.x / tl.tiles;
+  if (!p.active[b]) return;
+  const int tile = blockIdx.x - b * tl.tiles;
+  const int ty = tile / tl.tiles_x, tx = tile - ty * tl.tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, W = p.W, Z = p.Z;
+  const size_t n_cv = (size_t)H * W;
+  const int plan = p.n_plans == 1 ? 0 : b;
+  const float t_inf = (float)env_ambient(p, b, p.time_index);
+  const float h = (float)env_convection(p, b);
+  build_combo_table(tab, p, plan, b, h, t_inf, tid, kStreamThreads);
+  for (int i = tid; i < Z; i += kStreamThreads) qcv[i] = p.qcv[(size_t)b * Z + i];
+  __syncthreads();
+  const Fast fast = load_fast(tab);
+
+  const int cur = p.cur[b];
+  int bi, bo;
+  sweep_buffers(cur, k, bi, bo);
+  const float* __restrict__ tin = p.tbuf[bi] + (size_t)b * n_cv;
+  const float* __restrict__ tprev = p.tbuf[cur] + (size_t)b * n_cv;
+  float* __restrict__ tout = p.tbuf[bo] + (size_t)b * n_cv;
+  const uint16_t* __restrict__ dsc = p.desc + (size_t)plan * n_cv;
+
+  const int c0 = (tx * 32 + lane) * V;
+  const int r0 = (ty * (kStreamThreads / 32) + warp) * kStreamRowsPerWarp;
+  const bool col_ok = c0 < W;
+  float lmax = 0.f;
+  if (r0 < H) {
+    const int r1 = min(r0 + kStreamRowsPerWarp, H);
+    float up[V], c[V], dn[V];
+    fill<V>(up, t_inf);
+    fill<V>(c, t_inf);
+    if (col_ok) {
+      if (r0 > 0) load_f<V>(tin + (size_t)(r0 - 1) * W + c0, up);
+      load_f<V>(tin + (size_t)r0 * W + c0, c);
+    }
+    for (int r = r0; r < r1; ++r) {
+      fill<V>(dn, t_inf);
+      if (col_ok && r + 1 < H) load_f<V>(tin + (size_t)(r + 1) * W + c0, dn);
+      // horizontal neighbours: shuffle inside the warp, global load at its ends
+      float left = __shfl_up_sync(0xffffffffu, c[V - 1], 1);
+      float right = __shfl_down_sync(0xffffffffu, c[0], 1);
+      if (col_ok) {
+        if (lane == 0) left = c0 > 0 ? tin[(size_t)r * W + c0 - 1] : t_inf;
+        if (lane == 31 || c0 + V >= W) right = c0 + V < W ? tin[(size_t)r * W + c0 + V] : t_inf;
+        float tp[V], o[V];
+        uint32_t d[V];
+        load_f<V>(tprev + (size_t)r * W + c0, tp);
+        load_d<V>(dsc + (size_t)r * W + c0, d);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const float t_jm = e == 0 ? left : c[e - 1];
+          const float t_jp = e == V - 1 ? right : c[e + 1];
+          const float n3 = fdiv(mul(cv_cm(d[e], tab, fast), tp[e]), p.dt);
+          const float qv = (d[e] & SBX_DESC_DIFFUSER) ? qcv[desc_zone(d[e])] : 0.f;
+          o[e] = cv_update(d[e], t_jp, t_jm, up[e], dn[e], n3, qv, t_inf, tab, fast);
+          lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));
+        }
+        store_f<V>(tout + (size_t)r * W + c0, o);
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) { up[e] = c[e]; c[e] = dn[e]; }
+    }
+  }
+  lmax = warp_max(lmax);
+  if (lane == 0 && lmax > 0.f) atomicMax(&p.max_delta_bits[b], __float_as_uint(lmax));
+}
+
+// Convergence bookkeeping after sweep k (simulator.py:348-369).
+__global__ void k_check(const Params p, const int k) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  int still = 0;
+  if (b < p.B && p.active[b]) {
+    const float md = __uint_as_float(p.max_delta_bits[b]);
+    p.max_delta_bits[b] = 0u;
+    p.max_delta[b] = md;
+    p.n_sweeps[b] = k;
+    if (md <= p.threshold || k >= p.iteration_limit) {
+      int bi, bo;
+      sweep_buffers(p.cur[b], k, bi, bo);
+      p.cur[b] = (uint8_t)bo;
+      p.active[b] = 0;
+      if (!p.fd_only) atomicAdd(p.sweeps_total, (unsigned long long)k);
+    } else {
+      still = 1;
+    }
+  }
+  const unsigned m = __ballot_sync(0xffffffffu, still);
+  if ((threadIdx.x & 31) == 0 && m) atomicAdd(p.n_active, __popc(m));
+}
+
+__global__ void k_activate(const Params p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < p.B) {
+    p.active[b] = 1;
+    p.max_delta_bits[b] = 0u;
+    p.n_sweeps[b] = 0;
+  }
+}
+
+// Zone sums + grid total of building.temp (building.py:845-871, simulator.py:408).
+template <int V>
+__global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) {
+  __shared__ double bins[kMaxZones + 1];
+  const StreamTiling tl = stream_tiling(p.H, p.W, V);
+  const int b = blockIdx.x / tl.tiles;
+  const int tile = blockIdx.x - b * tl.tiles;
+  const int ty = tile / tl.tiles_x, tx = tile - ty * tl.tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, W = p.W, Z = p.Z;
+  const size_t n_cv = (size_t)H * W;
+  const int plan = p.n_plans == 1 ? 0 : b;
+  for (int i = tid; i <= Z; i += kStreamThreads) bins[i] = 0.0;
+  __syncthreads();
+  const float* __restrict__ t = p.tbuf[p.cur[b]] + (size_t)b * n_cv;
+  const uint16_t* __restrict__ dsc = p.desc + (size_t)plan * n_cv;
+  const int c0 = (tx * 32 + lane) * V;
+  const int r0 = (ty * (kStreamThreads / 32) + warp) * kStreamRowsPerWarp;
+  double total = 0.0;
+  if (c0 < W && r0 < H) {
+    const int r1 = min(r0 + kStreamRowsPerWarp, H);
+    for (int r = r0; r < r1; ++r) {
+      float tv[V];
+      uint32_t d[V];
+      load_f<V>(t + (size_t)r * W + c0, tv);
+      load_d<V>(dsc + (size_t)r * W + c0, d);
+      zone_accumulate<V>(tv, d, bins, total);
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if (lane == 0) atomicAdd(&bins[Z], total);
+  __syncthreads();
+  double* zs = p.zone_sum + (size_t)b * (Z + 1);
+  for (int i = tid; i <= Z; i += kStreamThreads)
+    if (bins[i] != 0.0) atomicAdd(&zs[i], bins[i]);
+}
+
+struct CarryStore {
+  double ahu_flow, boiler_flow, return_water;
+  int32_t ahu_count, boiler_count;
+};
+
+// HVAC prologue, warp per building (streaming path).
+__global__ void __launch_bounds__(128) k_pre(const Params p, CarryStore* carry) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int wpb = blockDim.x / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * wpb + warp;
+  if (b >= p.B) return;
+  const int Z = p.Z;
+  double* scratch = reinterpret_cast<double*>(smem) + (size_t)warp * (3 * Z + 64 + Z);
+  float* zpre = reinterpret_cast<float*>(scratch + 3 * Z + 64);
+  const int plan = p.n_plans == 1 ? 0 : b;
+  for (int zi = lane; zi < Z; zi += 32) zpre[zi] = p.zone_mean[(size_t)b * Z + zi];
+  __syncwarp();
+  PreOut o = hvac_pre(p, b, plan, lane, zpre, p.global_mean[b], scratch);
+  if (lane == 0) {
+    CarryStore c;
+    c.ahu_flow = o.ahu_flow; c.boiler_flow = o.boiler_flow; c.return_water = o.return_water;
+    c.ahu_count = o.ahu_count; c.boiler_count = o.boiler_count;
+    carry[b] = c;
+  }
+}
+
+// Means from zone sums, then observation + reward; warp per building.
+__global__ void __launch_bounds__(128) k_post(const Params p, const CarryStore* carry,
+                                              const int is_reset) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int wpb = blockDim.x / 32;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * wpb + warp;
+  if (b >= p.B) return;
+  const int Z = p.Z;
+  double* scratch = reinterpret_cast<double*>(smem) + (size_t)warp * (3 * Z + 64 + Z);
+  float* zpre = reinterpret_cast<float*>(scratch + 3 * Z + 64);
+  float* zpost = zpre + Z;
+  const int plan = p.n_plans == 1 ? 0 : b;
+  const int32_t* ncv = p.zone_ncv + (size_t)plan * Z;
+  const double* zs = p.zone_sum + (size_t)b * (Z + 1);
+  for (int zi = lane; zi < Z; zi += 32) {
+    const int n = ncv[zi];
+    const float m = n > 0 ? (float)(zs[zi] / (double)n) : 0.f;
+    zpost[zi] = m;
+    zpre[zi] = p.pre_zone_mean[(size_t)b * Z + zi];
+    p.zone_mean[(size_t)b * Z + zi] = m;
+    if (!is_reset) p.qcv[(size_t)b * Z + zi] = p.qcv_next[(size_t)b * Z + zi];
+  }
+  const float gmean = (float)(zs[Z] / (double)((size_t)p.H * p.W));
+  if (lane == 0) p.global_mean[b] = gmean;
+  __syncwarp();
+  Carry cy = {0, 0, 0, 0, 0};
+  if (!is_reset) {
+    const CarryStore c = carry[b];
+    cy.ahu_flow = c.ahu_flow; cy.boiler_flow = c.boiler_flow; cy.return_water = c.return_water;
+    cy.ahu_count = c.ahu_count; cy.boiler_count = c.boiler_count;
+  }
+  hvac_post(p, b, plan, lane, is_reset != 0, zpre, zpost, gmean, cy, scratch);
+}
+
+// Environment._reset: building.reset + hvac.reset (building.py:784-792,
+// hvac_floorplan_based.py:124-128).  Thermostat modes survive (vav.py:98).
+__global__ void k_reset_state(const Params p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= p.B) return;
+  p.ahu_heat_sp[b] = p.ahu_init_heat;
+  p.ahu_cool_sp[b] = p.ahu_init_cool;
+  p.boiler_sp[b] = p.boiler_init_sp;
+  p.boiler_tank[(size_t)b * 3 + 0] = p.boiler_init_sp;
+  p.boiler_tank[(size_t)b * 3 + 1] = 0.0;
+  p.boiler_tank[(size_t)b * 3 + 2] = 0.0;
+  p.cur[b] = 0;
+  p.n_sweeps[b] = 0;
+  p.max_delta[b] = 0.f;
+  for (int zi = 0; zi < p.Z; ++zi) {
+    p.qcv[(size_t)b * p.Z + zi] = 0.f;          // input_q = zeros
+    p.qcv_next[(size_t)b * p.Z + zi] = 0.f;
+    p.pre_zone_mean[(size_t)b * p.Z + zi] = 0.f;
+  }
+}
+
+__global__ void k_reset_temp(const Params p) {
+  const size_t n_cv = (size_t)p.H * p.W;
+  const size_t total = n_cv * p.B;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / n_cv, j = i - b * n_cv;
+    float v;
+    if (p.n_reset == 0) v = p.initial_temp[b];
+    else v = p.reset_temps[(p.n_reset == 1 ? 0 : b) * n_cv + j];
+    p.tbuf[0][i] = v;
+  }
+}
+
+// dst[b] = tbuf[cur[b]][b]  (download of building.temp in the streaming path)
+__global__ void k_gather_temp(const Params p, float* dst) {
+  const size_t n_cv = (size_t)p.H * p.W;
+  const size_t total = n_cv * p.B;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / n_cv;
+    dst[i] = p.tbuf[p.cur[b]][i];
+  }
+}
+
+}  // namespace sbx

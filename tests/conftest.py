@@ -1,0 +1,34 @@
+import os
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+  sys.path.insert(0, ROOT)
+TESTS = os.path.dirname(os.path.abspath(__file__))
+if TESTS not in sys.path:
+  sys.path.insert(0, TESTS)
+
+
+def pytest_configure(config):
+  config.addinivalue_line("markers", "gpu: needs a CUDA device (run on the B200 box)")
+  config.addinivalue_line("markers", "reference: needs /root/reference (this container only)")
+
+
+def _has_gpu():
+  try:
+    import torch
+    return torch.cuda.is_available()
+  except Exception:  # pylint: disable=broad-except
+    return False
+
+
+def pytest_collection_modifyitems(config, items):
+  have_gpu = None
+  for item in items:
+    if "gpu" in item.keywords:
+      if have_gpu is None:
+        have_gpu = _has_gpu()
+      if not have_gpu:
+        item.add_marker(pytest.mark.skip(reason="no CUDA device"))

@@ -1,0 +1,378 @@
+#!/usr/bin/env python
+"""Benchmark of the sbsim hot path (one Environment.step() over a batch of buildings).
+
+  python bench.py --gpus N --steps K --warmup W             # libsbx on B200
+  python bench.py --impl reference --gpus N --steps K ...    # CPU restatement of the reference
+
+Metric: building-env-steps/s (BASELINE.json).  Workload (config.workload):
+"randomized" = BASELINE.json configs[3] sharded per GPU (32768 randomised 64x96
+buildings per GPU; N=8 is exactly configs[3], N=1 with --envs-per-gpu 65536 is
+configs[2]); "office" = configs[1]'s size class (copies of one 744x1004 plan).
+
+One JSON line is printed by rank 0.  Keys follow the driver's contract:
+value = whole-job steps/s with inputs resident in HBM (actions already on the
+device, outputs left on the device), e2e = the same metric through the public
+host API `Environment.step(np.ndarray)` (pinned staging, H2D + D2H inside the
+timed region), roofline = achieved algorithmic HBM bytes/s of the step kernel
+against the measured copy bandwidth, cpu_baseline = the oracle timed on the
+host cores for a bounded sample.
+"""
+
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "building_env_steps_per_sec"
+UNIT = "env-steps/s"
+
+
+def parse_args():
+  ap = argparse.ArgumentParser()
+  ap.add_argument("--gpus", type=int, default=1)
+  ap.add_argument("--steps", type=int, default=40)
+  ap.add_argument("--warmup", type=int, default=5)
+  ap.add_argument("--impl", choices=["sbx", "reference"], default="sbx")
+  ap.add_argument("--workload", choices=["randomized", "office"], default="randomized")
+  ap.add_argument("--envs-per-gpu", type=int, default=None)
+  ap.add_argument("--layouts", type=int, default=1024)
+  ap.add_argument("--histogram", type=int, default=1)
+  ap.add_argument("--allgather", type=int, default=0,
+                  help="all-gather obs/reward/step_type to every rank each step (NCCL)")
+  ap.add_argument("--cpu-sample-envs", type=int, default=None)
+  ap.add_argument("--cpu-sample-steps", type=int, default=24)
+  ap.add_argument("--no-cpu-baseline", action="store_true")
+  ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--path", choices=["auto", "streaming", "resident"], default="auto")
+  return ap.parse_args()
+
+
+def dist_env():
+  return (int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0)),
+          int(os.environ.get("WORLD_SIZE", 1)))
+
+
+class ClockSampler(threading.Thread):
+  """Samples SM clocks and throttle reasons with nvidia-smi during the timed region."""
+
+  Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+       "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+       "clocks_event_reasons.sw_power_cap")
+
+  def __init__(self, index: int):
+    super().__init__(daemon=True)
+    self.index = index
+    self.samples = []
+    self._stop_evt = threading.Event()
+
+  def run(self):
+    while not self._stop_evt.is_set():
+      try:
+        out = subprocess.run(
+            ["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+             "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+        parts = [x.strip() for x in out.strip().split(",")]
+        if len(parts) >= 7:
+          self.samples.append(parts)
+      except Exception:  # pylint: disable=broad-except
+        pass
+      self._stop_evt.wait(0.2)
+
+  def stop(self):
+    self._stop_evt.set()
+    self.join(timeout=3)
+
+  def summary(self):
+    if not self.samples:
+      return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unsampled"]}
+    sm = [float(s[0]) for s in self.samples if s[0].replace(".", "").isdigit()]
+    mx = [float(s[1]) for s in self.samples if s[1].replace(".", "").isdigit()]
+    names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+    reasons = sorted({n for s in self.samples for n, v in zip(names, s[3:7]) if v == "Active"})
+    return {"sm_mhz": statistics.median(sm) if sm else None,
+            "sm_max_mhz": max(mx) if mx else None, "reasons": reasons,
+            "samples": len(self.samples)}
+
+
+def measured_peak_gbs():
+  path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+  if os.path.exists(path):
+    with open(path) as f:
+      return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+  return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+def algorithmic_bytes_per_env_step(n_cv, n_zones, obs_dim, n_actions, desc_bytes, sweeps, resident):
+  """SURVEY.md section 8d.  Resident: N*(4 read + 4 write) + N*s + 64*Z + 4*(D+A+3).
+  Streaming: n*N*12 + N*s (+ the same small terms)."""
+  small = 64 * n_zones + 4 * (obs_dim + n_actions + 3)
+  if resident:
+    return n_cv * 8 + n_cv * desc_bytes + small
+  return sweeps * n_cv * 12 + n_cv * desc_bytes + small
+
+
+def build_env(args, rank, local_rank):
+  import sbsim_b200 as sbx
+  from sbsim_b200 import floorplan, workloads
+  path = {"auto": sbx.PATH_AUTO, "streaming": sbx.PATH_STREAMING,
+          "resident": sbx.PATH_RESIDENT}[args.path]
+  episode = args.warmup + args.steps * 2 + 8
+  if args.workload == "randomized":
+    n = args.envs_per_gpu or 32768
+    env, wl = workloads.make_randomized_env(
+        n, seed=2024 + rank, episode_steps=episode, n_layouts=args.layouts,
+        histogram=bool(args.histogram), device=local_rank, kernel_path=path)
+    desc = {"workload": "randomized-64x96 (BASELINE.json configs[3] per-GPU shard)",
+            "envs_per_gpu": n, "grid": [64, 96], "layouts": wl.n_layouts,
+            "plans": "per-env descriptor, materials, weather, T0, actions"}
+    return env, wl, desc
+  n = args.envs_per_gpu or 4096
+  plan = workloads.synthetic_office_plan()
+  cp = floorplan.compile_plan(plan, None, cv_size_cm=10.0,
+                              inside_air=floorplan.MaterialProperties(50.0, 700.0, 1.0),
+                              inside_wall=floorplan.MaterialProperties(50.0, 1.0, 700.0),
+                              building_exterior=floorplan.MaterialProperties(0.05, 700.0, 1.0))
+  env = workloads.make_shared_plan_env(cp, n, episode_steps=episode,
+                                       histogram=bool(args.histogram), device=local_rank,
+                                       kernel_path=path)
+  desc = {"workload": "office-744x1004 x copies (BASELINE.json configs[1] size class)",
+          "envs_per_gpu": n, "grid": [cp.height, cp.width], "zones": cp.n_zones,
+          "plans": "one shared descriptor"}
+  return env, None, desc
+
+
+def run_sbx(args):
+  import torch
+  import torch.distributed as dist
+  rank, local_rank, world = dist_env()
+  if world != args.gpus and world > 1:
+    raise SystemExit(f"WORLD_SIZE {world} != --gpus {args.gpus}")
+  if not torch.cuda.is_available():
+    raise SystemExit("bench.py needs a CUDA device; sbsim_b200 has no CPU fallback")
+  torch.cuda.set_device(local_rank)
+  dev = torch.device("cuda", local_rank)
+  if world > 1:
+    dist.init_process_group("nccl", device_id=dev)
+
+  env, wl, cfg_desc = build_env(args, rank, local_rank)
+  B = env.batch_size
+  D = env.observation_spec().shape[0]
+  A = env.action_spec().shape[0]
+  W, K = args.warmup, args.steps
+  if W < 3:
+    raise SystemExit("--warmup must be >= 3")
+
+  gen = torch.Generator(device=dev)
+  gen.manual_seed(3000 + rank)
+  actions = torch.rand((W + K, B, A), device=dev, generator=gen) * 2.0 - 1.0
+  obs = torch.zeros((B, D), device=dev)
+  rew = torch.zeros(B, device=dev)
+  st = torch.zeros(B, dtype=torch.int32, device=dev)
+  dis = torch.zeros(B, device=dev)
+  stream = torch.cuda.current_stream(dev)
+  sptr = stream.cuda_stream
+  gathered = None
+  if world > 1 and args.allgather:
+    gathered = (torch.zeros((world, B, D), device=dev), torch.zeros((world, B), device=dev),
+                torch.zeros((world, B), dtype=torch.int32, device=dev))
+
+  def barrier():
+    if world > 1:
+      dist.barrier()
+    torch.cuda.synchronize(dev)
+
+  def one_step(i):
+    env.step_device(actions[i], obs, rew, st, dis, stream=sptr)
+    if gathered is not None:
+      dist.all_gather_into_tensor(gathered[0], obs)
+      dist.all_gather_into_tensor(gathered[1], rew)
+      dist.all_gather_into_tensor(gathered[2], st)
+
+  # ---- device-resident timing (value) ----
+  env.reset_device(obs, rew, st, dis, stream=sptr)
+  for i in range(W):
+    one_step(i)
+  barrier()
+  info0 = env.handle.info()
+  sampler = ClockSampler(local_rank)
+  sampler.start()
+  ev = [torch.cuda.Event(enable_timing=True) for _ in range(K + 1)]
+  barrier()
+  ev[0].record(stream)
+  for i in range(K):
+    one_step(W + i)
+    ev[i + 1].record(stream)
+  barrier()
+  sampler.stop()
+  info1 = env.handle.info()
+  per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
+  total_ms = ev[0].elapsed_time(ev[K])
+  t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+  if world > 1:
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+  max_ms = float(t.item())
+  launches = int(info1.kernel_launches - info0.kernel_launches)
+  sweeps = int(info1.sweeps_total - info0.sweeps_total)
+  mean_sweeps = sweeps / float(B * K)
+  value = world * B * K / (max_ms / 1e3)
+
+  # ---- end-to-end through the public host API (e2e) ----
+  e2e = None
+  if not args.no_e2e:
+    a_host = (np.random.default_rng(4000 + rank).uniform(-1, 1, (W + K, B, A))
+              .astype(np.float32))
+    for i in range(3):
+      env.step(a_host[i])
+    barrier()
+    t0 = time.perf_counter()
+    for i in range(K):
+      ts = env.step(a_host[3 + i])
+    torch.cuda.synchronize(dev)
+    el = time.perf_counter() - t0
+    t = torch.tensor([el], device=dev, dtype=torch.float64)
+    if world > 1:
+      dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    el = float(t.item())
+    e2e = {"value": world * B * K / el, "unit": UNIT,
+           "h2d_bytes_per_step": int(B * A * 4),
+           "d2h_bytes_per_step": int(B * (D + 3) * 4),
+           "api": "sbsim_b200.Environment.step(np.ndarray) -> TimeStep (sbx_step_host)",
+           "ms_per_step": el / K * 1e3}
+    del ts
+
+  # ---- roofline of the dominant kernel ----
+  resident = env.kernel_path == 2
+  n_cv = env.building.height * env.building.width
+  Z = env.building.n_zones
+  desc_bytes = 2 if len(env.building.plans) > 1 else 0
+  bytes_step = algorithmic_bytes_per_env_step(n_cv, Z, D, A, desc_bytes, mean_sweeps, resident)
+  peak, peak_src = measured_peak_gbs()
+  if resident:
+    kernel = "k_resident_step (whole step, one launch)"
+    launch_ms = statistics.mean(per_step_ms)
+    bytes_launch = bytes_step * B
+    achieved = bytes_launch / (launch_ms / 1e3) / 1e9
+  else:
+    kernel = "k_sweep (one Jacobi sweep of every active building)"
+    # sweeps dominate the step; the per-launch figure is the step's bytes over its time
+    launch_ms = statistics.mean(per_step_ms)
+    bytes_launch = bytes_step * B
+    achieved = bytes_launch / (launch_ms / 1e3) / 1e9
+  roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
+              "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
+              "traffic": None, "algorithmic_bytes_per_env_step": bytes_step,
+              "mean_sweeps_per_step": mean_sweeps,
+              "launch_ms": launch_ms}
+
+  # ---- CPU baseline beside it (rank 0, N=1 only) ----
+  cpu = None
+  if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "randomized":
+    cpu = cpu_baseline(args, wl, K=args.cpu_sample_steps)
+
+  if rank == 0:
+    line = {
+        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+        "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": dict(cfg_desc, global_envs=world * B,
+                       kernel_path="resident" if resident else "streaming",
+                       obs_dim=D, l2_policy="inputs larger than L2 (state %.0f MB per GPU)"
+                       % (B * n_cv * 4 / 1e6),
+                       allgather=bool(gathered is not None), episode_steps=288,
+                       time_step_sec=300),
+        "clocks": sampler.summary(), "gpu_launches": launches,
+        "roofline": roofline,
+    }
+    if e2e is not None:
+      line["e2e"] = e2e
+    if cpu is not None:
+      line["cpu_baseline"] = cpu
+    print(json.dumps(line), flush=True)
+  env.close()
+  if world > 1:
+    dist.destroy_process_group()
+
+
+def _oracle_specs(wl, n, episode_steps):
+  from sbsim_b200 import workloads
+  specs = []
+  for b in range(n):
+    specs.append((wl.plans[b], float(wl.weather_low[b]), float(wl.weather_high[b]),
+                  float(wl.convection[b]), float(wl.initial_temp[b]),
+                  workloads.NORMALIZATION, workloads.HISTOGRAM, episode_steps,
+                  workloads.DEFAULT_START))
+  return specs
+
+
+def cpu_baseline(args, wl, K):
+  """The oracle (CPU restatement of the reference) on a bounded sample."""
+  from oracle import bench_support
+  cores = bench_support.host_cores()
+  n = args.cpu_sample_envs or max(cores * 2, 8)
+  n = min(n, len(wl.plans))
+  rate, total, wall, sweeps = bench_support.time_oracle(
+      _oracle_specs(wl, n, K + 8), K, n_procs=cores)
+  return {"value": rate, "unit": UNIT, "cores": min(cores, n), "kind": "port",
+          "sample": f"first {n} buildings of the same randomized workload x {K} steps "
+                    f"({total} env-steps, {wall:.1f} s wall, {sweeps:.2f} sweeps/step), "
+                    "oracle/ NumPy-fp32 restatement, one process per core"}
+
+
+def run_reference(args):
+  """--impl reference: the CPU restatement of the reference's own path (oracle
+  port; the reference is Python with TensorFlow, which this image lacks) on all
+  host cores, on the same workload definition; each step is a bounded sample."""
+  rank, _, world = dist_env()
+  if rank != 0:
+    return
+  from oracle import bench_support
+  from sbsim_b200 import workloads
+  if args.workload != "randomized":
+    print(json.dumps({"impl": "reference", "unavailable":
+                      "reference arm implemented for the randomized workload only"}))
+    return
+  cores = bench_support.host_cores()
+  n = args.cpu_sample_envs or max(cores * 2, 8)
+  W, K = args.warmup, args.steps
+  # bound the run: ~250 env-steps/s/core => keep total env-steps near 30 s of work
+  budget = int(250 * cores * 30)
+  K_eff = max(1, min(K, budget // max(n, 1)))
+  wl = workloads.randomized(n, seed=2024, n_layouts=min(args.layouts, n))
+  rate, total, wall, sweeps = bench_support.time_oracle(
+      _oracle_specs(wl, n, K_eff + W + 8), K_eff, n_procs=cores)
+  line = {
+      "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT,
+      "n_gpus": args.gpus, "steps": K_eff, "warmup": 0, "ms_per_step": 1e3 * n / rate,
+      "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+      "data": "synthetic",
+      "config": {"workload": "randomized-64x96 (BASELINE.json configs[3] per-GPU shard)",
+                 "sample_envs": n, "grid": [64, 96]},
+      "cpu_baseline": {"value": rate, "unit": UNIT, "cores": min(cores, n), "kind": "port",
+                       "sample": f"{n} buildings x {K_eff} steps ({total} env-steps, "
+                                 f"{wall:.1f} s wall, {sweeps:.2f} sweeps/step)"},
+      "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+  }
+  print(json.dumps(line), flush=True)
+
+
+def main():
+  args = parse_args()
+  if args.impl == "reference":
+    run_reference(args)
+  else:
+    run_sbx(args)
+
+
+if __name__ == "__main__":
+  main()

@@ -36,10 +36,12 @@ constexpr double kGravity = 9.8;               // utils/constants.py:47
 // Coefficients of one (class, material) combination; tf_simulator.py:791-798,
 // 669-690.  k1 pairs with T(i,j+1), k3 with T(i,j-1) (shift semantics of
 // tf_simulator.py:459-472, 636-640), k2 with T(i+1,j), k4 with T(i-1,j).
-struct Combo {
+struct __align__(16) Combo {
   float k1, k3, k2, k4;
-  float hl_t, hr_t, hb_t, ha_t;  // T_inf * h on the left/right/bottom/top side
-  float vz, uz, den, cm;         // cm = ((((rho*U)*V)*c)*z)*c
+  // T_inf*h of the ambient-facing horizontal side (left OR right: no class has
+  // both, so (x + hl) + hr == x + hh exactly) and of the vertical side
+  float hh, hv, vz, uz;
+  float den, cm, pad0, pad1;     // cm = ((((rho*U)*V)*c)*z)*c
 };
 
 // Everything a kernel needs; passed by value.
@@ -186,10 +188,10 @@ __device__ inline Combo make_combo(int cls, const double* mat /*k,c,rho*/, doubl
   o.cm = d3;
   d3 = fdiv(d3, dt);                                    // :686
   o.den = add(add(d1, d2), d3);                         // :689-690
-  o.hl_t = mul(t_inf, hl);                              // :725
-  o.hr_t = mul(t_inf, hr);                              // :726
-  o.ha_t = mul(t_inf, ht);                              // :727
-  o.hb_t = mul(t_inf, hb);                              // :728
+  // :725-728; exactly one of (hl, hr) and one of (ht, hb) can be non-zero
+  o.hh = sl ? mul(t_inf, hl) : mul(t_inf, hr);
+  o.hv = sb ? mul(t_inf, hb) : mul(t_inf, ht);
+  o.pad0 = o.pad1 = 0.f;
   return o;
 }
 
@@ -204,66 +206,42 @@ __device__ inline void build_combo_table(Combo* tab, const Params& p, int plan, 
   }
 }
 
-// Interior-class coefficients of the three materials, kept in registers.
-struct Fast {
-  float kq[kNumMaterials], den[kNumMaterials], cm[kNumMaterials];
-  float vz;
+__device__ __forceinline__ int combo_index(uint32_t d) {
+  return desc_class(d) * kNumMaterials + desc_material(d);
+}
+
+struct ComboRegs {
+  float4 k;   // k1, k3, k2, k4
+  float4 h;   // hh, hv, vz, uz
+  float4 d;   // den, cm, -, -
 };
 
-__device__ inline Fast load_fast(const Combo* tab) {
-  Fast f;
-#pragma unroll
-  for (int m = 0; m < kNumMaterials; ++m) {
-    const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + m];
-    f.kq[m] = c.k1;
-    f.den[m] = c.den;
-    f.cm[m] = c.cm;
-  }
-  f.vz = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
-  return f;
-}
-
-__device__ __forceinline__ float sel3(const float (&a)[kNumMaterials], int m) {
-  return m == 0 ? a[0] : (m == 1 ? a[1] : a[2]);
-}
-
 // thermal-mass coefficient cm of a CV (for the n3 term)
-__device__ __forceinline__ float cv_cm(uint32_t d, const Combo* tab, const Fast& f) {
-  const int cls = desc_class(d), m = desc_material(d);
-  return cls == SBX_CV_INTERIOR ? sel3(f.cm, m) : tab[cls * kNumMaterials + m].cm;
+__device__ __forceinline__ float cv_cm(uint32_t d, const Combo* tab) {
+  return tab[combo_index(d)].cm;
 }
 
-// One CV update (tf_simulator.py:719-754, 843, 847-849).
+// One CV update (tf_simulator.py:719-754, 843, 847-849), branch-free: every
+// class runs the same instruction stream with its own coefficients (fetched as
+// three 128-bit shared-memory loads, broadcast when a warp shares a class), so
+// warps that mix interior / wall / boundary CVs do not diverge.
 //   t_jp = T(i,j+1), t_jm = T(i,j-1), t_im = T(i-1,j), t_ip = T(i+1,j)
 //   n3 = ((cm * T_prev) / dt)   precomputed (:743-749)
 //   q  = input_q at this CV (0 unless it is a diffuser)
 __device__ __forceinline__ float cv_update(uint32_t d, float t_jp, float t_jm, float t_im,
                                            float t_ip, float n3, float q, float t_inf,
-                                           const Combo* tab, const Fast& f) {
-  const int cls = desc_class(d);
-  const int m = desc_material(d);
-  if (cls == SBX_CV_INTERIOR) {
-    const float kq = sel3(f.kq, m);
-    // (((k1*Tl)+(k3*Tr))+0)+0 ; the h terms are exactly +0 for this class
-    float n1 = add(mul(kq, t_jp), mul(kq, t_jm));       // :719-720, 731
-    n1 = mul(f.vz, n1);                                 // :734
-    float n2 = add(mul(kq, t_ip), mul(kq, t_im));       // :721-722, 737
-    n2 = mul(f.vz, n2);                                 // :740 (uz == vz for interior)
-    float num = add(add(add(n1, n2), n3), q);           // :752-754
-    return fdiv(num, sel3(f.den, m));                   // :843
-  }
-  if (cls == SBX_CV_EXTERIOR) return t_inf;             // :847-849
-  const Combo c = tab[cls * kNumMaterials + m];
-  float n1 = add(mul(c.k1, t_jp), mul(c.k3, t_jm));
-  n1 = add(n1, c.hl_t);                                 // :732
-  n1 = add(n1, c.hr_t);                                 // :733
-  n1 = mul(c.vz, n1);
-  float n2 = add(mul(c.k2, t_ip), mul(c.k4, t_im));
-  n2 = add(n2, c.hb_t);                                 // :738
-  n2 = add(n2, c.ha_t);                                 // :739
-  n2 = mul(c.uz, n2);
-  float num = add(add(add(n1, n2), n3), q);
-  return fdiv(num, c.den);
+                                           const Combo* tab) {
+  const float4* c4 = reinterpret_cast<const float4*>(tab + combo_index(d));
+  const float4 k = c4[0], h = c4[1], dd = c4[2];
+  float n1 = add(mul(k.x, t_jp), mul(k.y, t_jm));       // :719-720, 731
+  n1 = add(n1, h.x);                                    // :732-733
+  n1 = mul(h.z, n1);                                    // :734
+  float n2 = add(mul(k.z, t_ip), mul(k.w, t_im));       // :721-722, 737
+  n2 = add(n2, h.y);                                    // :738-739
+  n2 = mul(h.w, n2);                                    // :740
+  const float num = add(add(add(n1, n2), n3), q);       // :752-754
+  const float t = fdiv(num, dd.x);                      // :843
+  return desc_class(d) == SBX_CV_EXTERIOR ? t_inf : t;  // :847-849
 }
 
 __device__ __forceinline__ float warp_max(float v) {

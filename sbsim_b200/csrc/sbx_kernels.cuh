@@ -139,7 +139,7 @@ __host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z) {
   L.off_desc = o; o = al(o + (size_t)n_cv * 2);
   L.off_tab = o; o = al(o + sizeof(Combo) * kNumCombos);
   L.off_qcv = o; o = al(o + (size_t)(Z + 1) * 4);
-  L.off_bins = o; o = al(o + (size_t)(Z + 1) * 8);
+  L.off_bins = o; o = al(o + (size_t)(Z + 1) * 8 * (kResidentThreads / 32 + 1));
   L.off_scratch = o; o = al(o + (size_t)(3 * Z + 64) * 8);
   L.off_wmax = o; o = al(o + 2 * 32 * 4);
   L.off_zpre = o; o = al(o + (size_t)Z * 4);
@@ -150,6 +150,7 @@ __host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z) {
 }
 
 // Accumulates V consecutive CVs into per-zone shared bins (fp64) + grid total.
+// (streaming path: one atomic per run of equal zone ids)
 template <int V>
 __device__ __forceinline__ void zone_accumulate(const float (&t)[V], const uint32_t (&d)[V],
                                                 double* bins, double& total) {
@@ -167,6 +168,41 @@ __device__ __forceinline__ void zone_accumulate(const float (&t)[V], const uint3
     run += (double)t[e];
   }
   if (z0 != SBX_ZONE_NONE) atomicAdd(&bins[z0], run);
+}
+
+// Warp-cooperative version for 32 consecutive vectors (one per lane): zone ids
+// form contiguous segments along a row, so a segmented shuffle reduction leaves
+// one partial sum per segment and only segment heads touch the (warp-private)
+// bins.  Vectors that straddle a zone boundary flush their tail directly.
+template <int V>
+__device__ __forceinline__ void zone_accumulate_warp(const float (&t)[V], const uint32_t (&d)[V],
+                                                     bool valid, int lane, double* wbins,
+                                                     double& total) {
+  int z = SBX_ZONE_NONE;
+  double s = 0.0;
+  if (valid) {
+    z = desc_zone(d[0]);
+    s = (double)t[0];
+    total += (double)t[0];
+#pragma unroll
+    for (int e = 1; e < V; ++e) {
+      const int ze = desc_zone(d[e]);
+      total += (double)t[e];
+      if (ze == z) s += (double)t[e];
+      else if (ze != SBX_ZONE_NONE) atomicAdd(&wbins[ze], (double)t[e]);  // rare: boundary vector
+    }
+  }
+  const int z_prev = __shfl_up_sync(0xffffffffu, z, 1);
+  const bool head = lane == 0 || z_prev != z;
+  const unsigned heads = __ballot_sync(0xffffffffu, head);
+  const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const double s_up = __shfl_down_sync(0xffffffffu, s, o);
+    const int seg_up = __shfl_down_sync(0xffffffffu, seg, o);
+    if (lane + o < 32 && seg_up == seg) s += s_up;
+  }
+  if (head && z != SBX_ZONE_NONE) atomicAdd(&wbins[z], s);
 }
 
 template <int V>
@@ -231,11 +267,10 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   } else if (warp == 1) {
     build_combo_table(tab, p, plan, b, h, t_inf, lane, 32);
   } else if (warp == 2) {
-    for (int i = lane; i <= Z; i += 32) bins[i] = 0.0;
+    for (int i = lane; i < (Z + 1) * (NW + 1); i += 32) bins[i] = 0.0;
   }
   __syncthreads();
   if (use_tma) mbar_wait(bar, 0);
-  const Fast fast = load_fast(tab);
 
   // ---- stage 2: n3 = (cm * T_prev) / dt  (tf_simulator.py:743-749) ----------
   const int n_items = n_cv / V;
@@ -245,7 +280,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     load_f<V>(bufA + it * V, t);
     load_d<V>(dsc + it * V, d);
 #pragma unroll
-    for (int e = 0; e < V; ++e) o[e] = fdiv(mul(cv_cm(d[e], tab, fast), t[e]), p.dt);
+    for (int e = 0; e < V; ++e) o[e] = fdiv(mul(cv_cm(d[e], tab), t[e]), p.dt);
     store_f<V>(n3p + it * V, o);
   }
   __syncthreads();
@@ -255,7 +290,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   float* out = bufB;
   const int wq = W / V;
   int k = 0;
-  float md = 0.f;
+  float md = 0.f, last_lmax = 0.f;
   const int limit = p.iteration_limit;
   while (k < limit) {
     ++k;
@@ -278,22 +313,27 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
         const float t_jm = e == 0 ? left : c[e - 1];
         const float t_jp = e == V - 1 ? right : c[e + 1];
         const float qv = (d[e] & SBX_DESC_DIFFUSER) ? qcv[desc_zone(d[e])] : 0.f;
-        o[e] = cv_update(d[e], t_jp, t_jm, up[e], dn[e], n3v[e], qv, t_inf, tab, fast);
+        o[e] = cv_update(d[e], t_jp, t_jm, up[e], dn[e], n3v[e], qv, t_inf, tab);
         lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));                     // :851-853
       }
       store_f<V>(out + base, o);
       r += dr; q += dq;
       if (q >= wq) { q -= wq; ++r; }
     }
-    lmax = warp_max(lmax);
-    if (lane == 0) wmax[(k & 1) * 32 + warp] = lmax;
-    __syncthreads();
-    md = 0.f;
-#pragma unroll
-    for (int w = 0; w < NW; ++w) md = fmaxf(md, wmax[(k & 1) * 32 + w]);
+    // max|dT| <= threshold  <=>  no thread saw a delta above it (simulator.py:362);
+    // the barrier doubles as the ping-pong hazard fence.
+    const int above = __syncthreads_or(lmax > p.threshold);
+    last_lmax = lmax;
     float* tmp = in; in = out; out = tmp;
-    if (md <= p.threshold) break;                                             // simulator.py:362
+    if (!above) break;
   }
+  // block max of the last sweep (diagnostic SBX_F_MAX_DELTA)
+  last_lmax = warp_max(last_lmax);
+  if (lane == 0) wmax[warp] = last_lmax;
+  __syncthreads();
+  md = 0.f;
+#pragma unroll
+  for (int w = 0; w < NW; ++w) md = fmaxf(md, wmax[w]);
   // `in` now holds building.temp for the next step (simulator.py:369)
 
   // ---- stage 4: write back + zone reductions + epilogue ---------------------
@@ -309,16 +349,28 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   }
   if (!p.fd_only) {
     double total = 0.0;
-    for (int it = tid; it < n_items; it += NT) {
+    double* wbins = bins + (size_t)(warp + 1) * (Z + 1);   // warp-private bins
+    for (int base_it = warp * 32; base_it < n_items; base_it += NT) {
+      const int it = base_it + lane;
+      const bool valid = it < n_items;
       float t[V];
       uint32_t d[V];
-      load_f<V>(in + it * V, t);
-      load_d<V>(dsc + it * V, d);
-      zone_accumulate<V>(t, d, bins, total);
+      if (valid) {
+        load_f<V>(in + it * V, t);
+        load_d<V>(dsc + it * V, d);
+      }
+      zone_accumulate_warp<V>(t, d, valid, lane, wbins, total);
     }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    if (lane == 0) atomicAdd(&bins[Z], total);
+    if (lane == 0) wbins[Z] = total;
+    __syncthreads();
+    for (int i = tid; i <= Z; i += NT) {       // fixed-order combine: deterministic
+      double acc = 0.0;
+#pragma unroll
+      for (int w = 1; w <= NW; ++w) acc += bins[(size_t)w * (Z + 1) + i];
+      bins[i] = acc;
+    }
     __syncthreads();
     if (warp == 0) {
       const int32_t* ncv = p.zone_ncv + (size_t)plan * Z;
@@ -380,7 +432,6 @@ __global__ void __launch_bounds__(kStreamThreads) k_sweep(const Params p, const 
   build_combo_table(tab, p, plan, b, h, t_inf, tid, kStreamThreads);
   for (int i = tid; i < Z; i += kStreamThreads) qcv[i] = p.qcv[(size_t)b * Z + i];
   __syncthreads();
-  const Fast fast = load_fast(tab);
 
   const int cur = p.cur[b];
   int bi, bo;
@@ -420,9 +471,9 @@ __global__ void __launch_bounds__(kStreamThreads) k_sweep(const Params p, const 
         for (int e = 0; e < V; ++e) {
           const float t_jm = e == 0 ? left : c[e - 1];
           const float t_jp = e == V - 1 ? right : c[e + 1];
-          const float n3 = fdiv(mul(cv_cm(d[e], tab, fast), tp[e]), p.dt);
+          const float n3 = fdiv(mul(cv_cm(d[e], tab), tp[e]), p.dt);
           const float qv = (d[e] & SBX_DESC_DIFFUSER) ? qcv[desc_zone(d[e])] : 0.f;
-          o[e] = cv_update(d[e], t_jp, t_jm, up[e], dn[e], n3, qv, t_inf, tab, fast);
+          o[e] = cv_update(d[e], t_jp, t_jm, up[e], dn[e], n3, qv, t_inf, tab);
           lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));
         }
         store_f<V>(tout + (size_t)r * W + c0, o);

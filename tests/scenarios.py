@@ -44,7 +44,7 @@ NORMALIZATION = {  # subset of sim_config.gin:253-580 that matches simulated dev
     "zone_air_temperature_sensor": (290.0, 25.0),
 }
 HISTOGRAM = (  # sim_config.gin:586-590, zone temperature bins in normalised units here
-    ("zone_air_temperature_sensor", tuple(np.linspace(-1.0, 2.6, 19))),
+    ("zone_air_temperature_sensor", tuple(np.linspace(-1.03, 2.57, 19))),
     ("supply_air_damper_percentage_command", (0.0, 0.2, 0.4, 0.6, 0.8, 1.0)),
     ("supply_air_flowrate_setpoint", (0., 0.05, .1, .2, .3, .4, .5, .7, .9)),
 )

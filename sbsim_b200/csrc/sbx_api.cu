@@ -6,9 +6,10 @@
 //   * All envs of a handle share one clock, so step_count / time_index /
 //     episode_ended and the thermostats' "previous timestamp" (which the
 //     reference never resets, vav.py:98) are host integers.
-//   * Resident path: one kernel launch per env step.  Streaming path: HVAC
-//     prologue, one launch per Jacobi sweep with a pinned-memory convergence
-//     poll, zone reduction, epilogue.
+//   * A step is HVAC prologue (k_pre) -> diffusion solve -> epilogue (k_post).
+//     Resident path: the solve is ONE launch, no host synchronisation anywhere
+//     in the step.  Streaming path: one launch per Jacobi sweep with a
+//     pinned-memory convergence poll, then a zone-reduction launch.
 //   * sbx_step_host stages through pinned buffers so that host<->device copies
 //     are asynchronous DMA on the handle's stream.
 #include <cuda_runtime.h>
@@ -284,15 +285,17 @@ int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_
   p.time_index = h->time_index; p.step_count = h->step_count;
   p.therm_seen = h->therm_seen; p.prev_comfort = h->prev_comfort;
   p.action = action; p.obs = obs; p.reward = reward; p.step_type = step_type; p.discount_out = discount;
-  if (h->path == SBX_PATH_RESIDENT) {
-    if (int rc = run_resident(h, st)) return rc;
-  } else {
+  {
     const int wpb = 4;
     const unsigned grid = (unsigned)((p.B + wpb - 1) / wpb);
     k_pre<<<grid, wpb * 32, pre_post_smem(h, wpb), st>>>(p, h->carry);
     if (int rc = launch_check(h, "k_pre")) return rc;
-    if (int rc = run_stream_sweeps(h, st)) return rc;
-    if (int rc = launch_zone_reduce(h, st)) return rc;
+    if (h->path == SBX_PATH_RESIDENT) {
+      if (int rc = run_resident(h, st)) return rc;      // solve + zone sums, one launch
+    } else {
+      if (int rc = run_stream_sweeps(h, st)) return rc;
+      if (int rc = launch_zone_reduce(h, st)) return rc;
+    }
     if (int rc = launch_post(h, st, 0)) return rc;
   }
   // host mirror of Thermostat._previous_timestamp (thermostat.py:147) and of the

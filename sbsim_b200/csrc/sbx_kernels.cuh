@@ -1,10 +1,10 @@
 // Kernels of libsbx (sm_100a).
 //
-//  k_resident_step   one CTA per building, the whole env step in ONE launch:
+//  k_resident_step   one CTA per building, the whole diffusion solve in ONE launch:
 //                    TMA bulk load of the temperature grid + descriptor into
-//                    shared memory, HVAC prologue, Jacobi sweeps to convergence
-//                    entirely on chip, zone reductions, observation + reward
-//                    epilogue, TMA bulk store of the new grid.
+//                    shared memory, Jacobi sweeps to convergence entirely on
+//                    chip, zone / whole-grid sums, TMA bulk store of the new
+//                    grid.  HBM sees each temperature once in and once out.
 //  k_sweep           streaming path (grids that do not fit an SM, e.g. the
 //                    744x1004 calibrated plan): one Jacobi sweep per launch,
 //                    128-bit coalesced row loads, rolling 3-row register window,
@@ -247,23 +247,12 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     }
   }
 
-  // ---- stage 1: HVAC prologue (warp 0) while the copies are in flight -------
+  // ---- stage 1: per-building constants while the copies are in flight ---------
   const double amb_d = env_ambient(p, b, p.time_index);
   const float t_inf = (float)amb_d;                       // tf_simulator.py:785
   const float h = (float)env_convection(p, b);
-  Carry cy = {0, 0, 0, 0, 0};
   if (warp == 0) {
-    for (int zi = lane; zi < Z; zi += 32) {
-      zpre[zi] = p.zone_mean[(size_t)b * Z + zi];
-      qcv[zi] = p.qcv[(size_t)b * Z + zi];
-    }
-    __syncwarp();
-    if (!p.fd_only) {
-      PreOut o = hvac_pre(p, b, plan, lane, zpre, p.global_mean[b], scratch);
-      cy.ahu_flow = o.ahu_flow; cy.boiler_flow = o.boiler_flow;
-      cy.return_water = o.return_water;
-      cy.ahu_count = o.ahu_count; cy.boiler_count = o.boiler_count;
-    }
+    for (int zi = lane; zi < Z; zi += 32) qcv[zi] = p.qcv[(size_t)b * Z + zi];
   } else if (warp == 1) {
     build_combo_table(tab, p, plan, b, h, t_inf, lane, 32);
   } else if (warp == 2) {
@@ -365,26 +354,14 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     if (lane == 0) wbins[Z] = total;
     __syncthreads();
-    for (int i = tid; i <= Z; i += NT) {       // fixed-order combine: deterministic
+    // fixed-order combine of the warp-private bins (deterministic), handed to
+    // k_post through zone_sum[b, 0..Z]
+    double* zs = p.zone_sum + (size_t)b * (Z + 1);
+    for (int i = tid; i <= Z; i += NT) {
       double acc = 0.0;
 #pragma unroll
       for (int w = 1; w <= NW; ++w) acc += bins[(size_t)w * (Z + 1) + i];
-      bins[i] = acc;
-    }
-    __syncthreads();
-    if (warp == 0) {
-      const int32_t* ncv = p.zone_ncv + (size_t)plan * Z;
-      for (int zi = lane; zi < Z; zi += 32) {
-        const int n = ncv[zi];
-        const float m = n > 0 ? (float)(bins[zi] / (double)n) : 0.f;
-        zpost[zi] = m;
-        p.zone_mean[(size_t)b * Z + zi] = m;
-        p.qcv[(size_t)b * Z + zi] = p.qcv_next[(size_t)b * Z + zi];  // input_q for the next solve
-      }
-      const float gmean = (float)(bins[Z] / (double)n_cv);
-      if (lane == 0) p.global_mean[b] = gmean;
-      __syncwarp();
-      hvac_post(p, b, plan, lane, false, zpre, zpost, gmean, cy, scratch);
+      zs[i] = acc;
     }
   }
   if (use_tma && tid == 0) tma_store_wait();

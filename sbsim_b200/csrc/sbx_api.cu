@@ -50,6 +50,7 @@ struct sbx_env {
   // host-level episode state
   int step_count = 0, time_index = 0, episode_ended = 0, reset_called = 0;
   int therm_seen = 0, prev_comfort = 0;
+  int plans_dirty = 1;           // packed descriptors / vector lists need (re)building
   uint8_t* h_comfort = nullptr;  // host copy of the comfort table (for prev_comfort)
   // device allocations
   DevBuf all[64];
@@ -247,7 +248,20 @@ int run_stream_sweeps(sbx_handle h, cudaStream_t st) {
   return SBX_OK;
 }
 
+int prepare_plans(sbx_handle h, cudaStream_t st) {
+  if (!h->plans_dirty) return SBX_OK;
+  const Params& p = h->P;
+  const int wpb = 4;
+  const unsigned grid = (unsigned)((p.n_plans + wpb - 1) / wpb);
+  if (h->V == 4) k_prepare_plan<4><<<grid, wpb * 32, 0, st>>>(p);
+  else k_prepare_plan<1><<<grid, wpb * 32, 0, st>>>(p);
+  if (int rc = launch_check(h, "k_prepare_plan")) return rc;
+  h->plans_dirty = 0;
+  return SBX_OK;
+}
+
 int run_resident(sbx_handle h, cudaStream_t st) {
+  if (int rc = prepare_plans(h, st)) return rc;
   const Params& p = h->P;
   if (h->V == 4) k_resident_step<4><<<p.B, kResidentThreads, h->resident_smem, st>>>(p);
   else k_resident_step<1><<<p.B, kResidentThreads, h->resident_smem, st>>>(p);
@@ -357,10 +371,10 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   h->V = (c.width % 4 == 0) ? 4 : 1;
 
   // path selection
-  const ResidentLayout L = resident_layout((int)N, (int)Z);
+  const ResidentLayout L = resident_layout((int)N, (int)Z, h->V);
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const bool fits = L.total <= (size_t)max_optin && (c.width / h->V) <= kResidentThreads * 64;
+  const bool fits = L.total <= (size_t)max_optin && N / h->V <= 65535;
   if (c.kernel_path == SBX_PATH_RESIDENT && !fits) {
     fail(h, SBX_E_INVALID, "resident path needs %zu B of shared memory per CTA; device allows %d", L.total, max_optin);
     return bail(SBX_E_INVALID);
@@ -393,6 +407,9 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.zone_ncv, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.zone_ndiff, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.obs_zone_order, int32_t, (size_t)c.n_plans * Z);
+  ALLOC(p.desc_packed, uint16_t, (size_t)c.n_plans * N);
+  ALLOC(p.qlist, uint16_t, (size_t)c.n_plans * (N / h->V));
+  ALLOC(p.n_fast, int32_t, (size_t)c.n_plans);
   ALLOC(p.reset_temps, float, (size_t)c.n_reset * N);
   ALLOC(p.initial_temp, float, B);
   ALLOC(p.ambient, double, (size_t)c.n_weather * T);
@@ -567,6 +584,7 @@ int sbx_upload(sbx_handle h, int field, const void* src, size_t nbytes) {
   CUDA_TRY(h, cudaMemcpy(fi.ptr, src, nbytes, cudaMemcpyHostToDevice));
   if (field == SBX_F_TEMP) CUDA_TRY(h, cudaMemset(h->P.cur, 0, h->cfg.n_envs));
   if (field == SBX_F_COMFORT) memcpy(h->h_comfort, src, nbytes);
+  if (field == SBX_F_PLAN_DESC) h->plans_dirty = 1;
   return SBX_OK;
 }
 

@@ -41,7 +41,7 @@ struct __align__(16) Combo {
   // T_inf*h of the ambient-facing horizontal side (left OR right: no class has
   // both, so (x + hl) + hr == x + hh exactly) and of the vertical side
   float hh, hv, vz, uz;
-  float den, cm, pad0, pad1;     // cm = ((((rho*U)*V)*c)*z)*c
+  float den, cm, rden, pad1;     // cm = ((((rho*U)*V)*c)*z)*c ; rden = RN(1/den)
 };
 
 // Everything a kernel needs; passed by value.
@@ -73,6 +73,9 @@ struct Params {
   const int32_t* zone_ncv;   // [P,Z]
   const int32_t* zone_ndiff; // [P,Z]
   const int32_t* obs_zone_order;  // [P,Z]
+  uint16_t* desc_packed;     // [P,H,W] combo index | diffuser | zone (k_prepare_plan)
+  uint16_t* qlist;           // [P,H*W/V] fast vectors from the front, slow from the back
+  int32_t* n_fast;           // [P]
   const float* reset_temps;  // [n_reset,H,W]
   const float* initial_temp; // [B]
   // tables
@@ -134,6 +137,23 @@ __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b);
 __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
 __device__ __forceinline__ float fdiv(float a, float b) { return __fdiv_rn(a, b); }
 
+// Correctly rounded a / b for a divisor whose correctly rounded reciprocal
+// y = RN(1/b) is known (Markstein's FMA iteration).  q0 = RN(a*y) is within
+// 2 ulp of a/b; each step q <- RN(q + (a - b*q) * y) uses the EXACT residual
+// (FMA) and shrinks the error by 2^-24, so q1 is a faithful rounding and q2 is
+// the IEEE-754 round-to-nearest quotient (no overflow / underflow / zero divisor
+// in this kernel's value ranges).  5 issue slots instead of the ~13 of the
+// generic division sequence (MUFU.RCP + Newton + FCHK + slow-path branch).
+// Verified against IEEE division: tests/test_division.py (CPU, 1e8 samples) and
+// the bit-exact GPU parity tests.
+__device__ __forceinline__ float div_rn(float a, float b, float y) {
+  float q = __fmul_rn(a, y);
+  float r = __fmaf_rn(-q, b, a);
+  q = __fmaf_rn(r, y, q);
+  r = __fmaf_rn(-q, b, a);
+  return __fmaf_rn(r, y, q);
+}
+
 __device__ __forceinline__ int desc_class(uint32_t d) { return d & SBX_DESC_CLASS_MASK; }
 __device__ __forceinline__ int desc_material(uint32_t d) { return (d >> SBX_DESC_MATERIAL_SHIFT) & 3; }
 __device__ __forceinline__ int desc_zone(uint32_t d) { return (d >> SBX_DESC_ZONE_SHIFT) & 0xFF; }
@@ -191,7 +211,16 @@ __device__ inline Combo make_combo(int cls, const double* mat /*k,c,rho*/, doubl
   // :725-728; exactly one of (hl, hr) and one of (ht, hb) can be non-zero
   o.hh = sl ? mul(t_inf, hl) : mul(t_inf, hr);
   o.hv = sb ? mul(t_inf, hb) : mul(t_inf, ht);
-  o.pad0 = o.pad1 = 0.f;
+  o.rden = __frcp_rn(o.den);
+  o.pad1 = 0.f;
+  if (cls == SBX_CV_EXTERIOR) {
+    // apply_exterior_temps (:847-849) folded into the coefficients: with
+    // k = 0, hh = T_inf, vz = den = 1, cm = 0 the generic expression evaluates
+    // to exactly T_inf ((0*a + 0*b) + T_inf = T_inf; + 0 terms; / 1).
+    o.k1 = o.k3 = o.k2 = o.k4 = 0.f;
+    o.hh = t_inf; o.hv = 0.f; o.vz = 1.f; o.uz = 1.f;
+    o.den = 1.f; o.rden = 1.f; o.cm = 0.f;
+  }
   return o;
 }
 
@@ -210,28 +239,21 @@ __device__ __forceinline__ int combo_index(uint32_t d) {
   return desc_class(d) * kNumMaterials + desc_material(d);
 }
 
-struct ComboRegs {
-  float4 k;   // k1, k3, k2, k4
-  float4 h;   // hh, hv, vz, uz
-  float4 d;   // den, cm, -, -
-};
-
 // thermal-mass coefficient cm of a CV (for the n3 term)
 __device__ __forceinline__ float cv_cm(uint32_t d, const Combo* tab) {
   return tab[combo_index(d)].cm;
 }
 
 // One CV update (tf_simulator.py:719-754, 843, 847-849), branch-free: every
-// class runs the same instruction stream with its own coefficients (fetched as
-// three 128-bit shared-memory loads, broadcast when a warp shares a class), so
-// warps that mix interior / wall / boundary CVs do not diverge.
+// class runs the same instruction stream with its own coefficients (three
+// 128-bit shared-memory loads, broadcast when a warp shares a class), so warps
+// that mix interior / wall / boundary / exterior CVs do not diverge.
 //   t_jp = T(i,j+1), t_jm = T(i,j-1), t_im = T(i-1,j), t_ip = T(i+1,j)
 //   n3 = ((cm * T_prev) / dt)   precomputed (:743-749)
 //   q  = input_q at this CV (0 unless it is a diffuser)
-__device__ __forceinline__ float cv_update(uint32_t d, float t_jp, float t_jm, float t_im,
-                                           float t_ip, float n3, float q, float t_inf,
-                                           const Combo* tab) {
-  const float4* c4 = reinterpret_cast<const float4*>(tab + combo_index(d));
+__device__ __forceinline__ float cv_update_idx(int idx, float t_jp, float t_jm, float t_im,
+                                               float t_ip, float n3, float q, const Combo* tab) {
+  const float4* c4 = reinterpret_cast<const float4*>(tab + idx);
   const float4 k = c4[0], h = c4[1], dd = c4[2];
   float n1 = add(mul(k.x, t_jp), mul(k.y, t_jm));       // :719-720, 731
   n1 = add(n1, h.x);                                    // :732-733
@@ -240,8 +262,30 @@ __device__ __forceinline__ float cv_update(uint32_t d, float t_jp, float t_jm, f
   n2 = add(n2, h.y);                                    // :738-739
   n2 = mul(h.w, n2);                                    // :740
   const float num = add(add(add(n1, n2), n3), q);       // :752-754
-  const float t = fdiv(num, dd.x);                      // :843
-  return desc_class(d) == SBX_CV_EXTERIOR ? t_inf : t;  // :847-849
+  return div_rn(num, dd.x, dd.z);                       // :843
+}
+
+__device__ __forceinline__ float cv_update(uint32_t d, float t_jp, float t_jm, float t_im,
+                                           float t_ip, float n3, float q, float t_inf,
+                                           const Combo* tab) {
+  (void)t_inf;
+  return cv_update_idx(combo_index(d), t_jp, t_jm, t_im, t_ip, n3, q, tab);
+}
+
+// Interior CV of the dominant material with no heat input: coefficients are
+// uniform over the building and live in registers (tf_simulator.py:719-754 with
+// h = 0, k1 = k3 = k2 = k4 = k/dx, uz = vz).
+struct FastCoef {
+  float kq, vz, den, rden;
+};
+__device__ __forceinline__ float cv_update_fast(const FastCoef& f, float t_jp, float t_jm,
+                                                float t_im, float t_ip, float n3) {
+  float n1 = add(mul(f.kq, t_jp), mul(f.kq, t_jm));
+  n1 = mul(f.vz, n1);        // (x + 0) + 0 == x: the convection terms vanish
+  float n2 = add(mul(f.kq, t_ip), mul(f.kq, t_im));
+  n2 = mul(f.vz, n2);
+  const float num = add(add(n1, n2), n3);                // + q with q == 0 is exact
+  return div_rn(num, f.den, f.rden);
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -125,11 +125,11 @@ __device__ __forceinline__ void tma_store_wait() {
 // ---------------------------------------------------------------------------
 
 struct ResidentLayout {
-  size_t off_a, off_b, off_n3, off_desc, off_tab, off_qcv, off_bins, off_scratch, off_wmax,
-      off_zpre, off_zpost, off_bar, total;
+  size_t off_a, off_b, off_n3, off_desc, off_list, off_tab, off_qcv, off_bins, off_wmax,
+      off_bar, total;
 };
 
-__host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z) {
+__host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z, int V) {
   ResidentLayout L;
   auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
   size_t o = 0;
@@ -137,13 +137,11 @@ __host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z) {
   L.off_b = o; o = al(o + (size_t)n_cv * 4);
   L.off_n3 = o; o = al(o + (size_t)n_cv * 4);
   L.off_desc = o; o = al(o + (size_t)n_cv * 2);
+  L.off_list = o; o = al(o + (size_t)(n_cv / V) * 2);
   L.off_tab = o; o = al(o + sizeof(Combo) * kNumCombos);
   L.off_qcv = o; o = al(o + (size_t)(Z + 1) * 4);
   L.off_bins = o; o = al(o + (size_t)(Z + 1) * 8 * (kResidentThreads / 32 + 1));
-  L.off_scratch = o; o = al(o + (size_t)(3 * Z + 64) * 8);
-  L.off_wmax = o; o = al(o + 2 * 32 * 4);
-  L.off_zpre = o; o = al(o + (size_t)Z * 4);
-  L.off_zpost = o; o = al(o + (size_t)Z * 4);
+  L.off_wmax = o; o = al(o + 32 * 4);
   L.off_bar = o; o = al(o + 16);
   L.total = o;
   return L;
@@ -181,15 +179,17 @@ __device__ __forceinline__ void zone_accumulate_warp(const float (&t)[V], const 
   int z = SBX_ZONE_NONE;
   double s = 0.0;
   if (valid) {
-    z = desc_zone(d[0]);
-    s = (double)t[0];
-    total += (double)t[0];
+    // primary zone of the vector = its first CV that belongs to a room (walls and
+    // exterior carry SBX_ZONE_NONE); CVs of a second room in the same vector are
+    // flushed directly (needs two rooms within V cells: practically never)
 #pragma unroll
-    for (int e = 1; e < V; ++e) {
+    for (int e = 0; e < V; ++e) {
       const int ze = desc_zone(d[e]);
       total += (double)t[e];
+      if (ze == SBX_ZONE_NONE) continue;
+      if (z == SBX_ZONE_NONE) z = ze;
       if (ze == z) s += (double)t[e];
-      else if (ze != SBX_ZONE_NONE) atomicAdd(&wbins[ze], (double)t[e]);  // rare: boundary vector
+      else atomicAdd(&wbins[ze], (double)t[e]);
     }
   }
   const int z_prev = __shfl_up_sync(0xffffffffu, z, 1);
@@ -205,6 +205,120 @@ __device__ __forceinline__ void zone_accumulate_warp(const float (&t)[V], const 
   if (head && z != SBX_ZONE_NONE) atomicAdd(&wbins[z], s);
 }
 
+// Packed descriptor: combo index (5 bits) | diffuser flag | zone.
+__device__ __forceinline__ uint32_t repack_desc(uint32_t d) {
+  return (uint32_t)combo_index(d) | (d & SBX_DESC_DIFFUSER) | (d & 0xFF00u);
+}
+constexpr uint32_t kFastDesc = SBX_CV_INTERIOR | (0u << SBX_DESC_MATERIAL_SHIFT);  // interior, air, no diffuser
+
+// Once per uploaded plan: repack the descriptors and split the plan's vectors
+// into a FAST list (every CV interior, air, no heat input: uniform register
+// coefficients, all four neighbours in range by construction) and a SLOW list
+// (generic, table-driven).  Both lists share one array: fast ascending from the
+// front, slow from the back.  One warp per plan => deterministic order.
+template <int V>
+__global__ void k_prepare_plan(const Params p) {
+  const int plan = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (plan >= p.n_plans) return;
+  const int n_cv = p.H * p.W, n_items = n_cv / V;
+  const uint16_t* raw = p.desc + (size_t)plan * n_cv;
+  uint16_t* packed = p.desc_packed + (size_t)plan * n_cv;
+  uint16_t* qlist = p.qlist + (size_t)plan * n_items;
+  int nf = 0, ns = 0;
+  for (int base_it = 0; base_it < n_items; base_it += 32) {
+    const int it = base_it + lane;
+    const bool valid = it < n_items;
+    bool fast = valid;
+    if (valid) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const uint32_t d = raw[it * V + e];
+        fast = fast && ((d & 0x007Fu) == kFastDesc);
+        packed[it * V + e] = (uint16_t)repack_desc(d);
+      }
+    }
+    const unsigned mf = __ballot_sync(0xffffffffu, fast);
+    const unsigned ms = __ballot_sync(0xffffffffu, valid && !fast);
+    const unsigned below = (1u << lane) - 1u;
+    if (fast) qlist[nf + __popc(mf & below)] = (uint16_t)it;
+    else if (valid) qlist[n_items - 1 - (ns + __popc(ms & below))] = (uint16_t)it;
+    nf += __popc(mf);
+    ns += __popc(ms);
+  }
+  if (lane == 0) p.n_fast[plan] = nf;
+}
+
+// One Jacobi sweep over the CTA's building.  FIRST: `in` is T_prev itself, so
+// n3 = (cm * T_prev) / dt (tf_simulator.py:743-749) is computed here and stored
+// for the following sweeps instead of being loaded.
+template <int V, bool FIRST>
+__device__ __forceinline__ float resident_sweep(
+    const float* __restrict__ in, float* __restrict__ out, float* __restrict__ n3p,
+    const uint16_t* __restrict__ dsc, const uint16_t* __restrict__ qlist, const Combo* tab,
+    const float* qcv, const FastCoef& fc, float cm_fast, float dt, float rdt, float t_inf,
+    int n_fast, int n_items, int H, int W, int Z, unsigned wq_magic, int tid) {
+  constexpr int NT = kResidentThreads;
+  const int wq = W / V;
+  float lmax = 0.f;
+  for (int i = tid; i < n_fast; i += NT) {
+    const int base = (int)qlist[i] * V;
+    float c[V], up[V], dn[V], n3v[V], o[V];
+    load_f<V>(in + base, c);
+    load_f<V>(in + base - W, up);
+    load_f<V>(in + base + W, dn);
+    if constexpr (FIRST) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) n3v[e] = div_rn(mul(cm_fast, c[e]), dt, rdt);
+      store_f<V>(n3p + base, n3v);
+    } else {
+      load_f<V>(n3p + base, n3v);
+    }
+    const float left = in[base - 1];
+    const float right = in[base + V];
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float t_jm = e == 0 ? left : c[e - 1];
+      const float t_jp = e == V - 1 ? right : c[e + 1];
+      o[e] = cv_update_fast(fc, t_jp, t_jm, up[e], dn[e], n3v[e]);
+      lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));                       // :851-853
+    }
+    store_f<V>(out + base, o);
+  }
+  const int n_slow = n_items - n_fast;
+  for (int i = tid; i < n_slow; i += NT) {
+    const int it = (int)qlist[n_items - 1 - i];
+    const int base = it * V;
+    const int r = (int)__umulhi((unsigned)it, wq_magic);
+    const int q = it - r * wq;
+    float c[V], up[V], dn[V], n3v[V], o[V];
+    uint32_t d[V];
+    load_f<V>(in + base, c);
+    load_d<V>(dsc + base, d);
+    if constexpr (FIRST) {
+#pragma unroll
+      for (int e = 0; e < V; ++e) n3v[e] = div_rn(mul(tab[d[e] & 31u].cm, c[e]), dt, rdt);
+      store_f<V>(n3p + base, n3v);
+    } else {
+      load_f<V>(n3p + base, n3v);
+    }
+    if (r > 0) load_f<V>(in + base - W, up); else fill<V>(up, t_inf);         // :642-644
+    if (r < H - 1) load_f<V>(in + base + W, dn); else fill<V>(dn, t_inf);     // :646
+    const float left = q > 0 ? in[base - 1] : t_inf;                          // :638-640
+    const float right = q < wq - 1 ? in[base + V] : t_inf;                    // :636
+#pragma unroll
+    for (int e = 0; e < V; ++e) {
+      const float t_jm = e == 0 ? left : c[e - 1];
+      const float t_jp = e == V - 1 ? right : c[e + 1];
+      const int slot = (d[e] & SBX_DESC_DIFFUSER) ? (int)(d[e] >> SBX_DESC_ZONE_SHIFT) : Z;
+      o[e] = cv_update_idx((int)(d[e] & 31u), t_jp, t_jm, up[e], dn[e], n3v[e], qcv[slot], tab);
+      lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));
+    }
+    store_f<V>(out + base, o);
+  }
+  return lmax;
+}
+
 template <int V>
 __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
@@ -213,46 +327,50 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   constexpr int NT = kResidentThreads, NW = NT / 32;
   const int H = p.H, W = p.W, Z = p.Z;
   const int n_cv = H * W;
+  const int n_items = n_cv / V;
   const int plan = p.n_plans == 1 ? 0 : b;
-  const ResidentLayout L = resident_layout(n_cv, Z);
+  const ResidentLayout L = resident_layout(n_cv, Z, V);
   float* bufA = reinterpret_cast<float*>(smem + L.off_a);
   float* bufB = reinterpret_cast<float*>(smem + L.off_b);
   float* n3p = reinterpret_cast<float*>(smem + L.off_n3);
   uint16_t* dsc = reinterpret_cast<uint16_t*>(smem + L.off_desc);
+  uint16_t* qlist = reinterpret_cast<uint16_t*>(smem + L.off_list);
   Combo* tab = reinterpret_cast<Combo*>(smem + L.off_tab);
   float* qcv = reinterpret_cast<float*>(smem + L.off_qcv);
   double* bins = reinterpret_cast<double*>(smem + L.off_bins);
-  double* scratch = reinterpret_cast<double*>(smem + L.off_scratch);
   float* wmax = reinterpret_cast<float*>(smem + L.off_wmax);
-  float* zpre = reinterpret_cast<float*>(smem + L.off_zpre);
-  float* zpost = reinterpret_cast<float*>(smem + L.off_zpost);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
 
   float* gT = p.tbuf[0] + (size_t)b * n_cv;
-  const uint16_t* gD = p.desc + (size_t)plan * n_cv;
-  const bool use_tma = (n_cv % 8) == 0;
+  const uint16_t* gD = p.desc_packed + (size_t)plan * n_cv;
+  const uint16_t* gL = p.qlist + (size_t)plan * n_items;
+  const bool use_tma = (n_cv % 8) == 0 && (n_items % 8) == 0;
 
-  // ---- stage 0: start the bulk loads ---------------------------------------
+  // ---- stage 0: start the bulk loads (TMA, one mbarrier) ----------------------
   if (use_tma) {
     if (tid == 0) {
       mbar_init(bar, 1);
-      mbar_expect_tx(bar, (uint32_t)(n_cv * 4 + n_cv * 2));
+      mbar_expect_tx(bar, (uint32_t)(n_cv * 4 + n_cv * 2 + n_items * 2));
       tma_load_1d(bufA, gT, (uint32_t)(n_cv * 4), bar);
       tma_load_1d(dsc, gD, (uint32_t)(n_cv * 2), bar);
+      tma_load_1d(qlist, gL, (uint32_t)(n_items * 2), bar);
     }
   } else {
     for (int i = tid; i < n_cv; i += NT) {
       bufA[i] = gT[i];
       dsc[i] = gD[i];
     }
+    for (int i = tid; i < n_items; i += NT) qlist[i] = gL[i];
   }
 
   // ---- stage 1: per-building constants while the copies are in flight ---------
   const double amb_d = env_ambient(p, b, p.time_index);
   const float t_inf = (float)amb_d;                       // tf_simulator.py:785
   const float h = (float)env_convection(p, b);
+  const int n_fast = p.n_fast[plan];
   if (warp == 0) {
     for (int zi = lane; zi < Z; zi += 32) qcv[zi] = p.qcv[(size_t)b * Z + zi];
+    if (lane == 0) qcv[Z] = 0.f;                          // slot Z: "no heat input"
   } else if (warp == 1) {
     build_combo_table(tab, p, plan, b, h, t_inf, lane, 32);
   } else if (warp == 2) {
@@ -260,55 +378,30 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   }
   __syncthreads();
   if (use_tma) mbar_wait(bar, 0);
-
-  // ---- stage 2: n3 = (cm * T_prev) / dt  (tf_simulator.py:743-749) ----------
-  const int n_items = n_cv / V;
-  for (int it = tid; it < n_items; it += NT) {
-    float t[V], o[V];
-    uint32_t d[V];
-    load_f<V>(bufA + it * V, t);
-    load_d<V>(dsc + it * V, d);
-#pragma unroll
-    for (int e = 0; e < V; ++e) o[e] = fdiv(mul(cv_cm(d[e], tab), t[e]), p.dt);
-    store_f<V>(n3p + it * V, o);
+  FastCoef fc;
+  {
+    const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + 0];
+    fc.kq = c.k1; fc.vz = c.vz; fc.den = c.den; fc.rden = c.rden;
   }
-  __syncthreads();
+  const float cm_fast = tab[SBX_CV_INTERIOR * kNumMaterials + 0].cm;
+  const float rdt = __frcp_rn(p.dt);
+  const unsigned wq_magic = 0xFFFFFFFFu / (unsigned)(W / V) + 1u;   // it / wq for it < 2^16
 
-  // ---- stage 3: Jacobi sweeps to convergence (simulator.py:348-364) ---------
+  // ---- stage 2: Jacobi sweeps to convergence (simulator.py:348-364) ---------
   float* in = bufA;
   float* out = bufB;
-  const int wq = W / V;
   int k = 0;
   float md = 0.f, last_lmax = 0.f;
   const int limit = p.iteration_limit;
   while (k < limit) {
     ++k;
-    float lmax = 0.f;
-    int r = tid / wq, q = tid - r * wq;
-    const int dr = NT / wq, dq = NT - dr * wq;
-    for (int it = tid; it < n_items; it += NT) {
-      const int base = it * V;
-      float c[V], up[V], dn[V], n3v[V], o[V];
-      uint32_t d[V];
-      load_f<V>(in + base, c);
-      load_d<V>(dsc + base, d);
-      load_f<V>(n3p + base, n3v);
-      if (r > 0) load_f<V>(in + base - W, up); else fill<V>(up, t_inf);       // :642-644
-      if (r < H - 1) load_f<V>(in + base + W, dn); else fill<V>(dn, t_inf);   // :646
-      const float left = q > 0 ? in[base - 1] : t_inf;                        // :638-640
-      const float right = q < wq - 1 ? in[base + V] : t_inf;                  // :636
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const float t_jm = e == 0 ? left : c[e - 1];
-        const float t_jp = e == V - 1 ? right : c[e + 1];
-        const float qv = (d[e] & SBX_DESC_DIFFUSER) ? qcv[desc_zone(d[e])] : 0.f;
-        o[e] = cv_update(d[e], t_jp, t_jm, up[e], dn[e], n3v[e], qv, t_inf, tab);
-        lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));                     // :851-853
-      }
-      store_f<V>(out + base, o);
-      r += dr; q += dq;
-      if (q >= wq) { q -= wq; ++r; }
-    }
+    float lmax;
+    if (k == 1)
+      lmax = resident_sweep<V, true>(in, out, n3p, dsc, qlist, tab, qcv, fc, cm_fast, p.dt, rdt,
+                                     t_inf, n_fast, n_items, H, W, Z, wq_magic, tid);
+    else
+      lmax = resident_sweep<V, false>(in, out, n3p, dsc, qlist, tab, qcv, fc, cm_fast, p.dt, rdt,
+                                      t_inf, n_fast, n_items, H, W, Z, wq_magic, tid);
     // max|dT| <= threshold  <=>  no thread saw a delta above it (simulator.py:362);
     // the barrier doubles as the ping-pong hazard fence.
     const int above = __syncthreads_or(lmax > p.threshold);
@@ -316,29 +409,20 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     float* tmp = in; in = out; out = tmp;
     if (!above) break;
   }
-  // block max of the last sweep (diagnostic SBX_F_MAX_DELTA)
-  last_lmax = warp_max(last_lmax);
-  if (lane == 0) wmax[warp] = last_lmax;
-  __syncthreads();
-  md = 0.f;
-#pragma unroll
-  for (int w = 0; w < NW; ++w) md = fmaxf(md, wmax[w]);
   // `in` now holds building.temp for the next step (simulator.py:369)
 
-  // ---- stage 4: write back + zone reductions + epilogue ---------------------
+  // ---- stage 3: write back + zone / grid sums ---------------------------------
   if (use_tma) {
     if (tid == 0) tma_store_1d(gT, in, (uint32_t)(n_cv * 4));
   } else {
     for (int i = tid; i < n_cv; i += NT) gT[i] = in[i];
   }
-  if (tid == 0) {
-    p.n_sweeps[b] = k;
-    p.max_delta[b] = md;
-    if (!p.fd_only) atomicAdd(p.sweeps_total, (unsigned long long)k);
-  }
+  // block max of the last sweep (diagnostic SBX_F_MAX_DELTA)
+  last_lmax = warp_max(last_lmax);
+  if (lane == 0) wmax[warp] = last_lmax;
+  double total = 0.0;
+  double* wbins = bins + (size_t)(warp + 1) * (Z + 1);   // warp-private bins
   if (!p.fd_only) {
-    double total = 0.0;
-    double* wbins = bins + (size_t)(warp + 1) * (Z + 1);   // warp-private bins
     for (int base_it = warp * 32; base_it < n_items; base_it += NT) {
       const int it = base_it + lane;
       const bool valid = it < n_items;
@@ -353,7 +437,17 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     if (lane == 0) wbins[Z] = total;
-    __syncthreads();
+  }
+  __syncthreads();
+  if (tid == 0) {
+    md = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w) md = fmaxf(md, wmax[w]);
+    p.n_sweeps[b] = k;
+    p.max_delta[b] = md;
+    if (!p.fd_only) atomicAdd(p.sweeps_total, (unsigned long long)k);
+  }
+  if (!p.fd_only) {
     // fixed-order combine of the warp-private bins (deterministic), handed to
     // k_post through zone_sum[b, 0..Z]
     double* zs = p.zone_sum + (size_t)b * (Z + 1);

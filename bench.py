@@ -184,8 +184,8 @@ def run_sbx(args):
   sptr = stream.cuda_stream
   gathered = None
   if world > 1 and args.allgather:
-    gathered = (torch.zeros((world, B, D), device=dev), torch.zeros((world, B), device=dev),
-                torch.zeros((world, B), dtype=torch.int32, device=dev))
+    from sbsim_b200 import distributed
+    gathered = distributed.TimeStepGather(obs, rew, st)
 
   def barrier():
     if world > 1:
@@ -195,9 +195,7 @@ def run_sbx(args):
   def one_step(i):
     env.step_device(actions[i], obs, rew, st, dis, stream=sptr)
     if gathered is not None:
-      dist.all_gather_into_tensor(gathered[0], obs)
-      dist.all_gather_into_tensor(gathered[1], rew)
-      dist.all_gather_into_tensor(gathered[2], st)
+      gathered(obs, rew, st)
 
   # ---- device-resident timing (value) ----
   env.reset_device(obs, rew, st, dis, stream=sptr)

@@ -1,0 +1,168 @@
+"""Host-side logic of sbsim_b200 (no GPU): exogenous tables against the oracle's
+scalar restatements, config validation, floor-plan compiler invariants."""
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import sbsim_b200 as sbx
+from sbsim_b200 import exogenous, floorplan, workloads
+from oracle import exogenous as oex
+from oracle import hvac as ohvac
+from oracle import tf_jacobi
+import scenarios as S
+
+
+def _ts(start, n, tz=None):
+  t0 = pd.Timestamp(start, tz=tz)
+  return exogenous.step_timestamps(t0, 300.0, n)
+
+
+def test_sinusoid_weather_table_matches_oracle_scalar():
+  ts = _ts("2023-07-06 07:00:00", 400)
+  w = sbx.WeatherController(275.0, 290.0, special_days={188: (270.0, 280.0)})
+  o = oex.WeatherController(275.0, 290.0, special_days={188: (270.0, 280.0)})
+  np.testing.assert_array_equal(w.table(ts), [o.get_current_temp(t) for t in ts])
+  # reference KATs (weather_controller_test.py:79-122): low at midnight, high at noon
+  w2 = sbx.WeatherController(273.0, 283.0)
+  assert w2.get_current_temp(pd.Timestamp("2021-05-09 00:00")) == pytest.approx(273.0)
+  assert w2.get_current_temp(pd.Timestamp("2021-05-09 12:00")) == pytest.approx(283.0)
+  assert w2.get_current_temp(pd.Timestamp("2021-05-09 06:00")) == pytest.approx(278.0)
+
+
+def test_batched_sinusoid_tables_match_per_building_controllers():
+  ts = _ts("2023-07-06 07:00:00", 300)
+  rng = np.random.default_rng(0)
+  low = rng.uniform(268, 288, 5)
+  high = low + rng.uniform(5, 15, 5)
+  tab = exogenous.sinusoid_weather_tables(ts, low, high)
+  for b in range(5):
+    o = oex.WeatherController(low[b], high[b])
+    np.testing.assert_array_equal(tab[b], [o.get_current_temp(t) for t in ts])
+
+
+def test_replay_weather_matches_oracle_and_raises_out_of_range():
+  g = np.load(S.__file__.replace("scenarios.py", "golden/sb1_calibrated.npz"))
+  w = sbx.ReplayWeatherController(times_utc_sec=g["weather_time_sec"],
+                                  temps_f=g["weather_temp_f"], convection_coefficient=100.0)
+  o = oex.ReplayWeatherController(g["weather_time_sec"], g["weather_temp_f"], 100.0)
+  ts = _ts("2023-07-06 07:00:00", 288, tz="UTC")
+  np.testing.assert_array_equal(w.table(ts), [o.get_current_temp(t) for t in ts])
+  with pytest.raises(ValueError, match="before"):
+    w.get_current_temp(pd.Timestamp("2023-06-01 00:00:00", tz="UTC"))
+  with pytest.raises(ValueError, match="after"):
+    w.get_current_temp(pd.Timestamp("2023-12-01 00:00:00", tz="UTC"))
+
+
+@pytest.mark.parametrize("tz,start_tz", [("UTC", None), ("US/Pacific", "UTC")])
+def test_schedule_table_matches_oracle(tz, start_tz):
+  ts = _ts("2023-07-06 07:00:00", 3 * 288, tz=start_tz)   # Thursday .. Sunday
+  s = sbx.SetpointSchedule(6, 19, (294, 297), (289, 298), time_zone=tz)
+  o = ohvac.SetpointSchedule(6, 19, (294, 297), (289, 298), time_zone=tz)
+  tab = s.table(ts)
+  assert list(tab) == [int(o.is_comfort_mode(t)) for t in ts]
+  assert 0 < tab.sum() < len(tab)
+  with pytest.raises(ValueError, match="morning_start_hour"):
+    sbx.SetpointSchedule(20, 19, (294, 297), (289, 298))
+
+
+def test_occupancy_and_energy_tables_match_oracle():
+  ts = _ts("2023-07-06 05:00:00", 600)
+  occ = sbx.StepFunctionOccupancy(pd.Timedelta(9, unit="h"), pd.Timedelta(17, unit="h"), 1.0, 0.1)
+  o = oex.StepFunctionOccupancy(pd.Timedelta(9, unit="h"), pd.Timedelta(17, unit="h"), 1.0, 0.1)
+  zones = ["zone_id_1", "zone_id_2", "zone_id_3"]
+  rew, obs = exogenous.occupancy_tables(occ, zones, ts, 300.0, per_zone=False)
+  dt = pd.Timedelta(300, unit="s")
+  five = pd.Timedelta(5, unit="minute")
+  for s in range(0, 600, 7):
+    assert rew[s, 0] == o.average_zone_occupancy("z", ts[s], ts[s] + dt)
+    n = 0.0
+    for _ in zones:
+      n += o.average_zone_occupancy("z", ts[s] - five, ts[s])
+    assert obs[s] == int(n)
+  pe, ce, pg = exogenous.energy_tables(sbx.ElectricityEnergyCost(), sbx.NaturalGasEnergyCost(), ts)
+  oe, og = oex.ElectricityEnergyCost(), oex.NaturalGasEnergyCost()
+  for s in range(0, 600, 11):
+    utc = pd.Timestamp(int(ts[s].timestamp()), unit="s", tz="UTC")
+    assert pe[s] * 1000.0 * 300.0 == oe.cost(utc, utc + dt, 1000.0)
+    assert ce[s] * 1000.0 * 300.0 == oe.carbon(utc, utc + dt, 1000.0)
+    assert pg[s] * (1000.0 * 300.0) == og.cost(utc, utc + dt, 1000.0)
+  # reference KATs (electricity_energy_cost_test.py / natural_gas_energy_cost_test.py values)
+  assert sbx.NaturalGasEnergyCost().carbon_rate == pytest.approx(53.12 / 293.07107 / 3.6e6)
+
+
+def test_time_features_match_oracle():
+  ts = _ts("2023-07-06 07:00:00", 300, tz="UTC")
+  tab = exogenous.time_feature_table(ts)
+  for s in range(0, 300, 13):
+    hod = oex.expand_time_features(1, oex.get_radian_time(ts[s], "hod"))
+    dow = oex.expand_time_features(1, oex.get_radian_time(ts[s], "dow"))
+    np.testing.assert_array_equal(tab[s], hod + dow)
+
+
+def test_config_validation_errors_mirror_reference():
+  with pytest.raises(ValueError, match="cooling_air_temp_setpoint must greater"):
+    sbx.AirHandler(0.3, 298, 285, 10000.0, 0.9)
+  with pytest.raises(ValueError, match="default_low_temp"):
+    sbx.WeatherController(300.0, 290.0)
+  n = sbx.BoundedActionNormalizer(310, 355.0)
+  assert n.setpoint_value(np.float32(-1.0)) == 310.0 and n.setpoint_value(np.float32(1.0)) == 355.0
+  assert n.agent_value(332.5) == pytest.approx(0.0)
+  with pytest.raises(ValueError, match="not within bounds"):
+    n.setpoint_value(np.float32(1.1))
+  with pytest.raises(ValueError, match="expected to be scalar"):
+    n.setpoint_value(np.zeros(2, dtype=np.float32))
+  with pytest.raises(ValueError, match="not within bounds"):
+    n.agent_value(400.0)
+  norm = sbx.StandardScoreObservationNormalizer({"a": (1.1, 2.2)})
+  assert norm.get("a") == (float(np.float32(1.1)), float(np.float32(2.2)))   # proto float fields
+  assert norm.get("unknown") == (0.0, 1.0)
+
+
+def test_floorplan_compiler_invariants_and_classes():
+  cp = S.Scenario(floor_plan=S.TF_TEST_PLAN, buffer_from_walls=0).compiled()
+  # classes by the rules of tf_simulator.py:208-243 on the plan of tf_simulator_test.py:36-52
+  assert cp.cv_class[1, 1] == floorplan.CV_CORNER_TL       # has (2,1) and (1,2)
+  assert cp.cv_class[1, 2] == floorplan.CV_CORNER_TR       # has (2,2) and (1,1); (1,3) is exterior
+  assert cp.cv_class[2, 1] == floorplan.CV_EDGE_LEFT       # missing (2,0)
+  assert cp.cv_class[8, 3] == floorplan.CV_EDGE_BOTTOM     # missing (9,3)
+  assert cp.cv_class[3, 3] == floorplan.CV_INTERIOR
+  assert cp.cv_class[0, 0] == floorplan.CV_EXTERIOR
+  np.testing.assert_array_equal(cp.cv_class, tf_jacobi.classify(cp.exterior_space))
+  assert cp.n_zones == 4 and list(cp.zone_ncv) == [5, 5, 4, 4]
+  # descriptor packing round trip
+  d = cp.desc.astype(np.int64)
+  np.testing.assert_array_equal(d & 15, cp.cv_class)
+  np.testing.assert_array_equal((d >> 4) & 3, cp.material_id)
+  np.testing.assert_array_equal(((d >> 8) & 255), np.where(cp.zone_id >= 0, cp.zone_id, 255))
+  np.testing.assert_array_equal((d & 0x40) != 0, cp.diffuser_weight > 0)
+  for zi in range(cp.n_zones):
+    w = cp.diffuser_weight[cp.zone_id == zi]
+    if cp.zone_ndiff[zi]:
+      assert w.sum() == pytest.approx(1.0)
+  # a 2-neighbour CV whose neighbours are opposite has no class (tf_simulator.py:219-221)
+  bad = np.full((5, 5), 2)
+  bad[1:4, 2] = 1
+  with pytest.raises(ValueError, match="wasn't able to determine"):
+    floorplan.classify_cvs(bad == 2)
+  # walls touching the frame get an air ring (building_utils.py:144-219)
+  tight = np.ones((6, 6), dtype=np.int64)
+  tight[1:5, 1:5] = 0
+  assert floorplan.guarantee_air_padding_in_frame(tight).shape == (8, 8)
+
+
+def test_randomized_workload_is_seeded_and_packs():
+  a = workloads.randomized(16, seed=5, n_layouts=4)
+  b = workloads.randomized(16, seed=5, n_layouts=4)
+  assert all(np.array_equal(x.desc, y.desc) for x, y in zip(a.plans, b.plans))
+  np.testing.assert_array_equal(a.weather_low, b.weather_low)
+  packed = floorplan.pack_plans(a.plans)
+  assert packed["plan_desc"].shape == (16, 64, 96)
+  assert packed["zone_ncv"].shape[0] == 16 and (packed["zone_ncv"].sum(1) > 0).all()
+  assert not np.array_equal(a.plans[0].material, a.plans[4].material)  # same layout, own materials
+
+
+def test_environment_rejects_bad_discount_before_touching_the_gpu():
+  sc = S.Scenario(floor_plan=S.small_plan(), discount=1.5)
+  with pytest.raises(ValueError, match=r"Discount factor must be in \(0,1\]"):
+    S.make_env(sc)

@@ -1,0 +1,101 @@
+"""Live checks against the UNMODIFIED reference (only where /root/reference is
+mounted; skipped on the GPU box, which relies on the committed goldens instead)."""
+
+import warnings
+
+import numpy as np
+import pandas as pd
+import pytest
+
+from oracle import refshim
+from oracle import tf_jacobi
+from sbsim_b200 import floorplan
+import scenarios as S
+
+pytestmark = pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+
+
+@pytest.fixture(scope="module")
+def ref():
+  warnings.filterwarnings("ignore")
+  from oracle import make_golden
+  return make_golden._ref_modules()
+
+
+def _ref_building(ref, plan, cv=20.0, bfw=3):
+  bp = ref["building"]
+  return bp.FloorPlanBasedBuilding(
+      cv_size_cm=cv, floor_height_cm=300.0, initial_temp=292.0,
+      inside_air_properties=bp.MaterialProperties(50.0, 700.0, 1.0),
+      inside_wall_properties=bp.MaterialProperties(2.0, 1000.0, 1800.0),
+      building_exterior_properties=bp.MaterialProperties(0.05, 1000.0, 3000.0),
+      floor_plan=plan, zone_map=plan.copy(), buffer_from_walls=bfw)
+
+
+@pytest.mark.parametrize("seed", [0, 1, 2, 3])
+def test_static_compiler_matches_reference_building(ref, seed):
+  rng = np.random.default_rng(seed)
+  spec = floorplan.RandomPlanSpec(40, 56, (1, 2), (2, 3), 5) if seed % 2 else floorplan.RandomPlanSpec()
+  plan = floorplan.random_floor_plan(rng, spec).astype(np.int64)
+  b = _ref_building(ref, plan, cv=10.0)
+  cp = S.Scenario(floor_plan=plan, cv_size_cm=10.0, buffer_from_walls=3).compiled()
+  np.testing.assert_array_equal(cp.exterior_space, b._exterior_space == -1)
+  np.testing.assert_array_equal(cp.dense_material(0), b.conductivity)
+  np.testing.assert_array_equal(cp.dense_material(1), b.heat_capacity)
+  np.testing.assert_array_equal(cp.dense_material(2), b.density)
+  np.testing.assert_array_equal(cp.diffuser_weight, b.diffusers)
+  rooms = [k for k in b._room_dict if k.startswith("room")]
+  assert rooms == cp.zone_names
+  for zi, k in enumerate(rooms):
+    r, c = cp.zone_indices(zi)
+    assert [tuple(x) for x in b._room_dict[k]] == list(zip(r.tolist(), c.tolist()))
+  # classes against the reference's classify_cv
+  tfs = ref["tfs"]
+  codes = {("EDGE", "TOP"): 2, ("EDGE", "BOTTOM"): 3, ("EDGE", "LEFT"): 4, ("EDGE", "RIGHT"): 5,
+           ("CORNER", "TOP_LEFT"): 6, ("CORNER", "BOTTOM_LEFT"): 7, ("CORNER", "TOP_RIGHT"): 8,
+           ("CORNER", "BOTTOM_RIGHT"): 9}
+  for (i, j), t in tfs.get_cv_mapping(b.neighbors, tfs.CVPositionType.BOUNDARY).items():
+    assert cp.cv_class[i, j] == codes[(t.boundary.name, (t.edge or t.corner).name)]
+  ext = tfs.get_cv_mapping(b.neighbors, tfs.CVPositionType.EXTERIOR)
+  assert set(ext) == set(map(tuple, np.argwhere(cp.cv_class == 0)))
+
+
+def test_tf_sweep_restatement_is_bit_identical_to_reference_code(ref):
+  """Unmodified TFSimulator.update_temperature_estimates (tf_simulator.py:573-853) on
+  the NumPy provider of its TF primitives vs oracle/tf_jacobi.py, random fields."""
+  rng = np.random.default_rng(7)
+  plan = S.small_plan()
+  b = _ref_building(ref, plan, bfw=2)
+  hv = ref["hvac"].FloorPlanBasedHvac(
+      air_handler=ref["ah"].AirHandler(0.3, 285, 298, 10000.0, 0.9),
+      boiler=ref["bl"].Boiler(360.0, 6.0, 0.98), schedule=ref["ss"].SetpointSchedule(
+          6, 19, (294, 297), (289, 298)),
+      vav_max_air_flow_rate=0.035, vav_reheat_max_water_flow_rate=0.03)
+  w = ref["wc"].WeatherController(275.0, 290.0)
+  sim = ref["tfs"].TFSimulator(b, hv, w, 300.0, 0.1, 100, 30, pd.Timestamp("2023-07-06"))
+  cp = S.Scenario(floor_plan=plan).compiled()
+  jac = tf_jacobi.TFJacobi(S.oracle_plan(cp, 300.0), 300.0, 0.1, 100)
+  for _ in range(5):
+    b.temp = rng.uniform(280, 300, plan.shape)
+    b.input_q = np.where(b.diffusers > 0, rng.uniform(-100, 900, plan.shape), 0.0)
+    est = rng.uniform(280, 300, plan.shape)
+    amb, h = float(rng.uniform(270, 300)), float(rng.uniform(5, 100))
+    want, wmd = sim.update_temperature_estimates(est.copy(), amb, h)
+    got, gmd = jac.sweep(est, b.temp, b.input_q, amb, h)
+    np.testing.assert_array_equal(got, want)
+    assert gmd == wmd
+
+
+def test_oracle_env_matches_live_reference_env(ref):
+  from oracle import make_golden
+  env, b = make_golden.build_reference_env(ref, S.small_plan(), "tf", histogram=True)
+  o = S.make_oracle(S.Scenario(floor_plan=S.small_plan(), histogram=True))
+  rts, ots = env.reset(), o.reset()
+  np.testing.assert_allclose(ots[3], rts.observation, rtol=1e-6, atol=1e-7)
+  rng = np.random.default_rng(5)
+  for _ in range(15):
+    a = rng.uniform(-1, 1, 2).astype(np.float32)
+    rts, ots = env.step(a), o.step(a)
+    np.testing.assert_allclose(ots[3], rts.observation, rtol=1e-6, atol=1e-7)
+    np.testing.assert_allclose(float(ots[1]), float(rts.reward), rtol=1e-6, atol=1e-9)
+    np.testing.assert_array_equal(np.asarray(o.temp), np.asarray(b.temp))

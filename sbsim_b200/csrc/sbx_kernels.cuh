@@ -286,7 +286,10 @@ __device__ __forceinline__ float resident_sweep(
     store_f<V>(out + base, o);
   }
   const int n_slow = n_items - n_fast;
-  for (int i = tid; i < n_slow; i += NT) {
+  // slow vectors are dealt from the LAST thread downwards: the fast loop leaves the
+  // low thread ids with one more iteration, so this evens out the work per warp
+  // before the sweep barrier
+  for (int i = NT - 1 - tid; i < n_slow; i += NT) {
     const int it = (int)qlist[n_items - 1 - i];
     const int base = it * V;
     const int r = (int)__umulhi((unsigned)it, wq_magic);

@@ -267,9 +267,18 @@ def run_sbx(args):
     launch_ms = statistics.mean(per_step_ms)
     bytes_launch = bytes_step * B
     achieved = bytes_launch / (launch_ms / 1e3) / 1e9
+  traffic = None
+  try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this B
+    with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+      tr = json.load(f).get(args.workload)
+    if tr and resident:
+      traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * B / tr["launch_envs"]
+  except Exception:  # pylint: disable=broad-except
+    traffic = None
   roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
               "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
-              "traffic": None, "algorithmic_bytes_per_env_step": bytes_step,
+              "traffic": traffic, "algorithmic_bytes_per_launch": bytes_launch,
+              "algorithmic_bytes_per_env_step": bytes_step,
               "mean_sweeps_per_step": mean_sweeps,
               "launch_ms": launch_ms}
 
@@ -317,7 +326,7 @@ def cpu_baseline(args, wl, K):
   """The oracle (CPU restatement of the reference) on a bounded sample."""
   from oracle import bench_support
   cores = bench_support.host_cores()
-  n = args.cpu_sample_envs or max(cores * 2, 8)
+  n = args.cpu_sample_envs or min(max(cores * 128, 256), 4096)   # ~10 s of CPU work incl. set-up
   n = min(n, len(wl.plans))
   rate, total, wall, sweeps = bench_support.time_oracle(
       _oracle_specs(wl, n, K + 8), K, n_procs=cores)
@@ -341,7 +350,7 @@ def run_reference(args):
                       "reference arm implemented for the randomized workload only"}))
     return
   cores = bench_support.host_cores()
-  n = args.cpu_sample_envs or max(cores * 2, 8)
+  n = args.cpu_sample_envs or min(max(cores * 128, 256), 4096)
   W, K = args.warmup, args.steps
   # bound the run: ~250 env-steps/s/core => keep total env-steps near 30 s of work
   budget = int(250 * cores * 30)

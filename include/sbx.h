@@ -248,8 +248,9 @@ int sbx_reset(sbx_handle h, float* obs, float* reward, int32_t* step_type,
 int sbx_step(sbx_handle h, const float* action, float* obs, float* reward,
              int32_t* step_type, float* discount, void* stream);
 
-/* Same calls with HOST pointers: the library stages through pinned buffers,
- * copies host->device, runs the step, copies device->host and synchronises. */
+/* Same calls with HOST pointers: host->device copy of the actions, the step,
+ * device->host copies of the outputs, one synchronisation.  Page-locked caller
+ * buffers (sbx_host_alloc) are used directly, pageable ones are staged. */
 int sbx_reset_host(sbx_handle h, float* obs, float* reward, int32_t* step_type,
                    float* discount);
 int sbx_step_host(sbx_handle h, const float* action, float* obs, float* reward,
@@ -261,6 +262,11 @@ int sbx_step_host(sbx_handle h, const float* action, float* obs, float* reward,
  * [B] are HOST pointers.  Results: SBX_F_TEMP, SBX_F_N_SWEEPS, SBX_F_MAX_DELTA.
  * Synchronous. */
 int sbx_fd_step(sbx_handle h, const double* ambient, const double* convection);
+
+/* Page-locked host memory.  Buffers obtained here make the *_host calls copy
+ * straight between the caller's arrays and the device (no staging memcpy). */
+int sbx_host_alloc(size_t bytes, void** out);
+int sbx_host_free(void* p);
 
 /* Blocks until all work queued by this handle has finished. */
 int sbx_sync(sbx_handle h);

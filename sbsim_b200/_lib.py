@@ -126,7 +126,7 @@ class SbxInfo(C.Structure):
 EXPORTS = (
     "sbx_create", "sbx_destroy", "sbx_last_error", "sbx_get_info", "sbx_upload",
     "sbx_download", "sbx_reset", "sbx_step", "sbx_reset_host", "sbx_step_host",
-    "sbx_fd_step", "sbx_sync", "sbx_abi_info",
+    "sbx_fd_step", "sbx_sync", "sbx_abi_info", "sbx_host_alloc", "sbx_host_free",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -160,6 +160,8 @@ def load() -> C.CDLL:
   lib.sbx_fd_step.argtypes = [vp, vp, vp]
   lib.sbx_sync.argtypes = [vp]
   lib.sbx_abi_info.argtypes = [C.POINTER(C.c_int32), C.POINTER(sz), C.POINTER(sz)]
+  lib.sbx_host_alloc.argtypes = [sz, C.POINTER(vp)]
+  lib.sbx_host_free.argtypes = [vp]
   for name in EXPORTS:
     if name != "sbx_last_error":
       getattr(lib, name).restype = C.c_int
@@ -171,6 +173,31 @@ def load() -> C.CDLL:
         f"binding (v{ABI_VERSION}, {C.sizeof(SbxConfig)} B, {C.sizeof(SbxInfo)} B); rebuild")
   _lib = lib
   return lib
+
+
+class PinnedArray:
+  """A NumPy array over page-locked host memory from sbx_host_alloc."""
+
+  def __init__(self, shape, dtype):
+    self._lib = load()
+    self._ptr = C.c_void_p()
+    dtype = np.dtype(dtype)
+    nbytes = int(np.prod(shape)) * dtype.itemsize
+    rc = self._lib.sbx_host_alloc(nbytes, C.byref(self._ptr))
+    if rc != OK:
+      msg = self._lib.sbx_last_error(None)
+      raise SbxLibraryError(f"sbx_host_alloc failed ({rc}): {msg.decode() if msg else ''}")
+    buf = (C.c_char * max(nbytes, 1)).from_address(self._ptr.value)
+    self.array = np.frombuffer(buf, dtype=dtype, count=int(np.prod(shape))).reshape(shape)
+    self.array[...] = 0
+
+  def __del__(self):
+    try:
+      if self._ptr.value:
+        self._lib.sbx_host_free(self._ptr)
+        self._ptr = C.c_void_p()
+    except Exception:  # pylint: disable=broad-except
+      pass
 
 
 class Handle:

@@ -636,19 +636,35 @@ int sbx_step(sbx_handle h, const float* action, float* obs, float* reward, int32
   return do_step(h, action, obs, reward, step_type, discount, (cudaStream_t)stream);
 }
 
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) {
+    cudaGetLastError();
+    return false;
+  }
+  return a.type == cudaMemoryTypeHost;
+}
+
+// device -> host for one output; straight into the caller's buffer when it is
+// page-locked (sbx_host_alloc), otherwise through the handle's pinned stage.
+static int d2h(sbx_handle h, void* user, void* stage, const void* dev, size_t bytes, bool* staged) {
+  *staged = !is_pinned(user);
+  CUDA_TRY(h, cudaMemcpyAsync(*staged ? stage : user, dev, bytes, cudaMemcpyDeviceToHost, h->stream));
+  return SBX_OK;
+}
+
 static int copy_out(sbx_handle h, float* obs, float* reward, int32_t* step_type, float* discount) {
   const size_t B = h->cfg.n_envs;
-  cudaStream_t st = h->stream;
-  // pinned staging keeps the copies asynchronous DMA; one sync at the end
-  if (obs) CUDA_TRY(h, cudaMemcpyAsync(h->h_obs, h->d_obs, sizeof(float) * B * h->D, cudaMemcpyDeviceToHost, st));
-  if (reward) CUDA_TRY(h, cudaMemcpyAsync(h->h_reward, h->d_reward, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
-  if (step_type) CUDA_TRY(h, cudaMemcpyAsync(h->h_step_type, h->d_step_type, sizeof(int32_t) * B, cudaMemcpyDeviceToHost, st));
-  if (discount) CUDA_TRY(h, cudaMemcpyAsync(h->h_discount, h->d_discount, sizeof(float) * B, cudaMemcpyDeviceToHost, st));
-  CUDA_TRY(h, cudaStreamSynchronize(st));
-  if (obs) memcpy(obs, h->h_obs, sizeof(float) * B * h->D);
-  if (reward) memcpy(reward, h->h_reward, sizeof(float) * B);
-  if (step_type) memcpy(step_type, h->h_step_type, sizeof(int32_t) * B);
-  if (discount) memcpy(discount, h->h_discount, sizeof(float) * B);
+  bool s_obs = false, s_rew = false, s_st = false, s_dis = false;
+  if (obs) if (int rc = d2h(h, obs, h->h_obs, h->d_obs, sizeof(float) * B * h->D, &s_obs)) return rc;
+  if (reward) if (int rc = d2h(h, reward, h->h_reward, h->d_reward, sizeof(float) * B, &s_rew)) return rc;
+  if (step_type) if (int rc = d2h(h, step_type, h->h_step_type, h->d_step_type, sizeof(int32_t) * B, &s_st)) return rc;
+  if (discount) if (int rc = d2h(h, discount, h->h_discount, h->d_discount, sizeof(float) * B, &s_dis)) return rc;
+  CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  if (s_obs) memcpy(obs, h->h_obs, sizeof(float) * B * h->D);
+  if (s_rew) memcpy(reward, h->h_reward, sizeof(float) * B);
+  if (s_st) memcpy(step_type, h->h_step_type, sizeof(int32_t) * B);
+  if (s_dis) memcpy(discount, h->h_discount, sizeof(float) * B);
   return SBX_OK;
 }
 
@@ -667,8 +683,12 @@ int sbx_step_host(sbx_handle h, const float* action, float* obs, float* reward, 
   const int A = h->cfg.n_actions;
   if (A > 0) {
     if (!action) return fail(h, SBX_E_INVALID, "action is NULL");
-    memcpy(h->h_action, action, sizeof(float) * B * A);
-    CUDA_TRY(h, cudaMemcpyAsync(h->d_action, h->h_action, sizeof(float) * B * A, cudaMemcpyHostToDevice, h->stream));
+    const float* src = action;
+    if (!is_pinned(action)) {
+      memcpy(h->h_action, action, sizeof(float) * B * A);
+      src = h->h_action;
+    }
+    CUDA_TRY(h, cudaMemcpyAsync(h->d_action, src, sizeof(float) * B * A, cudaMemcpyHostToDevice, h->stream));
   }
   if (int rc = do_step(h, h->d_action, h->d_obs, h->d_reward, h->d_step_type, h->d_discount, h->stream)) return rc;
   return copy_out(h, obs, reward, step_type, discount);
@@ -691,6 +711,18 @@ int sbx_fd_step(sbx_handle h, const double* ambient, const double* convection) {
   p.fd_only = 0;
   if (rc) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+  return SBX_OK;
+}
+
+int sbx_host_alloc(size_t bytes, void** out) {
+  if (!out) return fail(nullptr, SBX_E_INVALID, "null argument");
+  cudaError_t e = cudaMallocHost(out, bytes ? bytes : 1);
+  if (e != cudaSuccess) return fail(nullptr, SBX_E_NOMEM, "cudaMallocHost(%zu) failed: %s", bytes, cudaGetErrorString(e));
+  return SBX_OK;
+}
+
+int sbx_host_free(void* p) {
+  if (p) cudaFreeHost(p);
   return SBX_OK;
 }
 

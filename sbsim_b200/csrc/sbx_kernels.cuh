@@ -214,8 +214,16 @@ constexpr uint32_t kFastDesc = SBX_CV_INTERIOR | (0u << SBX_DESC_MATERIAL_SHIFT)
 // Once per uploaded plan: repack the descriptors and split the plan's vectors
 // into a FAST list (every CV interior, air, no heat input: uniform register
 // coefficients, all four neighbours in range by construction) and a SLOW list
-// (generic, table-driven).  Both lists share one array: fast ascending from the
-// front, slow from the back.  One warp per plan => deterministic order.
+// (generic, table-driven).  Both lists share one array: fast from the front, slow
+// from the back.
+//
+// Order inside each list: sorted by (rank within the vector's index-mod-8 class,
+// index mod 8).  Every aligned group of 8 list entries then holds 8 DIFFERENT
+// residues mod 8, so the 8 lanes of a quarter-warp touch 8 different 16-byte bank
+// groups and the 128-bit shared-memory loads / stores of the sweep are
+// conflict-free even though the lists skip vectors (a plain ascending list has a
+// gap in almost every quarter-warp, which costs one replay each: profiles/).
+// One warp per plan, fully deterministic.
 template <int V>
 __global__ void k_prepare_plan(const Params p) {
   const int plan = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
@@ -225,28 +233,36 @@ __global__ void k_prepare_plan(const Params p) {
   const uint16_t* raw = p.desc + (size_t)plan * n_cv;
   uint16_t* packed = p.desc_packed + (size_t)plan * n_cv;
   uint16_t* qlist = p.qlist + (size_t)plan * n_items;
-  int nf = 0, ns = 0;
-  for (int base_it = 0; base_it < n_items; base_it += 32) {
-    const int it = base_it + lane;
-    const bool valid = it < n_items;
-    bool fast = valid;
-    if (valid) {
+  for (int i = lane; i < n_cv; i += 32) packed[i] = (uint16_t)repack_desc(raw[i]);
+  // lanes 0-7: fast vectors of residue (lane & 7); lanes 8-15: slow vectors
+  const int res = lane & 7, kind = lane >> 3;   // kind 0 fast, 1 slow, >=2 idle
+  auto is_fast = [&](int it) {
+    bool f = true;
+    for (int e = 0; e < V; ++e) f = f && ((raw[it * V + e] & 0x007Fu) == kFastDesc);
+    return f;
+  };
+  int size = 0;
+  if (kind < 2)
+    for (int it = res; it < n_items; it += 8) size += (is_fast(it) == (kind == 0)) ? 1 : 0;
+  int sizes[8];
 #pragma unroll
-      for (int e = 0; e < V; ++e) {
-        const uint32_t d = raw[it * V + e];
-        fast = fast && ((d & 0x007Fu) == kFastDesc);
-        packed[it * V + e] = (uint16_t)repack_desc(d);
-      }
+  for (int r = 0; r < 8; ++r) sizes[r] = __shfl_sync(0xffffffffu, size, (lane & 8) | r);
+  int total = 0;
+#pragma unroll
+  for (int r = 0; r < 8; ++r) total += sizes[r];
+  if (kind < 2) {
+    int m = 0;
+    for (int it = res; it < n_items; it += 8) {
+      if (is_fast(it) != (kind == 0)) continue;
+      int pos = 0;                       // entries sorted before (m, res)
+#pragma unroll
+      for (int r = 0; r < 8; ++r) pos += min(sizes[r], m) + ((r < res && sizes[r] > m) ? 1 : 0);
+      if (kind == 0) qlist[pos] = (uint16_t)it;
+      else qlist[n_items - 1 - pos] = (uint16_t)it;
+      ++m;
     }
-    const unsigned mf = __ballot_sync(0xffffffffu, fast);
-    const unsigned ms = __ballot_sync(0xffffffffu, valid && !fast);
-    const unsigned below = (1u << lane) - 1u;
-    if (fast) qlist[nf + __popc(mf & below)] = (uint16_t)it;
-    else if (valid) qlist[n_items - 1 - (ns + __popc(ms & below))] = (uint16_t)it;
-    nf += __popc(mf);
-    ns += __popc(ms);
   }
-  if (lane == 0) p.n_fast[plan] = nf;
+  if (lane == 0) p.n_fast[plan] = total;
 }
 
 // One Jacobi sweep over the CTA's building.  FIRST: `in` is T_prev itself, so

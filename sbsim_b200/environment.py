@@ -287,10 +287,15 @@ class Environment:
     self._upload_static()
     self._upload_tables()
     B, D = b.n_envs, len(names)
-    self._obs = np.zeros((B, D), dtype=np.float32)
-    self._reward = np.zeros(B, dtype=np.float32)
-    self._step_type = np.zeros(B, dtype=np.int32)
-    self._discount = np.zeros(B, dtype=np.float32)
+    # Outputs land in page-locked host buffers (direct DMA, no staging memcpy).
+    # Two sets alternate, so the arrays of a returned TimeStep stay valid until the
+    # next-but-one reset()/step() call; copy them to keep them longer.
+    self._pinned = [[_lib.PinnedArray((B, D), np.float32), _lib.PinnedArray((B,), np.float32),
+                     _lib.PinnedArray((B,), np.int32), _lib.PinnedArray((B,), np.float32)]
+                    for _ in range(2)]
+    self._pinned_action = _lib.PinnedArray((B, max(len(targets), 1)), np.float32)
+    self._flip = 0
+    self._bind_outputs()
 
   # ---- uploads -------------------------------------------------------------
 
@@ -404,9 +409,16 @@ class Environment:
   def handle(self) -> _lib.Handle:
     return self._handle
 
+  def _bind_outputs(self):
+    self._obs, self._reward, self._step_type, self._discount = (
+        p.array for p in self._pinned[self._flip])
+
   def _time_step(self) -> specs.TimeStep:
-    return specs.TimeStep(step_type=self._step_type.copy(), reward=self._reward.copy(),
-                          discount=self._discount.copy(), observation=self._obs.copy())
+    ts = specs.TimeStep(step_type=self._step_type, reward=self._reward,
+                        discount=self._discount, observation=self._obs)
+    self._flip ^= 1
+    self._bind_outputs()
+    return ts
 
   def _sync_counters(self):
     info = self._handle.info()
@@ -435,13 +447,20 @@ class Environment:
     return a
 
   def step(self, action) -> specs.TimeStep:
-    """Environment._step (environment.py:1228-1360) for every env."""
+    """Environment._step (environment.py:1228-1360) for every env.
+
+    The returned arrays are views of page-locked buffers that the library fills by
+    DMA; two buffer sets alternate, so a TimeStep stays valid until the
+    next-but-one reset()/step().  Copy it to keep it longer."""
     if self._current_time_step is None:       # PyEnvironment.step [TF-Agents]
       return self.reset()
     if self._episode_ended:                   # environment.py:1252-1253
       return self.reset()
     a = self._validate_action(action)
-    self._handle.step_host(a, self._obs, self._reward, self._step_type, self._discount)
+    pa = self._pinned_action.array
+    if a.size:
+      pa[...] = a
+    self._handle.step_host(pa, self._obs, self._reward, self._step_type, self._discount)
     ended = self._step_count >= self._num_timesteps_in_episode
     self._episode_ended = ended
     if not ended:

@@ -195,6 +195,10 @@ enum {
   /* handle-level state shared by every env (all envs share one clock) */
   SBX_F_THERMOSTAT_PREV = 49, /* i32 [2]  {Thermostat._previous_timestamp is not None, is_comfort_mode(previous)}; survives reset (vav.py:98) */
   SBX_F_EPISODE = 50,         /* i32 [4]  {step_count, time_index, episode_ended, reset_called} */
+  /* one-shot input of the NEXT sbx_step: gather map of the stochastic convection model
+   * (stochastic_convection_simulator.py:62-145), applied after the diffusion solve and
+   * before the zone means: temp'[b, i] = temp[b, perm[b, i]].  Consumed by that step. */
+  SBX_F_CONVECTION_PERM = 51, /* i32 [B,H*W] */
   /* per-env results of the last step (diagnostics, read-only) */
   SBX_F_N_SWEEPS = 60,     /* i32 [B] */
   SBX_F_MAX_DELTA = 61,    /* f32 [B] */

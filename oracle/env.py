@@ -70,6 +70,7 @@ class OracleEnvConfig:
   iteration_limit: int = 100
   initial_temp: float = 294.0
   reset_temp_values: Optional[np.ndarray] = None
+  convection: Optional[object] = None   # oracle.convection.StochasticConvectionSimulator
   # air handler
   ahu_recirculation: float = 0.3
   ahu_heating_setpoint: float = 285.0
@@ -180,6 +181,10 @@ class OracleEnvironment:
     new_temp, n_sweeps, converged, max_delta = self.solver.fd_step(
         self.temp, self.input_q, ambient, h)
     self.temp = new_temp                                       # simulator.py:369
+    if cfg.convection is not None:                             # building.apply_convection :156
+      room_dict = {name: list(zip(rows.tolist(), cols.tolist()))
+                   for name, rows, cols in self.rooms}
+      cfg.convection.apply_convection(room_dict, self.temp)
     self.ahu.reset_demand()
     self.boiler.reset_demand()
     supply_temps = []

@@ -12,6 +12,7 @@ from sbsim_b200.config import (ActionConfig, AirHandler, Boiler, BoundedActionNo
                                FloorPlanBasedHvac, HistogramReducer,
                                SetpointEnergyCarbonRegretFunction,
                                StandardScoreObservationNormalizer)
+from sbsim_b200.convection import StochasticConvectionSimulator
 from sbsim_b200.environment import BatchedWeather, Environment, SimulatorBuilding
 from sbsim_b200.exogenous import (ConstantOccupancy, ElectricityEnergyCost,
                                   NaturalGasEnergyCost, ReplayWeatherController,
@@ -26,5 +27,5 @@ __all__ = [
     "NaturalGasEnergyCost", "PATH_AUTO", "PATH_RESIDENT", "PATH_STREAMING",
     "ReplayWeatherController", "SbxLibraryError", "SetpointEnergyCarbonRegretFunction",
     "SetpointSchedule", "SimulatorBuilding", "StandardScoreObservationNormalizer",
-    "StepFunctionOccupancy", "TableOccupancy", "WeatherController", "compile_plan",
+    "StepFunctionOccupancy", "StochasticConvectionSimulator", "TableOccupancy", "WeatherController", "compile_plan",
 ]

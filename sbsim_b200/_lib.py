@@ -54,7 +54,7 @@ FIELDS = {
     "thermostat_mode": (44, np.uint8), "ahu_heating_sp": (45, np.float64),
     "ahu_cooling_sp": (46, np.float64), "boiler_sp": (47, np.float64),
     "boiler_tank": (48, np.float64), "thermostat_prev": (49, np.int32),
-    "episode": (50, np.int32),
+    "episode": (50, np.int32), "convection_perm": (51, np.int32),
     "n_sweeps": (60, np.int32), "max_delta": (61, np.float32),
     "step_diag": (62, np.float64), "q_zone": (63, np.float64),
     "zone_supply_temp": (64, np.float64), "pre_zone_mean": (65, np.float32),

@@ -51,6 +51,8 @@ struct sbx_env {
   int step_count = 0, time_index = 0, episode_ended = 0, reset_called = 0;
   int therm_seen = 0, prev_comfort = 0;
   int plans_dirty = 1;           // packed descriptors / vector lists need (re)building
+  int32_t* conv_perm = nullptr;  // lazily allocated [B,H*W]
+  int conv_pending = 0;          // a permutation was uploaded for the next step
   uint8_t* h_comfort = nullptr;  // host copy of the comfort table (for prev_comfort)
   // device allocations
   DevBuf all[64];
@@ -299,6 +301,7 @@ int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_
   p.time_index = h->time_index; p.step_count = h->step_count;
   p.therm_seen = h->therm_seen; p.prev_comfort = h->prev_comfort;
   p.action = action; p.obs = obs; p.reward = reward; p.step_type = step_type; p.discount_out = discount;
+  p.conv_perm = h->conv_pending ? h->conv_perm : nullptr;
   {
     const int wpb = 4;
     const unsigned grid = (unsigned)((p.B + wpb - 1) / wpb);
@@ -308,10 +311,20 @@ int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_
       if (int rc = run_resident(h, st)) return rc;      // solve + zone sums, one launch
     } else {
       if (int rc = run_stream_sweeps(h, st)) return rc;
+      if (p.conv_perm) {
+        const size_t total = (size_t)p.B * p.H * p.W;
+        const unsigned g = (unsigned)((total + 256 * 8 - 1) / (256 * 8));
+        k_permute<<<g > 0 ? g : 1, 256, 0, st>>>(p);
+        if (int rc = launch_check(h, "k_permute")) return rc;
+        k_rotate_cur<<<(unsigned)((p.B + 255) / 256), 256, 0, st>>>(p);
+        if (int rc = launch_check(h, "k_rotate_cur")) return rc;
+      }
       if (int rc = launch_zone_reduce(h, st)) return rc;
     }
     if (int rc = launch_post(h, st, 0)) return rc;
   }
+  p.conv_perm = nullptr;
+  h->conv_pending = 0;
   // host mirror of Thermostat._previous_timestamp (thermostat.py:147) and of the
   // episode counters (environment.py:1313, 1358-1359)
   h->therm_seen = 1;
@@ -486,6 +499,7 @@ int sbx_destroy(sbx_handle h) {
   cudaDeviceSynchronize();
   for (int i = 0; i < h->n_all; ++i) cudaFree(h->all[i].p);
   if (h->gather) cudaFree(h->gather);
+  if (h->conv_perm) cudaFree(h->conv_perm);
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward);
   cudaFreeHost(h->h_step_type); cudaFreeHost(h->h_discount); cudaFreeHost(h->h_n_active);
   if (h->stream) cudaStreamDestroy(h->stream);
@@ -567,6 +581,19 @@ int sbx_upload(sbx_handle h, int field, const void* src, size_t nbytes) {
     if (nbytes != 2 * sizeof(int32_t)) return fail(h, SBX_E_INVALID, "field %d needs %zu bytes, got %zu", field, 2 * sizeof(int32_t), nbytes);
     const int32_t* v = (const int32_t*)src;
     h->therm_seen = v[0] != 0; h->prev_comfort = v[1] != 0;
+    return SBX_OK;
+  }
+  if (field == SBX_F_CONVECTION_PERM) {
+    const size_t need = sizeof(int32_t) * (size_t)h->cfg.n_envs * h->cfg.height * h->cfg.width;
+    if (nbytes != need) return fail(h, SBX_E_INVALID, "field %d needs %zu bytes, got %zu", field, need, nbytes);
+    if (!h->conv_perm) {
+      cudaError_t e = cudaMalloc((void**)&h->conv_perm, need);
+      if (e != cudaSuccess) return fail(h, SBX_E_NOMEM, "cudaMalloc(%zu) failed: %s", need, cudaGetErrorString(e));
+      h->device_bytes += (int64_t)need;
+    }
+    CUDA_TRY(h, cudaDeviceSynchronize());
+    CUDA_TRY(h, cudaMemcpy(h->conv_perm, src, need, cudaMemcpyHostToDevice));
+    h->conv_pending = 1;
     return SBX_OK;
   }
   if (field == SBX_F_EPISODE) {

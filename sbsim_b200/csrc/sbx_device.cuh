@@ -117,6 +117,7 @@ struct Params {
   uint8_t* active;           // [B]
   int32_t* n_active;         // [1]
   unsigned long long* sweeps_total;  // [1]
+  const int32_t* conv_perm;  // [B,H*W] or null: convection gather map for this step
   // sbx_fd_step: solve only, ambient / convection given per env
   int fd_only;
   const double* fd_ambient;     // [B]

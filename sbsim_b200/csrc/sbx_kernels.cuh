@@ -430,6 +430,15 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   }
   // `in` now holds building.temp for the next step (simulator.py:369)
 
+  // building.apply_convection() (simulator_flexible_floor_plan.py:156): the swaps of
+  // the stochastic convection model, pre-composed on the host into a gather map
+  if (p.conv_perm != nullptr && !p.fd_only) {
+    const int32_t* perm = p.conv_perm + (size_t)b * n_cv;
+    for (int i = tid; i < n_cv; i += NT) out[i] = in[perm[i]];
+    __syncthreads();
+    float* tmp = in; in = out; out = tmp;
+  }
+
   // ---- stage 3: write back + zone / grid sums ---------------------------------
   if (use_tma) {
     if (tid == 0) tma_store_1d(gT, in, (uint32_t)(n_cv * 4));
@@ -740,6 +749,23 @@ __global__ void k_reset_temp(const Params p) {
     else v = p.reset_temps[(p.n_reset == 1 ? 0 : b) * n_cv + j];
     p.tbuf[0][i] = v;
   }
+}
+
+// Streaming path: convection gather into the next buffer of the rotation, then
+// k_rotate_cur makes it current.
+__global__ void k_permute(const Params p) {
+  const size_t n_cv = (size_t)p.H * p.W;
+  const size_t total = n_cv * p.B;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x) {
+    const size_t b = i / n_cv;
+    const int c = p.cur[b];
+    p.tbuf[(c + 1) % 3][i] = p.tbuf[c][b * n_cv + p.conv_perm[i]];
+  }
+}
+__global__ void k_rotate_cur(const Params p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b < p.B) p.cur[b] = (uint8_t)((p.cur[b] + 1) % 3);
 }
 
 // dst[b] = tbuf[cur[b]][b]  (download of building.temp in the streaming path)

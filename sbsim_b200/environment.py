@@ -69,11 +69,7 @@ class SimulatorBuilding:
                initial_temp: Union[float, np.ndarray] = 294.0,
                reset_temp_values: Optional[np.ndarray] = None,
                convection_simulator=None):
-    if convection_simulator is not None:
-      raise NotImplementedError(
-          "stochastic convection (stochastic_convection_simulator.py) is listed as the next "
-          "component in SURVEY.md section 8f; pass convection_simulator=None "
-          "(allowed by building.py:647-649)")
+    self.convection_simulator = convection_simulator
     if isinstance(plans, floorplan.CompiledPlan):
       plans = [plans]
     self.plans: List[floorplan.CompiledPlan] = list(plans)
@@ -296,6 +292,17 @@ class Environment:
     self._pinned_action = _lib.PinnedArray((B, max(len(targets), 1)), np.float32)
     self._flip = 0
     self._bind_outputs()
+    # stochastic convection: exact host replay, one generator stream per env
+    self._conv = b.convection_simulator
+    if self._conv is not None:
+      self._conv_streams = [self._conv.make_stream() for _ in range(B)]
+      self._conv_rooms = []
+      for plan in b.plans:
+        rooms = []
+        for zi in range(plan.n_zones):
+          r, c = plan.zone_indices(zi)
+          rooms.append(list(zip(r.tolist(), c.tolist())))
+        self._conv_rooms.append(rooms)
 
   # ---- uploads -------------------------------------------------------------
 
@@ -457,6 +464,7 @@ class Environment:
     if self._episode_ended:                   # environment.py:1252-1253
       return self.reset()
     a = self._validate_action(action)
+    self._upload_convection()
     pa = self._pinned_action.array
     if a.size:
       pa[...] = a
@@ -468,6 +476,19 @@ class Environment:
     self._time_index += 1
     self._current_time_step = self._time_step()
     return self._current_time_step
+
+  def _upload_convection(self):
+    """building.apply_convection() of this step (simulator_flexible_floor_plan.py:156),
+    drawn on the host with the reference's generator calls (sbsim_b200/convection.py)."""
+    if self._conv is None:
+      return
+    b = self.building
+    shape = (b.height, b.width)
+    perm = np.empty((b.n_envs, b.height * b.width), dtype=np.int32)
+    for e in range(b.n_envs):
+      rooms = self._conv_rooms[0 if len(b.plans) == 1 else e]
+      perm[e] = self._conv.gather_index(rooms, shape, self._conv_streams[e])
+    self._handle.upload("convection_perm", perm)
 
   # ---- device-resident I/O (torch tensors as the device-memory container) ----
 
@@ -485,6 +506,7 @@ class Environment:
     guarantees actions within [-1, 1] (they are not validated on the host)."""
     if self._episode_ended:
       raise RuntimeError("episode has ended; call reset_device()")
+    self._upload_convection()
     self._handle.step_device(action.data_ptr(), obs.data_ptr(), reward.data_ptr(),
                              step_type.data_ptr(), discount.data_ptr(), stream)
     ended = self._step_count >= self._num_timesteps_in_episode

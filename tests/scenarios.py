@@ -4,6 +4,7 @@
 from __future__ import annotations
 
 import dataclasses
+import random
 from typing import List, Optional, Sequence
 
 import numpy as np
@@ -11,6 +12,7 @@ import pandas as pd
 
 import sbsim_b200 as sbx
 from sbsim_b200 import floorplan
+from oracle import convection as oconv
 from oracle import env as oenv
 from oracle import exogenous as oex
 from oracle import hvac as ohvac
@@ -78,6 +80,7 @@ class Scenario:
   histogram: bool = False
   schedule_tz: str = "UTC"
   occupancy: str = "step"      # "step" | "const"
+  convection: Optional[tuple] = None   # (p, distance, seed) of StochasticConvectionSimulator
 
   def compiled(self) -> floorplan.CompiledPlan:
     return floorplan.compile_plan(
@@ -129,6 +132,9 @@ def make_oracle(sc: Scenario, cp: Optional[floorplan.CompiledPlan] = None,
       convergence_threshold=sc.convergence_threshold, iteration_limit=sc.iteration_limit,
       initial_temp=sc.initial_temp if initial_temp is None else initial_temp,
       reset_temp_values=sc.reset_temp_values,
+      convection=(oconv.StochasticConvectionSimulator(
+          sc.convection[0], sc.convection[1], sc.convection[2],
+          rng=random.Random(sc.convection[2])) if sc.convection else None),
       normalization={k: (f32(m), f32(v)) for k, (m, v) in NORMALIZATION.items()},
       histogram=HISTOGRAM if sc.histogram else None,
       discount_factor=sc.discount, num_timesteps_in_episode=sc.n_steps,
@@ -156,7 +162,9 @@ def make_env(sc: Scenario, n_envs: int = 1, plans=None, weather=None, initial_te
       convergence_threshold=sc.convergence_threshold, iteration_limit=sc.iteration_limit,
       start_timestamp=sc.start_timestamp, floor_height_cm=sc.floor_height_cm,
       initial_temp=sc.initial_temp if initial_temp is None else initial_temp,
-      reset_temp_values=sc.reset_temp_values)
+      reset_temp_values=sc.reset_temp_values,
+      convection_simulator=(sbx.StochasticConvectionSimulator(*sc.convection)
+                            if sc.convection else None))
   reward = sbx.SetpointEnergyCarbonRegretFunction(
       300.0, 100.0, 160000, 400000, 0.5, 4.3, sbx.ElectricityEnergyCost(),
       sbx.NaturalGasEnergyCost(), 0.2, 0.4, 0.4)

@@ -243,3 +243,33 @@ def test_device_pointer_api_matches_host_api():
   finally:
     env_h.close()
     env_d.close()
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+def test_stochastic_convection_replay_matches_oracle(path):
+  """Shipped calibrated setting p=1, distance=5, seed=5 (sim_config.gin:37-39): the
+  host-drawn gather map applied on the GPU equals the oracle's in-place swaps."""
+  sc = S.Scenario(floor_plan=S.small_plan(), convection=(1.0, 5, 5))
+  cp = sc.compiled()
+  B = 2
+  env = S.make_env(sc, n_envs=B, plans=cp, kernel_path=PATHS[path])
+  try:
+    oracles = [S.make_oracle(sc, cp) for _ in range(B)]
+    ts = env.reset()
+    for o in oracles:
+      o.reset()
+    rng = np.random.default_rng(3)
+    exact = 0
+    for step in range(12):
+      a = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+      ts = env.step(a)
+      for b, o in enumerate(oracles):
+        o.step(a[b])
+      st = _compare_step(env, oracles, ts, B, cp, step)
+      exact += st["temp_exact"]
+    assert exact >= B          # first step: bit-identical field, permutation included
+    # convection really moved temperatures around: consecutive room CVs differ
+    temp = env.handle.download("temp", (B, cp.height, cp.width))
+    assert np.abs(np.diff(temp[0][5:10, 5:15], axis=1)).max() > 0
+  finally:
+    env.close()

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SBX_ABI_VERSION 1
+#define SBX_ABI_VERSION 2
 
 #define SBX_OK 0
 #define SBX_E_INVALID (-1)   /* bad argument / config                      */
@@ -63,6 +63,10 @@ extern "C" {
 #define SBX_PATH_AUTO 0
 #define SBX_PATH_STREAMING 1 /* any grid size; one launch per Jacobi sweep       */
 #define SBX_PATH_RESIDENT 2  /* grid held in shared memory; whole step = 1 launch */
+
+/* diffusion solver (the reference ships two different models behind one method) */
+#define SBX_SOLVER_TF_JACOBI 0   /* fp32 whole-grid Jacobi   tf_simulator.py:573-853 (calibrated config) */
+#define SBX_SOLVER_GAUSS_SEIDEL 1 /* fp64 in-place raster GS  simulator.py:98-316   (legacy config)     */
 
 /* TimeStep.step_type values [TF-Agents] */
 #define SBX_STEP_FIRST 0
@@ -104,11 +108,12 @@ typedef struct {
   int32_t n_table_steps; /* rows of every time-indexed table; >= episode_steps + 2 */
   int32_t episode_steps; /* Environment._num_timesteps_in_episode environment.py:433 */
   int32_t kernel_path;   /* SBX_PATH_* */
+  int32_t solver;        /* SBX_SOLVER_*; Gauss-Seidel needs the grid to fit one SM (resident) */
   /* ---- finite differences (simulator.py:45-78) ---- */
-  float time_step_sec;
-  float floor_height_m;
-  float convergence_threshold;
   int32_t iteration_limit;
+  double time_step_sec;
+  double floor_height_m;
+  double convergence_threshold; /* compared in fp32 by the Jacobi solver, in fp64 by Gauss-Seidel */
   /* ---- schedule windows (setpoint_schedule.py:118-128) ---- */
   double comfort_heat, comfort_cool, eco_heat, eco_cool;
   /* ---- air handler (air_handler.py:51-135) ---- */
@@ -192,6 +197,8 @@ enum {
   SBX_F_AHU_COOLING_SP = 46,  /* f64 [B] */
   SBX_F_BOILER_SP = 47,       /* f64 [B]   Boiler._reheat_water_setpoint */
   SBX_F_BOILER_TANK = 48,     /* f64 [B,3] current_temperature, step_tank_temperature_change, last_step_duration_sec */
+  SBX_F_TEMP64 = 52,          /* f64 [B,H,W] building.temp of the Gauss-Seidel solver (SBX_F_TEMP mirrors it in fp32) */
+  SBX_F_Q_CV64 = 53,          /* f64 [B,Z]   input_q at each diffuser CV, fp64 (Gauss-Seidel solver) */
   /* handle-level state shared by every env (all envs share one clock) */
   SBX_F_THERMOSTAT_PREV = 49, /* i32 [2]  {Thermostat._previous_timestamp is not None, is_comfort_mode(previous)}; survives reset (vav.py:98) */
   SBX_F_EPISODE = 50,         /* i32 [4]  {step_count, time_index, episode_ended, reset_called} */

@@ -15,7 +15,7 @@ import numpy as np
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libsbx.so")
 
-ABI_VERSION = 1
+ABI_VERSION = 2
 OK = 0
 MAX_ACTIONS = 3
 MAX_HIST_BINS = 32
@@ -30,6 +30,8 @@ OBS_HISTOGRAM = 1
 PATH_AUTO = 0
 PATH_STREAMING = 1
 PATH_RESIDENT = 2
+SOLVER_TF_JACOBI = 0
+SOLVER_GAUSS_SEIDEL = 1
 STEP_FIRST, STEP_MID, STEP_LAST = 0, 1, 2
 
 # per-CV descriptor bits (include/sbx.h)
@@ -55,6 +57,7 @@ FIELDS = {
     "ahu_cooling_sp": (46, np.float64), "boiler_sp": (47, np.float64),
     "boiler_tank": (48, np.float64), "thermostat_prev": (49, np.int32),
     "episode": (50, np.int32), "convection_perm": (51, np.int32),
+    "temp64": (52, np.float64), "q_cv64": (53, np.float64),
     "n_sweeps": (60, np.int32), "max_delta": (61, np.float32),
     "step_diag": (62, np.float64), "q_zone": (63, np.float64),
     "zone_supply_temp": (64, np.float64), "pre_zone_mean": (65, np.float32),
@@ -79,9 +82,10 @@ class SbxConfig(C.Structure):
       ("n_zones", C.c_int32), ("n_plans", C.c_int32), ("n_weather", C.c_int32),
       ("n_reset", C.c_int32), ("n_occ_zones", C.c_int32),
       ("n_table_steps", C.c_int32), ("episode_steps", C.c_int32),
-      ("kernel_path", C.c_int32),
-      ("time_step_sec", C.c_float), ("floor_height_m", C.c_float),
-      ("convergence_threshold", C.c_float), ("iteration_limit", C.c_int32),
+      ("kernel_path", C.c_int32), ("solver", C.c_int32),
+      ("iteration_limit", C.c_int32),
+      ("time_step_sec", C.c_double), ("floor_height_m", C.c_double),
+      ("convergence_threshold", C.c_double),
       ("comfort_heat", C.c_double), ("comfort_cool", C.c_double),
       ("eco_heat", C.c_double), ("eco_cool", C.c_double),
       ("ahu_recirculation", C.c_double), ("ahu_init_heating_setpoint", C.c_double),

@@ -46,6 +46,7 @@ struct sbx_env {
   int n_sms = 0;
   int resident_ctas_per_sm = 0;
   size_t resident_smem = 0;
+  size_t gs_smem = 0;
   Params P;
   // host-level episode state
   int step_count = 0, time_index = 0, episode_ended = 0, reset_called = 0;
@@ -147,7 +148,8 @@ int validate(const sbx_config& c) {
     for (int f = 0; f < 3; ++f)
       if (c.n_hist_bins[f] < 1 || c.n_hist_bins[f] > SBX_MAX_HIST_BINS) return fail(nullptr, SBX_E_INVALID, "n_hist_bins[%d] out of range", f);
   if (c.iteration_limit < 1) return fail(nullptr, SBX_E_INVALID, "iteration_limit must be >= 1");
-  if (!(c.time_step_sec > 0.f)) return fail(nullptr, SBX_E_INVALID, "time_step_sec must be > 0");
+  if (!(c.time_step_sec > 0.0)) return fail(nullptr, SBX_E_INVALID, "time_step_sec must be > 0");
+  if (c.solver != SBX_SOLVER_TF_JACOBI && c.solver != SBX_SOLVER_GAUSS_SEIDEL) return fail(nullptr, SBX_E_INVALID, "bad solver");
   if (c.discount_factor <= 0 || c.discount_factor > 1) return fail(nullptr, SBX_E_INVALID, "Discount factor must be in (0,1]");  // environment.py:446
   if (c.ahu_init_cooling_setpoint <= c.ahu_init_heating_setpoint) return fail(nullptr, SBX_E_INVALID, "cooling_air_temp_setpoint must greater than heating_air_temp_setpoint");  // air_handler.py:62-66
   if (c.max_productivity_personhour_usd <= c.min_productivity_personhour_usd) return fail(nullptr, SBX_E_INVALID, "max productivity must exceed min productivity");
@@ -169,7 +171,10 @@ void fill_params(sbx_handle h) {
     p.action_range[i] = (float)(c.action_max[i] - c.action_min[i]);
   }
   for (int f = 0; f < 3; ++f) p.n_hist_bins[f] = c.obs_mode == SBX_OBS_HISTOGRAM ? c.n_hist_bins[f] : 0;
-  p.dt = c.time_step_sec; p.z = c.floor_height_m; p.threshold = c.convergence_threshold;
+  p.dt = (float)c.time_step_sec; p.z = (float)c.floor_height_m;
+  p.threshold = (float)c.convergence_threshold;   // NumPy weak-scalar compare: fp32
+  p.dt_double = c.time_step_sec; p.z_double = c.floor_height_m;
+  p.threshold64 = c.convergence_threshold;
   p.iteration_limit = c.iteration_limit;
   p.comfort_heat = c.comfort_heat; p.comfort_cool = c.comfort_cool;
   p.eco_heat = c.eco_heat; p.eco_cool = c.eco_cool;
@@ -263,6 +268,10 @@ int prepare_plans(sbx_handle h, cudaStream_t st) {
 }
 
 int run_resident(sbx_handle h, cudaStream_t st) {
+  if (h->cfg.solver == SBX_SOLVER_GAUSS_SEIDEL) {
+    k_resident_gs<<<h->P.B, kGsThreads, h->gs_smem, st>>>(h->P);
+    return launch_check(h, "k_resident_gs");
+  }
   if (int rc = prepare_plans(h, st)) return rc;
   const Params& p = h->P;
   if (h->V == 4) k_resident_step<4><<<p.B, kResidentThreads, h->resident_smem, st>>>(p);
@@ -394,6 +403,17 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   }
   h->path = (c.kernel_path == SBX_PATH_AUTO) ? (fits ? SBX_PATH_RESIDENT : SBX_PATH_STREAMING) : c.kernel_path;
   h->resident_smem = L.total;
+  if (c.solver == SBX_SOLVER_GAUSS_SEIDEL) {
+    const GsLayout G = gs_layout((int)N, (int)Z);
+    if (G.total > (size_t)max_optin || c.kernel_path == SBX_PATH_STREAMING) {
+      fail(h, SBX_E_INVALID, "the Gauss-Seidel solver keeps the grid in shared memory: %zu B needed, %d available", G.total, max_optin);
+      return bail(SBX_E_INVALID);
+    }
+    h->path = SBX_PATH_RESIDENT;
+    h->gs_smem = G.total;
+    cudaError_t e = cudaFuncSetAttribute(k_resident_gs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
+    if (e != cudaSuccess) { fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return bail(SBX_E_CUDA); }
+  }
   if (h->path == SBX_PATH_RESIDENT) {
     cudaError_t e;
     if (h->V == 4) e = cudaFuncSetAttribute(k_resident_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
@@ -446,6 +466,9 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.global_mean, float, B);
   ALLOC(p.qcv, float, B * Z);
   ALLOC(p.qcv_next, float, B * Z);
+  ALLOC(p.qcv64, double, B * Z);
+  ALLOC(p.qcv64_next, double, B * Z);
+  if (c.solver == SBX_SOLVER_GAUSS_SEIDEL) ALLOC(p.temp64, double, B * N);
   ALLOC(p.therm_mode, uint8_t, B * Z);
   ALLOC(p.ahu_heat_sp, double, B);
   ALLOC(p.ahu_cool_sp, double, B);
@@ -562,6 +585,10 @@ static int field_info(sbx_handle h, int field, FieldInfo* fi) {
     F(SBX_F_AHU_COOLING_SP, p.ahu_cool_sp, B, double, true);
     F(SBX_F_BOILER_SP, p.boiler_sp, B, double, true);
     F(SBX_F_BOILER_TANK, p.boiler_tank, B * 3, double, true);
+    F(SBX_F_Q_CV64, p.qcv64, B * Z, double, true);
+    case SBX_F_TEMP64:
+      if (!p.temp64) return fail(h, SBX_E_INVALID, "SBX_F_TEMP64 exists only with the Gauss-Seidel solver");
+      fi->ptr = (void*)p.temp64; fi->bytes = B * N * sizeof(double); fi->writable = true; return SBX_OK;
     F(SBX_F_N_SWEEPS, p.n_sweeps, B, int32_t, false);
     F(SBX_F_MAX_DELTA, p.max_delta, B, float, false);
     F(SBX_F_STEP_DIAG, p.diag, B * SBX_DIAG_N, double, false);
@@ -610,6 +637,19 @@ int sbx_upload(sbx_handle h, int field, const void* src, size_t nbytes) {
   CUDA_TRY(h, cudaDeviceSynchronize());
   CUDA_TRY(h, cudaMemcpy(fi.ptr, src, nbytes, cudaMemcpyHostToDevice));
   if (field == SBX_F_TEMP) CUDA_TRY(h, cudaMemset(h->P.cur, 0, h->cfg.n_envs));
+  if (h->P.temp64 && (field == SBX_F_TEMP || field == SBX_F_TEMP64)) {
+    const size_t total = (size_t)h->cfg.n_envs * h->cfg.height * h->cfg.width;
+    const unsigned g = (unsigned)((total + 255) / 256);
+    k_mirror_temp<<<g, 256>>>(h->P, field == SBX_F_TEMP ? 1 : 0);
+    if (int rc = launch_check(h, "k_mirror_temp")) return rc;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+  }
+  if (field == SBX_F_Q_CV && h->P.qcv64) {   // keep the fp64 copy coherent for Gauss-Seidel
+    const unsigned g = (unsigned)(((size_t)h->cfg.n_envs * h->cfg.n_zones + 255) / 256);
+    k_mirror_q<<<g, 256>>>(h->P);
+    if (int rc = launch_check(h, "k_mirror_q")) return rc;
+    CUDA_TRY(h, cudaDeviceSynchronize());
+  }
   if (field == SBX_F_COMFORT) memcpy(h->h_comfort, src, nbytes);
   if (field == SBX_F_PLAN_DESC) h->plans_dirty = 1;
   return SBX_OK;

@@ -100,6 +100,10 @@ struct Params {
   float* global_mean;        // [B]
   float* qcv;                // [B,Z] heat per diffuser CV used by THIS step's solve
   float* qcv_next;           // [B,Z] produced by this step's VAV outputs
+  double* qcv64;             // same two, fp64 (Gauss-Seidel solver reads fp64 input_q)
+  double* qcv64_next;
+  double* temp64;            // [B,H,W] fp64 building.temp, Gauss-Seidel solver only
+  double threshold64, dt_double, z_double;
   uint8_t* therm_mode;       // [B,Z]
   double* ahu_heat_sp;
   double* ahu_cool_sp;
@@ -389,9 +393,12 @@ __device__ inline PreOut hvac_pre(const Params& p, int b, int plan, int lane,
       p.zone_supply[(size_t)b * Z + zi] = zs;
       // apply_thermal_power_zone building.py:873-889: power * (1/n_diffusers)
       const int nd = ndiff[zi];
-      p.qcv_next[(size_t)b * Z + zi] = nd > 0 ? (float)(q * (1.0 / (double)nd)) : 0.f;
+      const double qd = nd > 0 ? q * (1.0 / (double)nd) : 0.0;
+      p.qcv_next[(size_t)b * Z + zi] = (float)qd;
+      p.qcv64_next[(size_t)b * Z + zi] = qd;
       sh_zs[zi] = valve;  // stash valve; zs kept in zone_supply
     } else {
+      p.qcv64_next[(size_t)b * Z + zi] = 0.0;
       p.qcv_next[(size_t)b * Z + zi] = 0.f;
       p.q_zone[(size_t)b * Z + zi] = 0.0;
       p.zone_supply[(size_t)b * Z + zi] = 0.0;

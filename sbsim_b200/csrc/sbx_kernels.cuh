@@ -489,6 +489,181 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   if (use_tma && tid == 0) tma_store_wait();
 }
 
+
+// ---------------------------------------------------------------------------
+// Gauss-Seidel solver (the reference's legacy model, simulator.py:98-316): fp64,
+// in place, raster order.  Cell (i, j) reads the ALREADY UPDATED (i-1, j), (i, j-1)
+// and the old (i+1, j), (i, j+1), so the cells of one anti-diagonal i + j = d are
+// independent: sweeping d = 0 .. H+W-2 with a barrier in between reproduces the
+// sequential raster sweep exactly, operation for operation (Python floats are
+// IEEE fp64, evaluated left to right as written in the reference).
+// One CTA per building, grid resident in shared memory.
+// ---------------------------------------------------------------------------
+constexpr int kGsThreads = 128;
+
+struct GsLayout {
+  size_t off_t, off_prev, off_desc, off_q, off_bins, total;
+};
+__host__ __device__ inline GsLayout gs_layout(int n_cv, int Z) {
+  GsLayout L;
+  auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+  size_t o = 0;
+  L.off_t = o; o = al(o + (size_t)n_cv * 8);
+  L.off_prev = o; o = al(o + (size_t)n_cv * 8);
+  L.off_q = o; o = al(o + (size_t)(Z + 1) * 8);
+  L.off_bins = o; o = al(o + (size_t)(Z + 1) * 8);
+  L.off_desc = o; o = al(o + (size_t)n_cv * 2);
+  L.total = o;
+  return L;
+}
+
+// which of (up, down, left, right) exist, by class (tf_simulator.py:208-243)
+__device__ __forceinline__ unsigned gs_neighbor_mask(int cls) {
+  switch (cls) {
+    case SBX_CV_INTERIOR: return 0xF;      // up | down<<1 | left<<2 | right<<3
+    case SBX_CV_EDGE_TOP: return 0xE;
+    case SBX_CV_EDGE_BOTTOM: return 0xD;
+    case SBX_CV_EDGE_LEFT: return 0xB;
+    case SBX_CV_EDGE_RIGHT: return 0x7;
+    case SBX_CV_CORNER_TL: return 0xA;     // down, right
+    case SBX_CV_CORNER_BL: return 0x9;     // up, right
+    case SBX_CV_CORNER_TR: return 0x6;     // down, left
+    case SBX_CV_CORNER_BR: return 0x5;     // up, left
+    default: return 0x0;
+  }
+}
+
+__global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
+  extern __shared__ __align__(128) unsigned char smem[];
+  const int b = blockIdx.x, tid = threadIdx.x;
+  const int H = p.H, W = p.W, Z = p.Z, n_cv = H * W;
+  const int plan = p.n_plans == 1 ? 0 : b;
+  const GsLayout L = gs_layout(n_cv, Z);
+  double* T = reinterpret_cast<double*>(smem + L.off_t);
+  double* Tp = reinterpret_cast<double*>(smem + L.off_prev);
+  double* qz = reinterpret_cast<double*>(smem + L.off_q);
+  double* bins = reinterpret_cast<double*>(smem + L.off_bins);
+  uint16_t* dsc = reinterpret_cast<uint16_t*>(smem + L.off_desc);
+  double* gT = p.temp64 + (size_t)b * n_cv;
+  const uint16_t* gD = p.desc + (size_t)plan * n_cv;
+  for (int i = tid; i < n_cv; i += kGsThreads) {
+    const double v = gT[i];
+    T[i] = v;
+    Tp[i] = v;
+    dsc[i] = gD[i];
+  }
+  for (int i = tid; i <= Z; i += kGsThreads) {
+    qz[i] = i < Z ? p.qcv64[(size_t)b * Z + i] : 0.0;
+    bins[i] = 0.0;
+  }
+  const double t_inf = env_ambient(p, b, p.time_index);
+  const double h = env_convection(p, b);
+  const double dx = p.cv_size[plan];
+  const double z = (double)p.z_double;
+  const double dt = (double)p.dt_double;
+  const double* mat = p.material + (size_t)plan * 9;
+  __syncthreads();
+
+  int k = 0;
+  double md_block = 0.0;
+  while (k < p.iteration_limit) {
+    ++k;
+    double lmax = 0.0;
+    for (int d = 0; d <= H + W - 2; ++d) {
+      const int i_lo = max(0, d - W + 1), i_hi = min(H - 1, d);
+      for (int i = i_lo + tid; i <= i_hi; i += kGsThreads) {
+        const int j = d - i;
+        const int c = i * W + j;
+        const uint32_t desc = dsc[c];
+        const int cls = desc_class(desc);
+        double nv;
+        if (cls == SBX_CV_EXTERIOR) {
+          nv = t_inf;                                            // simulator.py:256-258
+        } else {
+          const double* m = mat + desc_material(desc) * 3;
+          const double kc = m[0], cap = m[1], rho = m[2];
+          const double last = Tp[c];
+          const unsigned mask = gs_neighbor_mask(cls);
+          // neighbours in the reference's list order (building.py:808)
+          const int nb[4] = {c - W, c + W, c - 1, c + 1};
+          if (cls == SBX_CV_INTERIOR) {                          // :210-237
+            const double alpha = kc / rho / cap;
+            const double t0 = dx * dx / dt / alpha;
+            double sum = 0.0;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) sum += T[nb[n]];
+            const double qv = (desc & SBX_DESC_DIFFUSER) ? qz[desc_zone(desc)] : 0.0;
+            const double source = qv / kc / z;
+            nv = (sum + source + t0 * last) / (4.0 + t0);
+          } else if (cls >= SBX_CV_CORNER_TL) {                  // corner :117-142
+            const double t0 = rho * (dx * dx) * cap / dt / 2.0;
+            double sum = 0.0;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) if (mask & (1u << n)) sum += T[nb[n]];
+            const double transfer = kc * sum;
+            const double conv = 2.0 * h * dx * t_inf;
+            const double den = 2.0 * kc + 2.0 * h * dx + t0;
+            nv = (transfer + conv + t0 * last) / den;
+          } else {                                               // edge :163-195
+            const double t0 = rho * (dx * dx) / 2 * cap / dt;
+            double sum = 0.0;
+#pragma unroll
+            for (int n = 0; n < 4; ++n) {
+              if (mask & (1u << n)) {
+                // 0.5 for neighbours that are themselves edges / corners (:180-183)
+                const double f = desc_class(dsc[nb[n]]) == SBX_CV_INTERIOR ? 1.0 : 0.5;
+                sum += f * T[nb[n]];
+              }
+            }
+            const double transfer = kc * sum;
+            const double conv = h * dx * t_inf;
+            const double den = 2.0 * kc + h * dx + t0;
+            nv = (transfer + conv + t0 * last) / den;
+          }
+        }
+        lmax = fmax(lmax, fabs(nv - T[c]));                      // :311-312
+        T[c] = nv;
+      }
+      __syncthreads();
+    }
+    // max_delta <= convergence_threshold (simulator.py:362), fp64
+    const int above = __syncthreads_or(lmax > p.threshold64);
+    md_block = lmax;
+    if (!above) break;
+  }
+  // write back (fp64 state + fp32 mirror), zone sums for k_post
+  float* g32 = p.tbuf[0] + (size_t)b * n_cv;
+  double total = 0.0;
+  for (int i = tid; i < n_cv; i += kGsThreads) {
+    const double v = T[i];
+    gT[i] = v;
+    g32[i] = (float)v;
+    total += v;
+    const int zn = desc_zone(dsc[i]);
+    if (zn != SBX_ZONE_NONE && !p.fd_only) atomicAdd(&bins[zn], v);
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    total += __shfl_xor_sync(0xffffffffu, total, o);
+    md_block = fmax(md_block, __shfl_xor_sync(0xffffffffu, md_block, o));
+  }
+  if ((tid & 31) == 0) {
+    atomicAdd(&bins[Z], total);
+    atomicMax(&p.max_delta_bits[b], __float_as_uint((float)md_block));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    p.n_sweeps[b] = k;
+    p.max_delta[b] = __uint_as_float(p.max_delta_bits[b]);
+    p.max_delta_bits[b] = 0u;
+    if (!p.fd_only) atomicAdd(p.sweeps_total, (unsigned long long)k);
+  }
+  if (!p.fd_only) {
+    double* zs = p.zone_sum + (size_t)b * (Z + 1);
+    for (int i = tid; i <= Z; i += kGsThreads) zs[i] = bins[i];
+  }
+}
+
 // ---------------------------------------------------------------------------
 // streaming path
 // ---------------------------------------------------------------------------
@@ -703,7 +878,10 @@ __global__ void __launch_bounds__(128) k_post(const Params p, const CarryStore* 
     zpost[zi] = m;
     zpre[zi] = p.pre_zone_mean[(size_t)b * Z + zi];
     p.zone_mean[(size_t)b * Z + zi] = m;
-    if (!is_reset) p.qcv[(size_t)b * Z + zi] = p.qcv_next[(size_t)b * Z + zi];
+    if (!is_reset) {
+      p.qcv[(size_t)b * Z + zi] = p.qcv_next[(size_t)b * Z + zi];
+      p.qcv64[(size_t)b * Z + zi] = p.qcv64_next[(size_t)b * Z + zi];
+    }
   }
   const float gmean = (float)(zs[Z] / (double)((size_t)p.H * p.W));
   if (lane == 0) p.global_mean[b] = gmean;
@@ -734,6 +912,8 @@ __global__ void k_reset_state(const Params p) {
   for (int zi = 0; zi < p.Z; ++zi) {
     p.qcv[(size_t)b * p.Z + zi] = 0.f;          // input_q = zeros
     p.qcv_next[(size_t)b * p.Z + zi] = 0.f;
+    p.qcv64[(size_t)b * p.Z + zi] = 0.0;
+    p.qcv64_next[(size_t)b * p.Z + zi] = 0.0;
     p.pre_zone_mean[(size_t)b * p.Z + zi] = 0.f;
   }
 }
@@ -748,6 +928,7 @@ __global__ void k_reset_temp(const Params p) {
     if (p.n_reset == 0) v = p.initial_temp[b];
     else v = p.reset_temps[(p.n_reset == 1 ? 0 : b) * n_cv + j];
     p.tbuf[0][i] = v;
+    if (p.temp64) p.temp64[i] = (double)v;
   }
 }
 
@@ -766,6 +947,19 @@ __global__ void k_permute(const Params p) {
 __global__ void k_rotate_cur(const Params p) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b < p.B) p.cur[b] = (uint8_t)((p.cur[b] + 1) % 3);
+}
+
+// keep the fp64 (Gauss-Seidel) and fp32 copies of building.temp coherent after an upload
+__global__ void k_mirror_temp(const Params p, const int from_f32) {
+  const size_t total = (size_t)p.B * p.H * p.W;
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  if (from_f32) p.temp64[i] = (double)p.tbuf[0][i];
+  else p.tbuf[0][i] = (float)p.temp64[i];
+}
+__global__ void k_mirror_q(const Params p) {
+  const size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < (size_t)p.B * p.Z) p.qcv64[i] = (double)p.qcv[i];
 }
 
 // dst[b] = tbuf[cur[b]][b]  (download of building.temp in the streaming path)

@@ -68,7 +68,14 @@ class SimulatorBuilding:
                floor_height_cm: float = 300.0,
                initial_temp: Union[float, np.ndarray] = 294.0,
                reset_temp_values: Optional[np.ndarray] = None,
-               convection_simulator=None):
+               convection_simulator=None,
+               solver: str = "tf_jacobi"):
+    # The reference picks the diffusion model by simulator class: TFSimulator
+    # (fp32 Jacobi, tf_simulator.py:502; calibrated config) or
+    # SimulatorFlexibleGeometries (fp64 Gauss-Seidel, simulator.py:278; legacy config).
+    if solver not in ("tf_jacobi", "gauss_seidel"):
+      raise ValueError("solver must be 'tf_jacobi' or 'gauss_seidel'")
+    self.solver = solver
     self.convection_simulator = convection_simulator
     if isinstance(plans, floorplan.CompiledPlan):
       plans = [plans]
@@ -220,6 +227,8 @@ class Environment:
     cfg.episode_steps = self._num_timesteps_in_episode
     cfg.n_table_steps = self._num_timesteps_in_episode + 3
     cfg.kernel_path = int(kernel_path)
+    cfg.solver = (_lib.SOLVER_GAUSS_SEIDEL if b.solver == "gauss_seidel"
+                  else _lib.SOLVER_TF_JACOBI)
     cfg.time_step_sec = b.time_step_sec
     cfg.floor_height_m = b.floor_height_cm / 100.0
     cfg.convergence_threshold = b.convergence_threshold

@@ -143,7 +143,8 @@ def make_oracle(sc: Scenario, cp: Optional[floorplan.CompiledPlan] = None,
 
 
 def make_env(sc: Scenario, n_envs: int = 1, plans=None, weather=None, initial_temp=None,
-             kernel_path: int = sbx.PATH_AUTO, device: int = 0) -> sbx.Environment:
+             kernel_path: int = sbx.PATH_AUTO, device: int = 0,
+             solver: str = "tf_jacobi") -> sbx.Environment:
   plans = plans or sc.compiled()
   schedule = sbx.SetpointSchedule(6, 19, (294, 297), (289, 298), time_zone=sc.schedule_tz)
   weather = weather or sbx.WeatherController(sc.weather_low, sc.weather_high,
@@ -164,7 +165,7 @@ def make_env(sc: Scenario, n_envs: int = 1, plans=None, weather=None, initial_te
       initial_temp=sc.initial_temp if initial_temp is None else initial_temp,
       reset_temp_values=sc.reset_temp_values,
       convection_simulator=(sbx.StochasticConvectionSimulator(*sc.convection)
-                            if sc.convection else None))
+                            if sc.convection else None), solver=solver)
   reward = sbx.SetpointEnergyCarbonRegretFunction(
       300.0, 100.0, 160000, 400000, 0.5, 4.3, sbx.ElectricityEnergyCost(),
       sbx.NaturalGasEnergyCost(), 0.2, 0.4, 0.4)

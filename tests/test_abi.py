@@ -48,7 +48,7 @@ def test_header_constants_match_binding():
   assert val("SBX_N_DEVICE_FIELDS") == _lib.N_DEVICE_FIELDS
   assert val("SBX_DESC_DIFFUSER") == _lib.DESC_DIFFUSER
   assert val("SBX_ZONE_NONE") == _lib.ZONE_NONE
-  fields = dict(re.findall(r"(SBX_F_[A-Z_]+)\s*=\s*(\d+)", text))
+  fields = dict(re.findall(r"(SBX_F_[A-Z_0-9]+)\s*=\s*(\d+)", text))
   for name, (fid, _) in _lib.FIELDS.items():
     assert int(fields["SBX_F_" + name.upper()]) == fid, name
   diag = dict(re.findall(r"(SBX_DIAG_[A-Z_]+)\s*=\s*(\d+)", text))

@@ -273,3 +273,61 @@ def test_stochastic_convection_replay_matches_oracle(path):
     assert np.abs(np.diff(temp[0][5:10, 5:15], axis=1)).max() > 0
   finally:
     env.close()
+
+
+@pytest.mark.parametrize("plan_name", ["tf_test_10x9", "small_24x34", "odd_23x31", "rand_64x96"])
+def test_gauss_seidel_fd_step_bit_exact_fp64(plan_name):
+  """the legacy fp64 in-place raster Gauss-Seidel sweep
+  (simulator.py:98-316) as anti-diagonal wavefronts, bit-identical in fp64."""
+  from oracle import gs_solver
+  plan, bfw = _plans()[plan_name]
+  sc = S.Scenario(floor_plan=plan, buffer_from_walls=bfw, cv_size_cm=10.0 if "rand" in plan_name else 20.0)
+  cp = sc.compiled()
+  B = 3
+  env = S.make_env(sc, n_envs=B, plans=cp, solver="gauss_seidel")
+  try:
+    env.reset()
+    rng = np.random.default_rng(5)
+    H, W, Z = cp.height, cp.width, env.building.n_zones
+    temp = rng.uniform(285, 300, (B, H, W))
+    qcv = rng.uniform(-50, 400, (B, Z))
+    ambient = rng.uniform(270, 300, B)
+    conv = rng.uniform(5, 100, B)
+    env.handle.upload("temp64", temp)
+    env.handle.upload("q_cv64", qcv)
+    env.handle.fd_step(ambient, conv)
+    got = env.handle.download("temp64", (B, H, W))
+    sweeps = env.handle.download("n_sweeps", (B,))
+    gs = gs_solver.GaussSeidel(S.oracle_plan(cp, sc.floor_height_cm), sc.time_step_sec,
+                               sc.convergence_threshold, sc.iteration_limit)
+    for b in range(B):
+      want, n, _, _ = gs.fd_step(temp[b], _dense_q(cp, qcv[b]), ambient[b], conv[b])
+      assert sweeps[b] == n, (b, sweeps[b], n)
+      np.testing.assert_array_equal(got[b], want, err_msg=f"env {b}")
+    np.testing.assert_array_equal(env.handle.download("temp", (B, H, W)), got.astype(np.float32))
+  finally:
+    env.close()
+
+
+def test_gauss_seidel_env_matches_unmodified_reference_fixture():
+  """Whole Environment.step() with the GS solver against a rollout of the
+  100 %-unmodified reference stack (tests/golden/ref_env_gs.npz)."""
+  import os
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ref_env_gs.npz"))
+  sc = S.Scenario(floor_plan=g["floor_plan"].astype(np.int64))
+  cp = sc.compiled()
+  env = S.make_env(sc, n_envs=2, plans=cp, solver="gauss_seidel")
+  try:
+    ts = env.reset()
+    np.testing.assert_allclose(ts.observation[0], g["observations"][0], rtol=RTOL, atol=2e-5)
+    for i, a in enumerate(g["actions"]):
+      ts = env.step(np.stack([a, a]))
+      np.testing.assert_allclose(ts.observation[1], g["observations"][i + 1], rtol=RTOL, atol=2e-5,
+                                 err_msg=f"obs step {i}")
+      np.testing.assert_allclose(ts.reward[0], g["rewards"][i + 1], rtol=RTOL, atol=1e-6)
+      zm = env.handle.download("zone_mean", (2, env.building.n_zones))
+      np.testing.assert_allclose(zm[0, :cp.n_zones], g["zone_temps"][i + 1], rtol=RTOL)
+    t64 = env.handle.download("temp64", (2, cp.height, cp.width))
+    np.testing.assert_allclose(t64[0], g["final_temp"], rtol=1e-6)
+  finally:
+    env.close()

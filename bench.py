@@ -55,6 +55,9 @@ def parse_args():
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
   ap.add_argument("--path", choices=["auto", "streaming", "resident"], default="auto")
+  ap.add_argument("--convergence-threshold", type=float, default=0.1,
+                  help="experiments only; BASELINE uses 0.1 K (sim_config.gin:161)")
+  ap.add_argument("--iteration-limit", type=int, default=100)
   return ap.parse_args()
 
 
@@ -132,7 +135,8 @@ def build_env(args, rank, local_rank):
     n = args.envs_per_gpu or 32768
     env, wl = workloads.make_randomized_env(
         n, seed=2024 + rank, episode_steps=episode, n_layouts=args.layouts,
-        histogram=bool(args.histogram), device=local_rank, kernel_path=path)
+        histogram=bool(args.histogram), device=local_rank, kernel_path=path,
+        convergence_threshold=args.convergence_threshold, iteration_limit=args.iteration_limit)
     desc = {"workload": "randomized-64x96 (BASELINE.json configs[3] per-GPU shard)",
             "envs_per_gpu": n, "grid": [64, 96], "layouts": wl.n_layouts,
             "plans": "per-env descriptor, materials, weather, T0, actions"}

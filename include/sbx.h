@@ -212,7 +212,9 @@ enum {
   SBX_F_STEP_DIAG = 62,    /* f64 [B,SBX_DIAG_N], see SBX_DIAG_* */
   SBX_F_Q_ZONE = 63,       /* f64 [B,Z]  VAV thermal power per zone computed this step */
   SBX_F_ZONE_SUPPLY_TEMP = 64, /* f64 [B,Z] */
-  SBX_F_PRE_ZONE_MEAN = 65 /* f32 [B,Z]  zone means the thermostats saw this step */
+  SBX_F_PRE_ZONE_MEAN = 65,/* f32 [B,Z]  zone means the thermostats saw this step */
+  SBX_F_PHASE_CYCLES = 66  /* u64 [8]    per-phase SM cycles of the resident kernel, summed over CTAs;
+                              only filled by builds with -DSBX_PROFILE_PHASES (profiling aid) */
 };
 
 enum {

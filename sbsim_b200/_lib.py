@@ -61,6 +61,7 @@ FIELDS = {
     "n_sweeps": (60, np.int32), "max_delta": (61, np.float32),
     "step_diag": (62, np.float64), "q_zone": (63, np.float64),
     "zone_supply_temp": (64, np.float64), "pre_zone_mean": (65, np.float32),
+    "phase_cycles": (66, np.uint64),
 }
 
 DIAG = {

@@ -33,7 +33,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
     return OUT
   os.makedirs(os.path.dirname(OUT), exist_ok=True)
   nvcc = os.environ.get("NVCC", "nvcc")
-  cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+  extra = os.environ.get("NVCC_EXTRA", "").split()
+  cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
   res = subprocess.run(cmd, capture_output=True, text=True)
   if res.returncode != 0:
     sys.stderr.write(res.stdout + res.stderr)

@@ -217,7 +217,7 @@ int launch_check(sbx_handle h, const char* what) {
 
 int launch_zone_reduce(sbx_handle h, cudaStream_t st) {
   const Params& p = h->P;
-  CUDA_TRY(h, cudaMemsetAsync(p.zone_sum, 0, sizeof(double) * (size_t)p.B * (p.Z + 1), st));
+  CUDA_TRY(h, cudaMemsetAsync(p.zone_sum, 0, sizeof(long long) * (size_t)p.B * (p.Z + 1), st));
   const StreamTiling tl = stream_tiling(p.H, p.W, h->V);
   const unsigned grid = (unsigned)((size_t)tl.tiles * p.B);
   if (h->V == 4) k_zone_reduce<4><<<grid, kStreamThreads, 0, st>>>(p);
@@ -274,6 +274,11 @@ int run_resident(sbx_handle h, cudaStream_t st) {
   }
   if (int rc = prepare_plans(h, st)) return rc;
   const Params& p = h->P;
+  {
+    const int wpb = 4;
+    k_build_header<<<(unsigned)((p.B + wpb - 1) / wpb), wpb * 32, 0, st>>>(p);
+    if (int rc = launch_check(h, "k_build_header")) return rc;
+  }
   if (h->V == 4) k_resident_step<4><<<p.B, kResidentThreads, h->resident_smem, st>>>(p);
   else k_resident_step<1><<<p.B, kResidentThreads, h->resident_smem, st>>>(p);
   return launch_check(h, "k_resident_step");
@@ -396,7 +401,7 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   const ResidentLayout L = resident_layout((int)N, (int)Z, h->V);
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const bool fits = L.total <= (size_t)max_optin && N / h->V <= 65535;
+  const bool fits = L.total <= (size_t)max_optin && N / h->V <= 32767;
   if (c.kernel_path == SBX_PATH_RESIDENT && !fits) {
     fail(h, SBX_E_INVALID, "resident path needs %zu B of shared memory per CTA; device allows %d", L.total, max_optin);
     return bail(SBX_E_INVALID);
@@ -443,6 +448,7 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.desc_packed, uint16_t, (size_t)c.n_plans * N);
   ALLOC(p.qlist, uint16_t, (size_t)c.n_plans * (N / h->V));
   ALLOC(p.n_fast, int32_t, (size_t)c.n_plans);
+  ALLOC(p.hdr, unsigned char, B * header_bytes((int)Z));
   ALLOC(p.reset_temps, float, (size_t)c.n_reset * N);
   ALLOC(p.initial_temp, float, B);
   ALLOC(p.ambient, double, (size_t)c.n_weather * T);
@@ -481,10 +487,11 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.n_sweeps, int32_t, B);
   ALLOC(p.max_delta_bits, uint32_t, B);
   ALLOC(p.max_delta, float, B);
-  ALLOC(p.zone_sum, double, B * (Z + 1));
+  ALLOC(p.zone_sum, long long, B * (Z + 1));
   ALLOC(p.active, uint8_t, B);
   ALLOC(p.n_active, int32_t, 1);
   ALLOC(p.sweeps_total, unsigned long long, 1);
+  ALLOC(p.phase_cycles, unsigned long long, 8);
   ALLOC(h->carry, CarryStore, B);
   ALLOC(h->fd_ambient, double, B);
   ALLOC(h->fd_convection, double, B);
@@ -595,6 +602,7 @@ static int field_info(sbx_handle h, int field, FieldInfo* fi) {
     F(SBX_F_Q_ZONE, p.q_zone, B * Z, double, false);
     F(SBX_F_ZONE_SUPPLY_TEMP, p.zone_supply, B * Z, double, false);
     F(SBX_F_PRE_ZONE_MEAN, p.pre_zone_mean, B * Z, float, false);
+    F(SBX_F_PHASE_CYCLES, p.phase_cycles, 8, unsigned long long, true);
     default: break;
   }
 #undef F

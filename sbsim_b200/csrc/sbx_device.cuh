@@ -40,9 +40,11 @@ struct __align__(16) Combo {
   float k1, k3, k2, k4;
   // T_inf*h of the ambient-facing horizontal side (left OR right: no class has
   // both, so (x + hl) + hr == x + hh exactly) and of the vertical side
-  float hh, hv, vz, uz;
-  float den, cm, rden, pad1;     // cm = ((((rho*U)*V)*c)*z)*c ; rden = RN(1/den)
+  float hh, hv, den, rden;       // rden = RN(1/den)
+  float vz, uz, cm, pad1;        // cm = ((((rho*U)*V)*c)*z)*c
 };
+// packed descriptor bits (k_prepare_plan): combo index | half-U | diffuser | half-V | zone
+constexpr uint32_t kPackIdxMask = 31u, kPackHalfU = 0x20u, kPackHalfV = 0x80u;
 
 // Everything a kernel needs; passed by value.
 struct Params {
@@ -76,6 +78,7 @@ struct Params {
   uint16_t* desc_packed;     // [P,H,W] combo index | diffuser | zone (k_prepare_plan)
   uint16_t* qlist;           // [P,H*W/V] fast vectors from the front, slow from the back
   int32_t* n_fast;           // [P]
+  unsigned char* hdr;        // [B, header_bytes(Z)] per-building solve header (k_build_header)
   const float* reset_temps;  // [n_reset,H,W]
   const float* initial_temp; // [B]
   // tables
@@ -117,10 +120,11 @@ struct Params {
   int32_t* n_sweeps;         // [B]
   uint32_t* max_delta_bits;  // [B] fp32 bits of the running max (non-negative => uint order)
   float* max_delta;          // [B] last completed sweep's max
-  double* zone_sum;          // [B,Z+1] streaming path; slot Z = whole grid
+  long long* zone_sum;       // [B,Z+1] fixed-point (2^-32 K) zone sums; slot Z = whole grid
   uint8_t* active;           // [B]
   int32_t* n_active;         // [1]
   unsigned long long* sweeps_total;  // [1]
+  unsigned long long* phase_cycles;  // [8] only with -DSBX_PROFILE_PHASES
   const int32_t* conv_perm;  // [B,H*W] or null: convection gather map for this step
   // sbx_fd_step: solve only, ambient / convection given per env
   int fd_only;
@@ -218,14 +222,6 @@ __device__ inline Combo make_combo(int cls, const double* mat /*k,c,rho*/, doubl
   o.hv = sb ? mul(t_inf, hb) : mul(t_inf, ht);
   o.rden = __frcp_rn(o.den);
   o.pad1 = 0.f;
-  if (cls == SBX_CV_EXTERIOR) {
-    // apply_exterior_temps (:847-849) folded into the coefficients: with
-    // k = 0, hh = T_inf, vz = den = 1, cm = 0 the generic expression evaluates
-    // to exactly T_inf ((0*a + 0*b) + T_inf = T_inf; + 0 terms; / 1).
-    o.k1 = o.k3 = o.k2 = o.k4 = 0.f;
-    o.hh = t_inf; o.hv = 0.f; o.vz = 1.f; o.uz = 1.f;
-    o.den = 1.f; o.rden = 1.f; o.cm = 0.f;
-  }
   return o;
 }
 
@@ -250,31 +246,50 @@ __device__ __forceinline__ float cv_cm(uint32_t d, const Combo* tab) {
 }
 
 // One CV update (tf_simulator.py:719-754, 843, 847-849), branch-free: every
-// class runs the same instruction stream with its own coefficients (three
-// 128-bit shared-memory loads, broadcast when a warp shares a class), so warps
-// that mix interior / wall / boundary / exterior CVs do not diverge.
+// class runs the same instruction stream with its own coefficients, so warps that
+// mix interior / wall / boundary / exterior CVs do not diverge.  Two 128-bit
+// shared-memory loads fetch {k1,k3,k2,k4} and {hh,hv,den,rden}; the face areas
+// vz / uz take one of two per-building values (full or half cell) selected by a
+// descriptor bit; exterior CVs (combo index < 3) are overridden with T_inf.
 //   t_jp = T(i,j+1), t_jm = T(i,j-1), t_im = T(i-1,j), t_ip = T(i+1,j)
 //   n3 = ((cm * T_prev) / dt)   precomputed (:743-749)
 //   q  = input_q at this CV (0 unless it is a diffuser)
-__device__ __forceinline__ float cv_update_idx(int idx, float t_jp, float t_jm, float t_im,
-                                               float t_ip, float n3, float q, const Combo* tab) {
+struct AreaCoef {
+  float full, half;   // z * dx, z * (dx / 2)   (:791-792)
+};
+__device__ __forceinline__ float cv_update_packed(uint32_t d, float t_jp, float t_jm, float t_im,
+                                                  float t_ip, float n3, float q, float t_inf,
+                                                  const AreaCoef& az, const Combo* tab) {
+  const int idx = (int)(d & kPackIdxMask);
   const float4* c4 = reinterpret_cast<const float4*>(tab + idx);
-  const float4 k = c4[0], h = c4[1], dd = c4[2];
+  const float4 k = c4[0], h = c4[1];
+  const float vz = (d & kPackHalfV) ? az.half : az.full;
+  const float uz = (d & kPackHalfU) ? az.half : az.full;
   float n1 = add(mul(k.x, t_jp), mul(k.y, t_jm));       // :719-720, 731
   n1 = add(n1, h.x);                                    // :732-733
-  n1 = mul(h.z, n1);                                    // :734
+  n1 = mul(vz, n1);                                     // :734
   float n2 = add(mul(k.z, t_ip), mul(k.w, t_im));       // :721-722, 737
   n2 = add(n2, h.y);                                    // :738-739
-  n2 = mul(h.w, n2);                                    // :740
+  n2 = mul(uz, n2);                                     // :740
   const float num = add(add(add(n1, n2), n3), q);       // :752-754
-  return div_rn(num, dd.x, dd.z);                       // :843
+  const float t = div_rn(num, h.z, h.w);                // :843
+  return idx < kNumMaterials ? t_inf : t;               // :847-849 (class EXTERIOR == 0)
 }
 
+// same update from a raw descriptor (streaming path)
 __device__ __forceinline__ float cv_update(uint32_t d, float t_jp, float t_jm, float t_im,
                                            float t_ip, float n3, float q, float t_inf,
                                            const Combo* tab) {
-  (void)t_inf;
-  return cv_update_idx(combo_index(d), t_jp, t_jm, t_im, t_ip, n3, q, tab);
+  const Combo& c = tab[combo_index(d)];
+  float n1 = add(mul(c.k1, t_jp), mul(c.k3, t_jm));
+  n1 = add(n1, c.hh);
+  n1 = mul(c.vz, n1);
+  float n2 = add(mul(c.k2, t_ip), mul(c.k4, t_im));
+  n2 = add(n2, c.hv);
+  n2 = mul(c.uz, n2);
+  const float num = add(add(add(n1, n2), n3), q);
+  const float t = div_rn(num, c.den, c.rden);
+  return desc_class(d) == SBX_CV_EXTERIOR ? t_inf : t;
 }
 
 // Interior CV of the dominant material with no heat input: coefficients are
@@ -291,6 +306,21 @@ __device__ __forceinline__ float cv_update_fast(const FastCoef& f, float t_jp, f
   n2 = mul(f.vz, n2);
   const float num = add(add(n1, n2), n3);                // + q with q == 0 is exact
   return div_rn(num, f.den, f.rden);
+}
+
+// Zone / grid sums are accumulated as 64-bit fixed point with 32 fractional bits.
+// An fp32 temperature (|T| >= 2^-9 K) converts EXACTLY, integer addition is
+// associative, so the sums -- and therefore the zone means the thermostats and the
+// reward see -- are exact and independent of the order in which warps, CTAs or
+// atomics happen to run (bitwise reproducible), and shared-memory integer atomics
+// are native (no compare-and-swap loop as for fp64).
+constexpr double kFixScale = 4294967296.0;   // 2^32
+// t * 2^32 is exact in fp32 (power-of-two scaling) and integer-valued for |t| >= 2^-9
+__device__ __forceinline__ long long to_fix(float t) { return __float2ll_rz(t * 4294967296.0f); }
+__device__ __forceinline__ long long to_fix(double t) { return __double2ll_rn(t * kFixScale); }
+__device__ __forceinline__ double from_fix(long long s) { return (double)s / kFixScale; }
+__device__ __forceinline__ void fix_add(long long* addr, long long v) {
+  atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)v);
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -124,8 +124,17 @@ __device__ __forceinline__ void tma_store_wait() {
 // resident path
 // ---------------------------------------------------------------------------
 
+// Per-building header the solve kernels consume, built by k_build_header and
+// fetched with one TMA bulk copy: the 30-entry coefficient table for this
+// building's (h, T_inf), the heat input per diffuser CV of each zone (slot Z = 0:
+// "no heat input"), and {T_inf, n_fast}.
+__host__ __device__ inline size_t header_q_slots(int Z) { return (size_t)((Z + 1 + 3) / 4) * 4; }
+__host__ __device__ inline size_t header_bytes(int Z) {
+  return sizeof(Combo) * kNumCombos + header_q_slots(Z) * 4 + 16;
+}
+
 struct ResidentLayout {
-  size_t off_a, off_b, off_n3, off_desc, off_list, off_tab, off_qcv, off_bins, off_wmax,
+  size_t off_a, off_b, off_n3, off_desc, off_list, off_hdr, off_bins, off_wmax,
       off_bar, total;
 };
 
@@ -138,8 +147,7 @@ __host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z, int V
   L.off_n3 = o; o = al(o + (size_t)n_cv * 4);
   L.off_desc = o; o = al(o + (size_t)n_cv * 2);
   L.off_list = o; o = al(o + (size_t)(n_cv / V) * 2);
-  L.off_tab = o; o = al(o + sizeof(Combo) * kNumCombos);
-  L.off_qcv = o; o = al(o + (size_t)(Z + 1) * 4);
+  L.off_hdr = o; o = al(o + header_bytes(Z));
   L.off_bins = o; o = al(o + (size_t)(Z + 1) * 8 * (kResidentThreads / 32 + 1));
   L.off_wmax = o; o = al(o + 32 * 4);
   L.off_bar = o; o = al(o + 16);
@@ -147,25 +155,26 @@ __host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z, int V
   return L;
 }
 
-// Accumulates V consecutive CVs into per-zone shared bins (fp64) + grid total.
+// Accumulates V consecutive CVs into per-zone shared bins (fixed point) + grid total.
 // (streaming path: one atomic per run of equal zone ids)
 template <int V>
 __device__ __forceinline__ void zone_accumulate(const float (&t)[V], const uint32_t (&d)[V],
-                                                double* bins, double& total) {
+                                                long long* bins, long long& total) {
   int z0 = desc_zone(d[0]);
-  double run = 0.0;
+  long long run = 0;
 #pragma unroll
   for (int e = 0; e < V; ++e) {
     const int z = desc_zone(d[e]);
-    total += (double)t[e];
+    const long long v = to_fix(t[e]);
+    total += v;
     if (z != z0) {
-      if (z0 != SBX_ZONE_NONE) atomicAdd(&bins[z0], run);
+      if (z0 != SBX_ZONE_NONE) fix_add(&bins[z0], run);
       z0 = z;
-      run = 0.0;
+      run = 0;
     }
-    run += (double)t[e];
+    run += v;
   }
-  if (z0 != SBX_ZONE_NONE) atomicAdd(&bins[z0], run);
+  if (z0 != SBX_ZONE_NONE) fix_add(&bins[z0], run);
 }
 
 // Warp-cooperative version for 32 consecutive vectors (one per lane): zone ids
@@ -174,10 +183,10 @@ __device__ __forceinline__ void zone_accumulate(const float (&t)[V], const uint3
 // bins.  Vectors that straddle a zone boundary flush their tail directly.
 template <int V>
 __device__ __forceinline__ void zone_accumulate_warp(const float (&t)[V], const uint32_t (&d)[V],
-                                                     bool valid, int lane, double* wbins,
-                                                     double& total) {
+                                                     bool valid, int lane, long long* wbins,
+                                                     long long& total) {
   int z = SBX_ZONE_NONE;
-  double s = 0.0;
+  long long s = 0;
   if (valid) {
     // primary zone of the vector = its first CV that belongs to a room (walls and
     // exterior carry SBX_ZONE_NONE); CVs of a second room in the same vector are
@@ -185,11 +194,12 @@ __device__ __forceinline__ void zone_accumulate_warp(const float (&t)[V], const 
 #pragma unroll
     for (int e = 0; e < V; ++e) {
       const int ze = desc_zone(d[e]);
-      total += (double)t[e];
+      const long long v = to_fix(t[e]);
+      total += v;
       if (ze == SBX_ZONE_NONE) continue;
       if (z == SBX_ZONE_NONE) z = ze;
-      if (ze == z) s += (double)t[e];
-      else atomicAdd(&wbins[ze], (double)t[e]);
+      if (ze == z) s += v;
+      else fix_add(&wbins[ze], v);
     }
   }
   const int z_prev = __shfl_up_sync(0xffffffffu, z, 1);
@@ -198,18 +208,47 @@ __device__ __forceinline__ void zone_accumulate_warp(const float (&t)[V], const 
   const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));
 #pragma unroll
   for (int o = 1; o < 32; o <<= 1) {
-    const double s_up = __shfl_down_sync(0xffffffffu, s, o);
+    const long long s_up = __shfl_down_sync(0xffffffffu, s, o);
     const int seg_up = __shfl_down_sync(0xffffffffu, seg, o);
     if (lane + o < 32 && seg_up == seg) s += s_up;
   }
-  if (head && z != SBX_ZONE_NONE) atomicAdd(&wbins[z], s);
+  if (head && z != SBX_ZONE_NONE) fix_add(&wbins[z], s);
 }
 
 // Packed descriptor: combo index (5 bits) | diffuser flag | zone.
 __device__ __forceinline__ uint32_t repack_desc(uint32_t d) {
-  return (uint32_t)combo_index(d) | (d & SBX_DESC_DIFFUSER) | (d & 0xFF00u);
+  const int cls = desc_class(d);
+  const bool half_u = cls == SBX_CV_EDGE_LEFT || cls == SBX_CV_EDGE_RIGHT || cls >= SBX_CV_CORNER_TL;
+  const bool half_v = cls == SBX_CV_EDGE_TOP || cls == SBX_CV_EDGE_BOTTOM || cls >= SBX_CV_CORNER_TL;
+  return (uint32_t)combo_index(d) | (half_u ? kPackHalfU : 0u) | (d & SBX_DESC_DIFFUSER) |
+         (half_v ? kPackHalfV : 0u) | (d & 0xFF00u);
 }
 constexpr uint32_t kFastDesc = SBX_CV_INTERIOR | (0u << SBX_DESC_MATERIAL_SHIFT);  // interior, air, no diffuser
+
+// Warp per building: coefficient table + per-zone heat + scalars -> hdr[b].
+__global__ void __launch_bounds__(128) k_build_header(const Params p) {
+  const int wpb = blockDim.x / 32;
+  const int b = blockIdx.x * wpb + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31;
+  if (b >= p.B) return;
+  const int Z = p.Z;
+  const int plan = p.n_plans == 1 ? 0 : b;
+  unsigned char* h8 = p.hdr + (size_t)b * header_bytes(Z);
+  Combo* tab = reinterpret_cast<Combo*>(h8);
+  float* qcv = reinterpret_cast<float*>(h8 + sizeof(Combo) * kNumCombos);
+  float* scal = qcv + header_q_slots(Z);
+  const float t_inf = (float)env_ambient(p, b, p.time_index);   // tf_simulator.py:785
+  const float h = (float)env_convection(p, b);
+  build_combo_table(tab, p, plan, b, h, t_inf, lane, 32);
+  for (int zi = lane; zi < (int)header_q_slots(Z); zi += 32)
+    qcv[zi] = zi < Z ? p.qcv[(size_t)b * Z + zi] : 0.f;
+  if (lane == 0) {
+    scal[0] = t_inf;
+    scal[1] = h;
+    scal[2] = __int_as_float(p.n_fast ? p.n_fast[plan] : 0);
+    scal[3] = 0.f;
+  }
+}
 
 // Once per uploaded plan: repack the descriptors and split the plan's vectors
 // into a FAST list (every CV interior, air, no heat input: uniform register
@@ -257,8 +296,13 @@ __global__ void k_prepare_plan(const Params p) {
       int pos = 0;                       // entries sorted before (m, res)
 #pragma unroll
       for (int r = 0; r < 8; ++r) pos += min(sizes[r], m) + ((r < res && sizes[r] > m) ? 1 : 0);
-      if (kind == 0) qlist[pos] = (uint16_t)it;
-      else qlist[n_items - 1 - pos] = (uint16_t)it;
+      if (kind == 0) {
+        qlist[pos] = (uint16_t)it;
+      } else {
+        bool diff = false;                 // bit 15: the vector holds a diffuser CV
+        for (int e = 0; e < V; ++e) diff = diff || (raw[it * V + e] & SBX_DESC_DIFFUSER);
+        qlist[n_items - 1 - pos] = (uint16_t)(it | (diff ? 0x8000 : 0));
+      }
       ++m;
     }
   }
@@ -272,7 +316,7 @@ template <int V, bool FIRST>
 __device__ __forceinline__ float resident_sweep(
     const float* __restrict__ in, float* __restrict__ out, float* __restrict__ n3p,
     const uint16_t* __restrict__ dsc, const uint16_t* __restrict__ qlist, const Combo* tab,
-    const float* qcv, const FastCoef& fc, float cm_fast, float dt, float rdt, float t_inf,
+    const float* qcv, const FastCoef& fc, const AreaCoef& az, float cm_fast, float dt, float rdt, float t_inf,
     int n_fast, int n_items, int H, int W, int Z, unsigned wq_magic, int tid) {
   constexpr int NT = kResidentThreads;
   const int wq = W / V;
@@ -306,7 +350,9 @@ __device__ __forceinline__ float resident_sweep(
   // low thread ids with one more iteration, so this evens out the work per warp
   // before the sweep barrier
   for (int i = NT - 1 - tid; i < n_slow; i += NT) {
-    const int it = (int)qlist[n_items - 1 - i];
+    const int entry = (int)qlist[n_items - 1 - i];
+    const int it = entry & 0x7FFF;
+    const bool has_q = (entry & 0x8000) != 0;
     const int base = it * V;
     const int r = (int)__umulhi((unsigned)it, wq_magic);
     const int q = it - r * wq;
@@ -329,8 +375,9 @@ __device__ __forceinline__ float resident_sweep(
     for (int e = 0; e < V; ++e) {
       const float t_jm = e == 0 ? left : c[e - 1];
       const float t_jp = e == V - 1 ? right : c[e + 1];
-      const int slot = (d[e] & SBX_DESC_DIFFUSER) ? (int)(d[e] >> SBX_DESC_ZONE_SHIFT) : Z;
-      o[e] = cv_update_idx((int)(d[e] & 31u), t_jp, t_jm, up[e], dn[e], n3v[e], qcv[slot], tab);
+      float qv = 0.f;
+      if (has_q) qv = qcv[(d[e] & SBX_DESC_DIFFUSER) ? (int)(d[e] >> SBX_DESC_ZONE_SHIFT) : Z];
+      o[e] = cv_update_packed(d[e], t_jp, t_jm, up[e], dn[e], n3v[e], qv, t_inf, az, tab);
       lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));
     }
     store_f<V>(out + base, o);
@@ -338,9 +385,27 @@ __device__ __forceinline__ float resident_sweep(
   return lmax;
 }
 
+// Optional per-phase cycle counters (build with -DSBX_PROFILE_PHASES; read back with
+// SBX_F_PHASE_CYCLES).  Thread 0 of every CTA adds its phase durations.
+#ifdef SBX_PROFILE_PHASES
+#define SBX_PHASE(i)                                                                 \
+  do {                                                                               \
+    if (tid == 0) {                                                                  \
+      const long long now__ = clock64();                                             \
+      atomicAdd(&p.phase_cycles[i], (unsigned long long)(now__ - phase_t0__));       \
+      phase_t0__ = now__;                                                            \
+    }                                                                                \
+  } while (0)
+#else
+#define SBX_PHASE(i) do {} while (0)
+#endif
+
 template <int V>
 __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
+#ifdef SBX_PROFILE_PHASES
+  long long phase_t0__ = clock64();
+#endif
   const int b = blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = kResidentThreads, NW = NT / 32;
@@ -354,22 +419,26 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   float* n3p = reinterpret_cast<float*>(smem + L.off_n3);
   uint16_t* dsc = reinterpret_cast<uint16_t*>(smem + L.off_desc);
   uint16_t* qlist = reinterpret_cast<uint16_t*>(smem + L.off_list);
-  Combo* tab = reinterpret_cast<Combo*>(smem + L.off_tab);
-  float* qcv = reinterpret_cast<float*>(smem + L.off_qcv);
-  double* bins = reinterpret_cast<double*>(smem + L.off_bins);
+  Combo* tab = reinterpret_cast<Combo*>(smem + L.off_hdr);
+  float* qcv = reinterpret_cast<float*>(smem + L.off_hdr + sizeof(Combo) * kNumCombos);
+  const float* scal = qcv + header_q_slots(Z);
+  long long* bins = reinterpret_cast<long long*>(smem + L.off_bins);
   float* wmax = reinterpret_cast<float*>(smem + L.off_wmax);
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
 
   float* gT = p.tbuf[0] + (size_t)b * n_cv;
   const uint16_t* gD = p.desc_packed + (size_t)plan * n_cv;
   const uint16_t* gL = p.qlist + (size_t)plan * n_items;
+  const uint32_t hdr_bytes = (uint32_t)header_bytes(Z);
+  const unsigned char* gH = p.hdr + (size_t)b * hdr_bytes;
   const bool use_tma = (n_cv % 8) == 0 && (n_items % 8) == 0;
 
   // ---- stage 0: start the bulk loads (TMA, one mbarrier) ----------------------
   if (use_tma) {
     if (tid == 0) {
       mbar_init(bar, 1);
-      mbar_expect_tx(bar, (uint32_t)(n_cv * 4 + n_cv * 2 + n_items * 2));
+      mbar_expect_tx(bar, (uint32_t)(n_cv * 4 + n_cv * 2 + n_items * 2) + hdr_bytes);
+      tma_load_1d(smem + L.off_hdr, gH, hdr_bytes, bar);
       tma_load_1d(bufA, gT, (uint32_t)(n_cv * 4), bar);
       tma_load_1d(dsc, gD, (uint32_t)(n_cv * 2), bar);
       tma_load_1d(qlist, gL, (uint32_t)(n_items * 2), bar);
@@ -380,29 +449,27 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
       dsc[i] = gD[i];
     }
     for (int i = tid; i < n_items; i += NT) qlist[i] = gL[i];
+    for (int i = tid; i < (int)(hdr_bytes / 4); i += NT)
+      reinterpret_cast<uint32_t*>(smem + L.off_hdr)[i] = reinterpret_cast<const uint32_t*>(gH)[i];
   }
 
-  // ---- stage 1: per-building constants while the copies are in flight ---------
-  const double amb_d = env_ambient(p, b, p.time_index);
-  const float t_inf = (float)amb_d;                       // tf_simulator.py:785
-  const float h = (float)env_convection(p, b);
-  const int n_fast = p.n_fast[plan];
-  if (warp == 0) {
-    for (int zi = lane; zi < Z; zi += 32) qcv[zi] = p.qcv[(size_t)b * Z + zi];
-    if (lane == 0) qcv[Z] = 0.f;                          // slot Z: "no heat input"
-  } else if (warp == 1) {
-    build_combo_table(tab, p, plan, b, h, t_inf, lane, 32);
-  } else if (warp == 2) {
-    for (int i = lane; i < (Z + 1) * (NW + 1); i += 32) bins[i] = 0.0;
-  }
+  // ---- stage 1: zero the zone bins while the copies are in flight ---------------
+  for (int i = tid; i < (Z + 1) * (NW + 1); i += NT) bins[i] = 0;
   __syncthreads();
+  SBX_PHASE(0);   // launch .. TMA issued
   if (use_tma) mbar_wait(bar, 0);
+  SBX_PHASE(1);   // waiting for the TMA loads
+  const float t_inf = scal[0];
+  const int n_fast = __float_as_int(scal[2]);
   FastCoef fc;
   {
     const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + 0];
     fc.kq = c.k1; fc.vz = c.vz; fc.den = c.den; fc.rden = c.rden;
   }
   const float cm_fast = tab[SBX_CV_INTERIOR * kNumMaterials + 0].cm;
+  AreaCoef az;
+  az.full = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
+  az.half = tab[SBX_CV_CORNER_TL * kNumMaterials].vz;
   const float rdt = __frcp_rn(p.dt);
   const unsigned wq_magic = 0xFFFFFFFFu / (unsigned)(W / V) + 1u;   // it / wq for it < 2^16
 
@@ -416,16 +483,17 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     ++k;
     float lmax;
     if (k == 1)
-      lmax = resident_sweep<V, true>(in, out, n3p, dsc, qlist, tab, qcv, fc, cm_fast, p.dt, rdt,
+      lmax = resident_sweep<V, true>(in, out, n3p, dsc, qlist, tab, qcv, fc, az, cm_fast, p.dt, rdt,
                                      t_inf, n_fast, n_items, H, W, Z, wq_magic, tid);
     else
-      lmax = resident_sweep<V, false>(in, out, n3p, dsc, qlist, tab, qcv, fc, cm_fast, p.dt, rdt,
+      lmax = resident_sweep<V, false>(in, out, n3p, dsc, qlist, tab, qcv, fc, az, cm_fast, p.dt, rdt,
                                       t_inf, n_fast, n_items, H, W, Z, wq_magic, tid);
     // max|dT| <= threshold  <=>  no thread saw a delta above it (simulator.py:362);
     // the barrier doubles as the ping-pong hazard fence.
     const int above = __syncthreads_or(lmax > p.threshold);
     last_lmax = lmax;
     float* tmp = in; in = out; out = tmp;
+    if (k == 1) SBX_PHASE(2); else SBX_PHASE(3);   // first sweep (computes n3) / later sweeps
     if (!above) break;
   }
   // `in` now holds building.temp for the next step (simulator.py:369)
@@ -448,8 +516,8 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   // block max of the last sweep (diagnostic SBX_F_MAX_DELTA)
   last_lmax = warp_max(last_lmax);
   if (lane == 0) wmax[warp] = last_lmax;
-  double total = 0.0;
-  double* wbins = bins + (size_t)(warp + 1) * (Z + 1);   // warp-private bins
+  long long total = 0;
+  long long* wbins = bins + (size_t)(warp + 1) * (Z + 1);   // warp-private bins
   if (!p.fd_only) {
     for (int base_it = warp * 32; base_it < n_items; base_it += NT) {
       const int it = base_it + lane;
@@ -467,6 +535,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     if (lane == 0) wbins[Z] = total;
   }
   __syncthreads();
+  SBX_PHASE(4);   // convection gather (if any) + zone / grid sums
   if (tid == 0) {
     md = 0.f;
 #pragma unroll
@@ -476,11 +545,11 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     if (!p.fd_only) atomicAdd(p.sweeps_total, (unsigned long long)k);
   }
   if (!p.fd_only) {
-    // fixed-order combine of the warp-private bins (deterministic), handed to
+    // combine the warp-private bins (integer sums: exact, order-free), handed to
     // k_post through zone_sum[b, 0..Z]
-    double* zs = p.zone_sum + (size_t)b * (Z + 1);
+    long long* zs = p.zone_sum + (size_t)b * (Z + 1);
     for (int i = tid; i <= Z; i += NT) {
-      double acc = 0.0;
+      long long acc = 0;
 #pragma unroll
       for (int w = 1; w <= NW; ++w) acc += bins[(size_t)w * (Z + 1) + i];
       zs[i] = acc;
@@ -542,7 +611,7 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
   double* T = reinterpret_cast<double*>(smem + L.off_t);
   double* Tp = reinterpret_cast<double*>(smem + L.off_prev);
   double* qz = reinterpret_cast<double*>(smem + L.off_q);
-  double* bins = reinterpret_cast<double*>(smem + L.off_bins);
+  long long* bins = reinterpret_cast<long long*>(smem + L.off_bins);
   uint16_t* dsc = reinterpret_cast<uint16_t*>(smem + L.off_desc);
   double* gT = p.temp64 + (size_t)b * n_cv;
   const uint16_t* gD = p.desc + (size_t)plan * n_cv;
@@ -554,7 +623,7 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
   }
   for (int i = tid; i <= Z; i += kGsThreads) {
     qz[i] = i < Z ? p.qcv64[(size_t)b * Z + i] : 0.0;
-    bins[i] = 0.0;
+    bins[i] = 0;
   }
   const double t_inf = env_ambient(p, b, p.time_index);
   const double h = env_convection(p, b);
@@ -633,14 +702,15 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
   }
   // write back (fp64 state + fp32 mirror), zone sums for k_post
   float* g32 = p.tbuf[0] + (size_t)b * n_cv;
-  double total = 0.0;
+  long long total = 0;
   for (int i = tid; i < n_cv; i += kGsThreads) {
     const double v = T[i];
     gT[i] = v;
     g32[i] = (float)v;
-    total += v;
+    const long long f = to_fix(v);
+    total += f;
     const int zn = desc_zone(dsc[i]);
-    if (zn != SBX_ZONE_NONE && !p.fd_only) atomicAdd(&bins[zn], v);
+    if (zn != SBX_ZONE_NONE && !p.fd_only) fix_add(&bins[zn], f);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
@@ -648,7 +718,7 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
     md_block = fmax(md_block, __shfl_xor_sync(0xffffffffu, md_block, o));
   }
   if ((tid & 31) == 0) {
-    atomicAdd(&bins[Z], total);
+    fix_add(&bins[Z], total);
     atomicMax(&p.max_delta_bits[b], __float_as_uint((float)md_block));
   }
   __syncthreads();
@@ -659,7 +729,7 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
     if (!p.fd_only) atomicAdd(p.sweeps_total, (unsigned long long)k);
   }
   if (!p.fd_only) {
-    double* zs = p.zone_sum + (size_t)b * (Z + 1);
+    long long* zs = p.zone_sum + (size_t)b * (Z + 1);
     for (int i = tid; i <= Z; i += kGsThreads) zs[i] = bins[i];
   }
 }
@@ -795,7 +865,7 @@ __global__ void k_activate(const Params p) {
 // Zone sums + grid total of building.temp (building.py:845-871, simulator.py:408).
 template <int V>
 __global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) {
-  __shared__ double bins[kMaxZones + 1];
+  __shared__ long long bins[kMaxZones + 1];
   const StreamTiling tl = stream_tiling(p.H, p.W, V);
   const int b = blockIdx.x / tl.tiles;
   const int tile = blockIdx.x - b * tl.tiles;
@@ -804,13 +874,13 @@ __global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) 
   const int H = p.H, W = p.W, Z = p.Z;
   const size_t n_cv = (size_t)H * W;
   const int plan = p.n_plans == 1 ? 0 : b;
-  for (int i = tid; i <= Z; i += kStreamThreads) bins[i] = 0.0;
+  for (int i = tid; i <= Z; i += kStreamThreads) bins[i] = 0;
   __syncthreads();
   const float* __restrict__ t = p.tbuf[p.cur[b]] + (size_t)b * n_cv;
   const uint16_t* __restrict__ dsc = p.desc + (size_t)plan * n_cv;
   const int c0 = (tx * 32 + lane) * V;
   const int r0 = (ty * (kStreamThreads / 32) + warp) * kStreamRowsPerWarp;
-  double total = 0.0;
+  long long total = 0;
   if (c0 < W && r0 < H) {
     const int r1 = min(r0 + kStreamRowsPerWarp, H);
     for (int r = r0; r < r1; ++r) {
@@ -823,11 +893,11 @@ __global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) 
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-  if (lane == 0) atomicAdd(&bins[Z], total);
+  if (lane == 0) fix_add(&bins[Z], total);
   __syncthreads();
-  double* zs = p.zone_sum + (size_t)b * (Z + 1);
+  long long* zs = p.zone_sum + (size_t)b * (Z + 1);
   for (int i = tid; i <= Z; i += kStreamThreads)
-    if (bins[i] != 0.0) atomicAdd(&zs[i], bins[i]);
+    if (bins[i] != 0) fix_add(&zs[i], bins[i]);
 }
 
 struct CarryStore {
@@ -871,10 +941,10 @@ __global__ void __launch_bounds__(128) k_post(const Params p, const CarryStore* 
   float* zpost = zpre + Z;
   const int plan = p.n_plans == 1 ? 0 : b;
   const int32_t* ncv = p.zone_ncv + (size_t)plan * Z;
-  const double* zs = p.zone_sum + (size_t)b * (Z + 1);
+  const long long* zs = p.zone_sum + (size_t)b * (Z + 1);
   for (int zi = lane; zi < Z; zi += 32) {
     const int n = ncv[zi];
-    const float m = n > 0 ? (float)(zs[zi] / (double)n) : 0.f;
+    const float m = n > 0 ? (float)(from_fix(zs[zi]) / (double)n) : 0.f;
     zpost[zi] = m;
     zpre[zi] = p.pre_zone_mean[(size_t)b * Z + zi];
     p.zone_mean[(size_t)b * Z + zi] = m;
@@ -883,7 +953,7 @@ __global__ void __launch_bounds__(128) k_post(const Params p, const CarryStore* 
       p.qcv64[(size_t)b * Z + zi] = p.qcv64_next[(size_t)b * Z + zi];
     }
   }
-  const float gmean = (float)(zs[Z] / (double)((size_t)p.H * p.W));
+  const float gmean = (float)(from_fix(zs[Z]) / (double)((size_t)p.H * p.W));
   if (lane == 0) p.global_mean[b] = gmean;
   __syncwarp();
   Carry cy = {0, 0, 0, 0, 0};

@@ -120,7 +120,8 @@ def randomized(n_envs: int, seed: int = 2024, n_layouts: int = 1024,
 def make_randomized_env(n_envs: int, seed: int = 2024, episode_steps: int = 288,
                         n_layouts: int = 1024, histogram: bool = False, device: int = 0,
                         kernel_path: int = sbx.PATH_AUTO, start: str = DEFAULT_START,
-                        workload: Optional[RandomizedWorkload] = None
+                        workload: Optional[RandomizedWorkload] = None,
+                        convergence_threshold: float = 0.1, iteration_limit: int = 100
                         ) -> Tuple[sbx.Environment, RandomizedWorkload]:
   wl = workload or randomized(n_envs, seed, n_layouts)
   weather = sbx.BatchedWeather(
@@ -130,7 +131,8 @@ def make_randomized_env(n_envs: int, seed: int = 2024, episode_steps: int = 288,
                                   1.0, 0.1)
   building = sbx.SimulatorBuilding(
       wl.plans, calibrated_hvac(), weather, occ, n_envs=n_envs, time_step_sec=300.0,
-      convergence_threshold=0.1, iteration_limit=100, start_timestamp=pd.Timestamp(start),
+      convergence_threshold=convergence_threshold, iteration_limit=iteration_limit,
+      start_timestamp=pd.Timestamp(start),
       floor_height_cm=300.0, initial_temp=wl.initial_temp)
   env = sbx.Environment(
       building, calibrated_reward(), sbx.StandardScoreObservationNormalizer(NORMALIZATION),

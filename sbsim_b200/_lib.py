@@ -13,7 +13,8 @@ from typing import Optional
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libsbx.so")
+# SBX_LIB: developer override used to A/B kernel variants (profiles/); same ABI, same checks
+LIB_PATH = os.environ.get("SBX_LIB") or os.path.join(_HERE, "lib", "libsbx.so")
 
 ABI_VERSION = 2
 OK = 0

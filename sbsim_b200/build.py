@@ -34,14 +34,15 @@ def build(force: bool = False, verbose: bool = False) -> str:
   os.makedirs(os.path.dirname(OUT), exist_ok=True)
   nvcc = os.environ.get("NVCC", "nvcc")
   extra = os.environ.get("NVCC_EXTRA", "").split()
-  cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", OUT, SRC]
+  out = os.environ.get("SBX_LIB_OUT") or OUT     # variant builds for A/B profiling
+  cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", out, SRC]
   res = subprocess.run(cmd, capture_output=True, text=True)
   if res.returncode != 0:
     sys.stderr.write(res.stdout + res.stderr)
     raise RuntimeError("nvcc failed building libsbx.so")
   if verbose:
     sys.stderr.write(res.stderr)
-  return OUT
+  return out
 
 
 if __name__ == "__main__":

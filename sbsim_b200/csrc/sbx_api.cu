@@ -258,10 +258,13 @@ int run_stream_sweeps(sbx_handle h, cudaStream_t st) {
 int prepare_plans(sbx_handle h, cudaStream_t st) {
   if (!h->plans_dirty) return SBX_OK;
   const Params& p = h->P;
-  const int wpb = 4;
-  const unsigned grid = (unsigned)((p.n_plans + wpb - 1) / wpb);
-  if (h->V == 4) k_prepare_plan<4><<<grid, wpb * 32, 0, st>>>(p);
-  else k_prepare_plan<1><<<grid, wpb * 32, 0, st>>>(p);
+  const size_t smem = (sizeof(uint32_t) + sizeof(uint16_t)) * (size_t)(p.H * p.W / h->V);
+  cudaError_t e;
+  if (h->V == 4) e = cudaFuncSetAttribute(k_prepare_plan<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  else e = cudaFuncSetAttribute(k_prepare_plan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+  if (h->V == 4) k_prepare_plan<4><<<p.n_plans, kPrepThreads, smem, st>>>(p);
+  else k_prepare_plan<1><<<p.n_plans, kPrepThreads, smem, st>>>(p);
   if (int rc = launch_check(h, "k_prepare_plan")) return rc;
   h->plans_dirty = 0;
   return SBX_OK;
@@ -488,6 +491,7 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.max_delta_bits, uint32_t, B);
   ALLOC(p.max_delta, float, B);
   ALLOC(p.zone_sum, long long, B * (Z + 1));
+  ALLOC(p.zone_ref, float, B);
   ALLOC(p.active, uint8_t, B);
   ALLOC(p.n_active, int32_t, 1);
   ALLOC(p.sweeps_total, unsigned long long, 1);

@@ -120,7 +120,8 @@ struct Params {
   int32_t* n_sweeps;         // [B]
   uint32_t* max_delta_bits;  // [B] fp32 bits of the running max (non-negative => uint order)
   float* max_delta;          // [B] last completed sweep's max
-  long long* zone_sum;       // [B,Z+1] fixed-point (2^-32 K) zone sums; slot Z = whole grid
+  long long* zone_sum;       // [B,Z+1] integer sums of round((T - zone_ref[b]) * 2^16); slot Z = whole grid
+  float* zone_ref;           // [B] reference temperature of those sums
   uint8_t* active;           // [B]
   int32_t* n_active;         // [1]
   unsigned long long* sweeps_total;  // [1]
@@ -308,19 +309,29 @@ __device__ __forceinline__ float cv_update_fast(const FastCoef& f, float t_jp, f
   return div_rn(num, f.den, f.rden);
 }
 
-// Zone / grid sums are accumulated as 64-bit fixed point with 32 fractional bits.
-// An fp32 temperature (|T| >= 2^-9 K) converts EXACTLY, integer addition is
-// associative, so the sums -- and therefore the zone means the thermostats and the
-// reward see -- are exact and independent of the order in which warps, CTAs or
-// atomics happen to run (bitwise reproducible), and shared-memory integer atomics
-// are native (no compare-and-swap loop as for fp64).
-constexpr double kFixScale = 4294967296.0;   // 2^32
-// t * 2^32 is exact in fp32 (power-of-two scaling) and integer-valued for |t| >= 2^-9
-__device__ __forceinline__ long long to_fix(float t) { return __float2ll_rz(t * 4294967296.0f); }
+// Zone / grid sums are accumulated as integers: each temperature enters as
+// round((T - T_ref) * 2^16), T_ref a per-building reference (the ambient
+// temperature in the resident kernel, 0 elsewhere).  For fp32 temperatures >= 128 K
+// the difference is exact (Sterbenz) and a multiple of 2^-16 K, so the conversion is
+// EXACT; integer addition is associative, so the sums -- and therefore the zone
+// means the thermostats and the reward see -- do not depend on the order in which
+// lanes, warps or atomics happen to run: bitwise reproducible, and exact means.
+constexpr float kFixScaleF = 65536.0f;   // 2^16
+constexpr double kFixScale = 65536.0;
+__device__ __forceinline__ int to_fix32(float t, float ref) {
+  return __float2int_rn(__fmul_rn(__fsub_rn(t, ref), kFixScaleF));   // |T - ref| < 32768 K
+}
+__device__ __forceinline__ long long to_fix(float t) { return (long long)__float2ll_rn(__fmul_rn(t, kFixScaleF)); }
 __device__ __forceinline__ long long to_fix(double t) { return __double2ll_rn(t * kFixScale); }
 __device__ __forceinline__ double from_fix(long long s) { return (double)s / kFixScale; }
 __device__ __forceinline__ void fix_add(long long* addr, long long v) {
   atomicAdd(reinterpret_cast<unsigned long long*>(addr), (unsigned long long)v);
+}
+// exact warp-wide sum of int32 lane values (two hardware REDUX on 16-bit halves)
+__device__ __forceinline__ long long warp_sum_i32(int s) {
+  const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)s & 0xFFFFu);
+  const int hi = __reduce_add_sync(0xffffffffu, s >> 16);
+  return (long long)hi * 65536 + (long long)lo;
 }
 
 __device__ __forceinline__ float warp_max(float v) {

@@ -256,57 +256,74 @@ __global__ void __launch_bounds__(128) k_build_header(const Params p) {
 // (generic, table-driven).  Both lists share one array: fast from the front, slow
 // from the back.
 //
-// Order inside each list: sorted by (rank within the vector's index-mod-8 class,
-// index mod 8).  Every aligned group of 8 list entries then holds 8 DIFFERENT
-// residues mod 8, so the 8 lanes of a quarter-warp touch 8 different 16-byte bank
-// groups and the 128-bit shared-memory loads / stores of the sweep are
-// conflict-free even though the lists skip vectors (a plain ascending list has a
-// gap in almost every quarter-warp, which costs one replay each: profiles/).
-// One warp per plan, fully deterministic.
+// Order inside each list: by zone, then by (rank within the vector's index-mod-8
+// class, index mod 8).
+//   * by zone: a warp's 32 consecutive entries almost always belong to one room, so
+//     the zone sums reduce with one hardware REDUX per warp instead of a segmented
+//     scan plus atomics;
+//   * residue interleave: every aligned group of 8 entries holds 8 different
+//     residues mod 8, so the 8 lanes of a quarter-warp touch 8 different 16-byte
+//     bank groups and the 128-bit shared-memory accesses of the sweep stay
+//     conflict-free although the lists skip vectors.
+// One CTA per plan; ranks are computed by counting smaller keys (O(n^2) on a few
+// thousand items, once per upload), so the order is deterministic.
+constexpr int kPrepThreads = 256;
 template <int V>
-__global__ void k_prepare_plan(const Params p) {
-  const int plan = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (plan >= p.n_plans) return;
+__global__ void __launch_bounds__(kPrepThreads) k_prepare_plan(const Params p) {
+  extern __shared__ __align__(16) unsigned char smem_prep[];
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem_prep);
+  const int n_items_ = p.H * p.W / V;
+  uint16_t* key1 = reinterpret_cast<uint16_t*>(key + n_items_);
+  __shared__ int s_nfast;
+  const int plan = blockIdx.x, tid = threadIdx.x;
   const int n_cv = p.H * p.W, n_items = n_cv / V;
   const uint16_t* raw = p.desc + (size_t)plan * n_cv;
   uint16_t* packed = p.desc_packed + (size_t)plan * n_cv;
   uint16_t* qlist = p.qlist + (size_t)plan * n_items;
-  for (int i = lane; i < n_cv; i += 32) packed[i] = (uint16_t)repack_desc(raw[i]);
-  // lanes 0-7: fast vectors of residue (lane & 7); lanes 8-15: slow vectors
-  const int res = lane & 7, kind = lane >> 3;   // kind 0 fast, 1 slow, >=2 idle
-  auto is_fast = [&](int it) {
-    bool f = true;
-    for (int e = 0; e < V; ++e) f = f && ((raw[it * V + e] & 0x007Fu) == kFastDesc);
-    return f;
-  };
-  int size = 0;
-  if (kind < 2)
-    for (int it = res; it < n_items; it += 8) size += (is_fast(it) == (kind == 0)) ? 1 : 0;
-  int sizes[8];
-#pragma unroll
-  for (int r = 0; r < 8; ++r) sizes[r] = __shfl_sync(0xffffffffu, size, (lane & 8) | r);
-  int total = 0;
-#pragma unroll
-  for (int r = 0; r < 8; ++r) total += sizes[r];
-  if (kind < 2) {
+  if (tid == 0) s_nfast = 0;
+  for (int i = tid; i < n_cv; i += kPrepThreads) packed[i] = (uint16_t)repack_desc(raw[i]);
+  __syncthreads();
+  // key1 = kind | zone | residue
+  int my_fast = 0;
+  for (int it = tid; it < n_items; it += kPrepThreads) {
+    bool fast = true;
+    int zone = SBX_ZONE_NONE;
+    for (int e = 0; e < V; ++e) {
+      const uint32_t d = raw[it * V + e];
+      fast = fast && ((d & 0x007Fu) == kFastDesc);
+      if (zone == SBX_ZONE_NONE) zone = desc_zone(d);
+    }
+#ifndef SBX_LIST_ZONE_SORT
+    zone = 0;
+#endif
+    key1[it] = (uint16_t)(((fast ? 0u : 1u) << 11) | ((uint32_t)zone << 3) | (uint32_t)(it & 7));
+    my_fast += fast ? 1 : 0;
+  }
+  atomicAdd(&s_nfast, my_fast);
+  __syncthreads();
+  // m = rank inside the (kind, zone, residue) bucket; key2 = kind | zone | m | residue
+  for (int it = tid; it < n_items; it += kPrepThreads) {
+    const uint32_t k1 = key1[it];
     int m = 0;
-    for (int it = res; it < n_items; it += 8) {
-      if (is_fast(it) != (kind == 0)) continue;
-      int pos = 0;                       // entries sorted before (m, res)
-#pragma unroll
-      for (int r = 0; r < 8; ++r) pos += min(sizes[r], m) + ((r < res && sizes[r] > m) ? 1 : 0);
-      if (kind == 0) {
-        qlist[pos] = (uint16_t)it;
-      } else {
-        bool diff = false;                 // bit 15: the vector holds a diffuser CV
-        for (int e = 0; e < V; ++e) diff = diff || (raw[it * V + e] & SBX_DESC_DIFFUSER);
-        qlist[n_items - 1 - pos] = (uint16_t)(it | (diff ? 0x8000 : 0));
-      }
-      ++m;
+    for (int j = (it & 7); j < it; j += 8) m += (key1[j] == k1) ? 1 : 0;   // same residue only
+    key[it] = ((k1 >> 3) << 18) | ((uint32_t)m << 3) | (k1 & 7u);
+  }
+  __syncthreads();
+  // final rank = number of smaller keys (keys are unique)
+  const int n_fast = s_nfast;
+  for (int it = tid; it < n_items; it += kPrepThreads) {
+    const uint32_t k2 = key[it];
+    int rank = 0;
+    for (int j = 0; j < n_items; ++j) rank += (key[j] < k2) ? 1 : 0;
+    if (rank < n_fast) {
+      qlist[rank] = (uint16_t)it;
+    } else {
+      bool diff = false;                 // bit 15: the vector holds a diffuser CV
+      for (int e = 0; e < V; ++e) diff = diff || (raw[it * V + e] & SBX_DESC_DIFFUSER);
+      qlist[n_items - 1 - (rank - n_fast)] = (uint16_t)(it | (diff ? 0x8000 : 0));
     }
   }
-  if (lane == 0) p.n_fast[plan] = total;
+  if (tid == 0) p.n_fast[plan] = n_fast;
 }
 
 // One Jacobi sweep over the CTA's building.  FIRST: `in` is T_prev itself, so
@@ -519,17 +536,54 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   long long total = 0;
   long long* wbins = bins + (size_t)(warp + 1) * (Z + 1);   // warp-private bins
   if (!p.fd_only) {
-    for (int base_it = warp * 32; base_it < n_items; base_it += NT) {
-      const int it = base_it + lane;
-      const bool valid = it < n_items;
-      float t[V];
-      uint32_t d[V];
-      if (valid) {
+    // Zone sums: every lane converts its vector to integers and the warp reduces
+    // them zone by zone with exact hardware integer REDUX (a warp's 32 vectors touch
+    // a handful of rooms).  The running sum of zone z lives in a REGISTER of lane
+    // z mod 32; shared memory is touched once per warp at the end.  No atomics in the
+    // common case (a shared-memory 64-bit atomic is a CAS loop on this hardware).
+    long long acc = 0;            // this lane's zone (lane, lane+32, ...: see flush below)
+    int acc_zone = lane;
+    for (int base_u = warp * 32; base_u < n_items; base_u += NT) {
+      const int it = base_u + lane;
+      int z1 = SBX_ZONE_NONE, z2 = SBX_ZONE_NONE, s1 = 0, s2 = 0;
+      if (it < n_items) {
+        float t[V];
+        uint32_t d[V];
         load_f<V>(in + it * V, t);
         load_d<V>(dsc + it * V, d);
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const int v = to_fix32(t[e], t_inf);
+          const int ze = desc_zone(d[e]);
+          total += v;
+          if (ze == SBX_ZONE_NONE) continue;
+          if (z1 == SBX_ZONE_NONE || ze == z1) { z1 = ze; s1 += v; }
+          else if (z2 == SBX_ZONE_NONE || ze == z2) { z2 = ze; s2 += v; }   // room | wall | room
+          else fix_add(&bins[ze], (long long)v);      // 3 rooms in one vector: CTA-level row 0, atomic
+        }
       }
-      zone_accumulate_warp<V>(t, d, valid, lane, wbins, total);
+      unsigned todo1 = __ballot_sync(0xffffffffu, z1 != SBX_ZONE_NONE);
+      unsigned todo2 = __ballot_sync(0xffffffffu, z2 != SBX_ZONE_NONE);
+      while (todo1 | todo2) {
+        const int z0 = todo1 ? __shfl_sync(0xffffffffu, z1, __ffs(todo1) - 1)
+                             : __shfl_sync(0xffffffffu, z2, __ffs(todo2) - 1);
+        const bool m1 = (z1 == z0), m2 = (z2 == z0);
+        const long long sum = warp_sum_i32((m1 ? s1 : 0) + (m2 ? s2 : 0));
+        todo1 &= ~__ballot_sync(0xffffffffu, m1);
+        todo2 &= ~__ballot_sync(0xffffffffu, m2);
+        if (lane == (z0 & 31)) {
+          if (z0 != acc_zone) {          // only with more than 32 zones
+            wbins[acc_zone] += acc;      // warp-private, this lane owns zones = lane mod 32
+            acc_zone = z0;
+            acc = 0;
+          }
+          acc += sum;
+        }
+      }
     }
+    __syncwarp();
+    if (acc_zone < Z && acc != 0) wbins[acc_zone] += acc;
+    __syncwarp();
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
     if (lane == 0) wbins[Z] = total;
@@ -548,10 +602,11 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     // combine the warp-private bins (integer sums: exact, order-free), handed to
     // k_post through zone_sum[b, 0..Z]
     long long* zs = p.zone_sum + (size_t)b * (Z + 1);
+    if (tid == 0) p.zone_ref[b] = t_inf;
     for (int i = tid; i <= Z; i += NT) {
       long long acc = 0;
 #pragma unroll
-      for (int w = 1; w <= NW; ++w) acc += bins[(size_t)w * (Z + 1) + i];
+      for (int w = 0; w <= NW; ++w) acc += bins[(size_t)w * (Z + 1) + i];
       zs[i] = acc;
     }
   }
@@ -730,6 +785,7 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
   }
   if (!p.fd_only) {
     long long* zs = p.zone_sum + (size_t)b * (Z + 1);
+    if (tid == 0) p.zone_ref[b] = 0.f;
     for (int i = tid; i <= Z; i += kGsThreads) zs[i] = bins[i];
   }
 }
@@ -896,6 +952,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) 
   if (lane == 0) fix_add(&bins[Z], total);
   __syncthreads();
   long long* zs = p.zone_sum + (size_t)b * (Z + 1);
+  if (tile == 0 && tid == 0) p.zone_ref[b] = 0.f;
   for (int i = tid; i <= Z; i += kStreamThreads)
     if (bins[i] != 0) fix_add(&zs[i], bins[i]);
 }
@@ -942,9 +999,10 @@ __global__ void __launch_bounds__(128) k_post(const Params p, const CarryStore* 
   const int plan = p.n_plans == 1 ? 0 : b;
   const int32_t* ncv = p.zone_ncv + (size_t)plan * Z;
   const long long* zs = p.zone_sum + (size_t)b * (Z + 1);
+  const double ref = (double)p.zone_ref[b];
   for (int zi = lane; zi < Z; zi += 32) {
     const int n = ncv[zi];
-    const float m = n > 0 ? (float)(from_fix(zs[zi]) / (double)n) : 0.f;
+    const float m = n > 0 ? (float)(ref + from_fix(zs[zi]) / (double)n) : 0.f;
     zpost[zi] = m;
     zpre[zi] = p.pre_zone_mean[(size_t)b * Z + zi];
     p.zone_mean[(size_t)b * Z + zi] = m;
@@ -953,7 +1011,7 @@ __global__ void __launch_bounds__(128) k_post(const Params p, const CarryStore* 
       p.qcv64[(size_t)b * Z + zi] = p.qcv64_next[(size_t)b * Z + zi];
     }
   }
-  const float gmean = (float)(from_fix(zs[Z]) / (double)((size_t)p.H * p.W));
+  const float gmean = (float)(ref + from_fix(zs[Z]) / (double)((size_t)p.H * p.W));
   if (lane == 0) p.global_mean[b] = gmean;
   __syncwarp();
   Carry cy = {0, 0, 0, 0, 0};

@@ -266,6 +266,16 @@ int prepare_plans(sbx_handle h, cudaStream_t st) {
   if (h->V == 4) k_prepare_plan<4><<<p.n_plans, kPrepThreads, smem, st>>>(p);
   else k_prepare_plan<1><<<p.n_plans, kPrepThreads, smem, st>>>(p);
   if (int rc = launch_check(h, "k_prepare_plan")) return rc;
+  {
+    const size_t n_items = (size_t)(p.H * p.W / h->V);
+    const size_t sm2 = sizeof(uint2) * n_items + sizeof(int) * 2 * (size_t)(p.Z + 1);
+    if (h->V == 4) e = cudaFuncSetAttribute(k_prepare_reduce<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    else e = cudaFuncSetAttribute(k_prepare_reduce<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
+    if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    if (h->V == 4) k_prepare_reduce<4><<<p.n_plans, kPrepThreads, sm2, st>>>(p);
+    else k_prepare_reduce<1><<<p.n_plans, kPrepThreads, sm2, st>>>(p);
+    if (int rc = launch_check(h, "k_prepare_reduce")) return rc;
+  }
   h->plans_dirty = 0;
   return SBX_OK;
 }
@@ -450,8 +460,11 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.obs_zone_order, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.desc_packed, uint16_t, (size_t)c.n_plans * N);
   ALLOC(p.qlist, uint16_t, (size_t)c.n_plans * (N / h->V));
-  ALLOC(p.n_fast, int32_t, (size_t)c.n_plans);
+  ALLOC(p.n_fast, int32_t, (size_t)c.n_plans * 4);
   ALLOC(p.hdr, unsigned char, B * header_bytes((int)Z));
+  p.rl_cap = reduce_list_capacity((int)(N / h->V), (int)Z);
+  ALLOC(p.rlist, uint32_t, (size_t)c.n_plans * p.rl_cap);
+  ALLOC(p.rl_chunks, int32_t, (size_t)c.n_plans);
   ALLOC(p.reset_temps, float, (size_t)c.n_reset * N);
   ALLOC(p.initial_temp, float, B);
   ALLOC(p.ambient, double, (size_t)c.n_weather * T);

@@ -77,7 +77,10 @@ struct Params {
   const int32_t* obs_zone_order;  // [P,Z]
   uint16_t* desc_packed;     // [P,H,W] combo index | diffuser | zone (k_prepare_plan)
   uint16_t* qlist;           // [P,H*W/V] fast vectors from the front, slow from the back
-  int32_t* n_fast;           // [P]
+  int32_t* n_fast;           // [P,4] sizes of the FAST / MEDIUM / EXT / SLOW vector lists
+  uint32_t* rlist;           // [P, rl_cap] zone-sum list (k_prepare_reduce)
+  int32_t* rl_chunks;        // [P] warps' worth of entries in it, -1 = does not fit
+  int rl_cap;
   unsigned char* hdr;        // [B, header_bytes(Z)] per-building solve header (k_build_header)
   const float* reset_temps;  // [n_reset,H,W]
   const float* initial_temp; // [B]

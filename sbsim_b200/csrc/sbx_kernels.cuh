@@ -129,14 +129,23 @@ __device__ __forceinline__ void tma_store_wait() {
 // building's (h, T_inf), the heat input per diffuser CV of each zone (slot Z = 0:
 // "no heat input"), and {T_inf, n_fast}.
 __host__ __device__ inline size_t header_q_slots(int Z) { return (size_t)((Z + 1 + 3) / 4) * 4; }
+// + 8 scalars {T_inf, h, n_fast, n_fast+n_med, n_fast+n_med+n_ext, n_reduce_chunks, 0, 0}
+// + 3 x {k/dx, cm, den, 1/den}: interior-class coefficients per material (MEDIUM list)
 __host__ __device__ inline size_t header_bytes(int Z) {
-  return sizeof(Combo) * kNumCombos + header_q_slots(Z) * 4 + 16;
+  return sizeof(Combo) * kNumCombos + header_q_slots(Z) * 4 + 32 + 48;
 }
 
 struct ResidentLayout {
-  size_t off_a, off_b, off_n3, off_desc, off_list, off_hdr, off_bins, off_wmax,
+  size_t off_a, off_b, off_n3, off_desc, off_list, off_rlist, off_hdr, off_bins, off_wmax,
       off_bar, total;
 };
+
+// Capacity (entries) of a plan's zone-sum list: one entry per (vector, zone) pair --
+// a vector straddling a wall contributes two or three -- plus each zone segment
+// padded to a whole warp.  Plans that need more fall back to a generic loop.
+__host__ __device__ inline int reduce_list_capacity(int n_items, int Z) {
+  return ((n_items + n_items / 2 + 31) & ~31) + 32 * (Z + 1);
+}
 
 __host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z, int V) {
   ResidentLayout L;
@@ -147,6 +156,7 @@ __host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z, int V
   L.off_n3 = o; o = al(o + (size_t)n_cv * 4);
   L.off_desc = o; o = al(o + (size_t)n_cv * 2);
   L.off_list = o; o = al(o + (size_t)(n_cv / V) * 2);
+  L.off_rlist = o; o = al(o + (size_t)reduce_list_capacity(n_cv / V, Z) * 4);
   L.off_hdr = o; o = al(o + header_bytes(Z));
   L.off_bins = o; o = al(o + (size_t)(Z + 1) * 8 * (kResidentThreads / 32 + 1));
   L.off_wmax = o; o = al(o + 32 * 4);
@@ -177,44 +187,6 @@ __device__ __forceinline__ void zone_accumulate(const float (&t)[V], const uint3
   if (z0 != SBX_ZONE_NONE) fix_add(&bins[z0], run);
 }
 
-// Warp-cooperative version for 32 consecutive vectors (one per lane): zone ids
-// form contiguous segments along a row, so a segmented shuffle reduction leaves
-// one partial sum per segment and only segment heads touch the (warp-private)
-// bins.  Vectors that straddle a zone boundary flush their tail directly.
-template <int V>
-__device__ __forceinline__ void zone_accumulate_warp(const float (&t)[V], const uint32_t (&d)[V],
-                                                     bool valid, int lane, long long* wbins,
-                                                     long long& total) {
-  int z = SBX_ZONE_NONE;
-  long long s = 0;
-  if (valid) {
-    // primary zone of the vector = its first CV that belongs to a room (walls and
-    // exterior carry SBX_ZONE_NONE); CVs of a second room in the same vector are
-    // flushed directly (needs two rooms within V cells: practically never)
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const int ze = desc_zone(d[e]);
-      const long long v = to_fix(t[e]);
-      total += v;
-      if (ze == SBX_ZONE_NONE) continue;
-      if (z == SBX_ZONE_NONE) z = ze;
-      if (ze == z) s += v;
-      else fix_add(&wbins[ze], v);
-    }
-  }
-  const int z_prev = __shfl_up_sync(0xffffffffu, z, 1);
-  const bool head = lane == 0 || z_prev != z;
-  const unsigned heads = __ballot_sync(0xffffffffu, head);
-  const int seg = __popc(heads & (0xffffffffu >> (31 - lane)));
-#pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const long long s_up = __shfl_down_sync(0xffffffffu, s, o);
-    const int seg_up = __shfl_down_sync(0xffffffffu, seg, o);
-    if (lane + o < 32 && seg_up == seg) s += s_up;
-  }
-  if (head && z != SBX_ZONE_NONE) fix_add(&wbins[z], s);
-}
-
 // Packed descriptor: combo index (5 bits) | diffuser flag | zone.
 __device__ __forceinline__ uint32_t repack_desc(uint32_t d) {
   const int cls = desc_class(d);
@@ -243,65 +215,69 @@ __global__ void __launch_bounds__(128) k_build_header(const Params p) {
   for (int zi = lane; zi < (int)header_q_slots(Z); zi += 32)
     qcv[zi] = zi < Z ? p.qcv[(size_t)b * Z + zi] : 0.f;
   if (lane == 0) {
+    const int n_f = p.n_fast[plan * 4 + 0], n_m = p.n_fast[plan * 4 + 1], n_e = p.n_fast[plan * 4 + 2];
     scal[0] = t_inf;
     scal[1] = h;
-    scal[2] = __int_as_float(p.n_fast ? p.n_fast[plan] : 0);
-    scal[3] = 0.f;
+    scal[2] = __int_as_float(n_f);
+    scal[3] = __int_as_float(n_f + n_m);
+    scal[4] = __int_as_float(n_f + n_m + n_e);
+    scal[5] = __int_as_float(p.rl_chunks[plan]);
+    scal[6] = scal[7] = 0.f;
+  }
+  __syncwarp();
+  if (lane < kNumMaterials) {
+    const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + lane];
+    reinterpret_cast<float4*>(scal + 8)[lane] = make_float4(c.k1, c.cm, c.den, c.rden);
   }
 }
 
-// Once per uploaded plan: repack the descriptors and split the plan's vectors
-// into a FAST list (every CV interior, air, no heat input: uniform register
-// coefficients, all four neighbours in range by construction) and a SLOW list
-// (generic, table-driven).  Both lists share one array: fast from the front, slow
-// from the back.
+// Once per uploaded plan: repack the descriptors and sort the plan's vectors
+// (V consecutive CVs) into four lists, stored back to back in one array:
+//   FAST    every CV interior class, air, no diffuser: uniform register
+//           coefficients, all four neighbours in range by construction;
+//   MEDIUM  every CV interior class (walls, diffusers): per-material coefficients,
+//           neighbours in range, no convection terms;
+//   EXT     every CV exterior space: T = T_inf;
+//   SLOW    everything else (boundary classes): generic, table-driven.
+// Bit 15 of a MEDIUM / SLOW entry says the vector holds a diffuser CV.
 //
-// Order inside each list: by zone, then by (rank within the vector's index-mod-8
-// class, index mod 8).
-//   * by zone: a warp's 32 consecutive entries almost always belong to one room, so
-//     the zone sums reduce with one hardware REDUX per warp instead of a segmented
-//     scan plus atomics;
-//   * residue interleave: every aligned group of 8 entries holds 8 different
-//     residues mod 8, so the 8 lanes of a quarter-warp touch 8 different 16-byte
-//     bank groups and the 128-bit shared-memory accesses of the sweep stay
-//     conflict-free although the lists skip vectors.
-// One CTA per plan; ranks are computed by counting smaller keys (O(n^2) on a few
-// thousand items, once per upload), so the order is deterministic.
+// Order inside each list: (rank within the vector's index-mod-8 class, index mod
+// 8), i.e. every aligned group of 8 entries holds 8 different residues mod 8, so the
+// 8 lanes of a quarter-warp touch 8 different 16-byte bank groups and the 128-bit
+// shared-memory accesses of the sweep stay conflict-free although the lists skip
+// vectors.  One CTA per plan; ranks are computed by counting smaller keys (O(n^2)
+// on a few thousand items, once per upload), so the order is deterministic.
 constexpr int kPrepThreads = 256;
+enum { kListFast = 0, kListMedium = 1, kListExt = 2, kListSlow = 3 };
 template <int V>
 __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan(const Params p) {
   extern __shared__ __align__(16) unsigned char smem_prep[];
-  uint32_t* key = reinterpret_cast<uint32_t*>(smem_prep);
-  const int n_items_ = p.H * p.W / V;
-  uint16_t* key1 = reinterpret_cast<uint16_t*>(key + n_items_);
-  __shared__ int s_nfast;
   const int plan = blockIdx.x, tid = threadIdx.x;
   const int n_cv = p.H * p.W, n_items = n_cv / V;
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem_prep);
+  uint16_t* key1 = reinterpret_cast<uint16_t*>(key + n_items);
+  __shared__ int s_count[4];
   const uint16_t* raw = p.desc + (size_t)plan * n_cv;
   uint16_t* packed = p.desc_packed + (size_t)plan * n_cv;
   uint16_t* qlist = p.qlist + (size_t)plan * n_items;
-  if (tid == 0) s_nfast = 0;
+  if (tid < 4) s_count[tid] = 0;
   for (int i = tid; i < n_cv; i += kPrepThreads) packed[i] = (uint16_t)repack_desc(raw[i]);
   __syncthreads();
-  // key1 = kind | zone | residue
-  int my_fast = 0;
+  // key1 = list | residue
   for (int it = tid; it < n_items; it += kPrepThreads) {
-    bool fast = true;
-    int zone = SBX_ZONE_NONE;
+    bool fast = true, interior = true, ext = true;
     for (int e = 0; e < V; ++e) {
       const uint32_t d = raw[it * V + e];
       fast = fast && ((d & 0x007Fu) == kFastDesc);
-      if (zone == SBX_ZONE_NONE) zone = desc_zone(d);
+      interior = interior && (desc_class(d) == SBX_CV_INTERIOR);
+      ext = ext && (desc_class(d) == SBX_CV_EXTERIOR);
     }
-#ifndef SBX_LIST_ZONE_SORT
-    zone = 0;
-#endif
-    key1[it] = (uint16_t)(((fast ? 0u : 1u) << 11) | ((uint32_t)zone << 3) | (uint32_t)(it & 7));
-    my_fast += fast ? 1 : 0;
+    const int kind = fast ? kListFast : interior ? kListMedium : ext ? kListExt : kListSlow;
+    key1[it] = (uint16_t)((kind << 3) | (it & 7));
+    atomicAdd(&s_count[kind], 1);
   }
-  atomicAdd(&s_nfast, my_fast);
   __syncthreads();
-  // m = rank inside the (kind, zone, residue) bucket; key2 = kind | zone | m | residue
+  // m = rank inside the (list, residue) bucket; key2 = list | m | residue
   for (int it = tid; it < n_items; it += kPrepThreads) {
     const uint32_t k1 = key1[it];
     int m = 0;
@@ -309,94 +285,218 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan(const Params p) {
     key[it] = ((k1 >> 3) << 18) | ((uint32_t)m << 3) | (k1 & 7u);
   }
   __syncthreads();
-  // final rank = number of smaller keys (keys are unique)
-  const int n_fast = s_nfast;
+  // position = number of smaller keys (keys are unique)
   for (int it = tid; it < n_items; it += kPrepThreads) {
     const uint32_t k2 = key[it];
     int rank = 0;
     for (int j = 0; j < n_items; ++j) rank += (key[j] < k2) ? 1 : 0;
-    if (rank < n_fast) {
-      qlist[rank] = (uint16_t)it;
-    } else {
-      bool diff = false;                 // bit 15: the vector holds a diffuser CV
-      for (int e = 0; e < V; ++e) diff = diff || (raw[it * V + e] & SBX_DESC_DIFFUSER);
-      qlist[n_items - 1 - (rank - n_fast)] = (uint16_t)(it | (diff ? 0x8000 : 0));
+    bool diff = false;
+    for (int e = 0; e < V; ++e) diff = diff || (raw[it * V + e] & SBX_DESC_DIFFUSER);
+    qlist[rank] = (uint16_t)(it | (diff ? 0x8000 : 0));
+  }
+  if (tid < 4) p.n_fast[plan * 4 + tid] = s_count[tid];
+}
+
+// Once per uploaded plan: the ZONE-SUM list.  Entry = vector index | element mask
+// << 16 | zone slot << 20 (slot Z = "no zone", needed for the grid mean).  Entries
+// are grouped by zone slot and every group is padded to a multiple of 32 with null
+// entries (mask 0), so a warp's 32 entries always belong to ONE zone: the zone sums
+// then take one integer REDUX per warp and no per-element zone logic at all.
+// A vector that straddles a wall appears once per zone it touches, with
+// complementary masks, so every CV is counted exactly once.
+template <int V>
+__global__ void __launch_bounds__(kPrepThreads) k_prepare_reduce(const Params p) {
+  extern __shared__ __align__(16) unsigned char smem_prep[];
+  const int plan = blockIdx.x, tid = threadIdx.x;
+  const int n_cv = p.H * p.W, n_items = n_cv / V, Z = p.Z;
+  uint2* parts = reinterpret_cast<uint2*>(smem_prep);   // 4 x u16 slot per vector (0xFFFF = unused)
+  int* cnt = reinterpret_cast<int*>(parts + n_items);   // [Z+1]
+  int* start = cnt + (Z + 1);                           // [Z+1]
+  __shared__ int s_total;
+  const uint16_t* raw = p.desc + (size_t)plan * n_cv;
+  uint32_t* rl = p.rlist + (size_t)plan * p.rl_cap;
+  for (int i = tid; i <= Z; i += kPrepThreads) cnt[i] = 0;
+  __syncthreads();
+  for (int it = tid; it < n_items; it += kPrepThreads) {
+    uint32_t z[4] = {0xFFFFu, 0xFFFFu, 0xFFFFu, 0xFFFFu};
+    int np = 0;
+    for (int e = 0; e < V; ++e) {
+      const int zs = desc_zone(raw[it * V + e]);
+      const uint32_t slot = zs == SBX_ZONE_NONE ? (uint32_t)Z : (uint32_t)zs;
+      bool found = false;
+      for (int k = 0; k < np; ++k) found = found || z[k] == slot;
+      if (!found) {
+        z[np++] = slot;
+        atomicAdd(&cnt[slot], 1);
+      }
+    }
+    parts[it] = make_uint2(z[0] | (z[1] << 16), z[2] | (z[3] << 16));
+  }
+  __syncthreads();
+  if (tid == 0) {
+    int o = 0;
+    for (int i = 0; i <= Z; ++i) {
+      start[i] = o;
+      o += (cnt[i] + 31) & ~31;
+    }
+    s_total = o;
+  }
+  __syncthreads();
+  const int total = s_total;
+  if (total > p.rl_cap) {            // pathological plan: k_resident_step takes its generic loop
+    if (tid == 0) p.rl_chunks[plan] = -1;
+    return;
+  }
+  for (int i = tid; i <= Z; i += kPrepThreads)
+    for (int k = start[i] + cnt[i]; k < start[i] + ((cnt[i] + 31) & ~31); ++k) rl[k] = (uint32_t)i << 20;
+  for (int it = tid; it < n_items; it += kPrepThreads) {
+    const uint2 pz = parts[it];
+    for (int k = 0; k < 4; ++k) {
+      const uint32_t slot = ((k < 2 ? pz.x : pz.y) >> (16 * (k & 1))) & 0xFFFFu;
+      if (slot == 0xFFFFu) break;
+      // position inside the zone's group: vectors in index order
+      const uint32_t pat = slot * 0x00010001u;
+      int rank = 0;
+      for (int j = 0; j < it; ++j) {
+        const uint2 q = parts[j];
+        rank += ((__vcmpeq2(q.x, pat) | __vcmpeq2(q.y, pat)) != 0u) ? 1 : 0;
+      }
+      uint32_t mask = 0;
+      for (int e = 0; e < V; ++e) {
+        const int zs = desc_zone(raw[it * V + e]);
+        if ((zs == SBX_ZONE_NONE ? (uint32_t)Z : (uint32_t)zs) == slot) mask |= 1u << e;
+      }
+      rl[start[slot] + rank] = (uint32_t)it | (mask << 16) | (slot << 20);
     }
   }
-  if (tid == 0) p.n_fast[plan] = n_fast;
+  if (tid == 0) p.rl_chunks[plan] = total / 32;
 }
+
+// Per-material coefficients of an interior-class CV (header, MEDIUM list)
+struct MedCoef {
+  float kq, cm, den, rden;
+};
 
 // One Jacobi sweep over the CTA's building.  FIRST: `in` is T_prev itself, so
 // n3 = (cm * T_prev) / dt (tf_simulator.py:743-749) is computed here and stored
 // for the following sweeps instead of being loaded.
+// The four lists are walked as ONE sequence strided by the CTA size, so every warp
+// gets the same number of vectors (+-1) whatever the mix; a warp diverges only
+// where its 32 entries straddle a list boundary (three places per building).
+struct SweepCtx {
+  const uint16_t* dsc;
+  const uint16_t* qlist;
+  const Combo* tab;
+  const float4* mtab;
+  const float* qcv;
+  FastCoef fc;
+  AreaCoef az;
+  float cm_fast, dt, rdt, t_inf;
+  int n_fast, n_fm, n_fme, n_items, H, W, Z;
+  unsigned wq_magic;
+};
 template <int V, bool FIRST>
-__device__ __forceinline__ float resident_sweep(
-    const float* __restrict__ in, float* __restrict__ out, float* __restrict__ n3p,
-    const uint16_t* __restrict__ dsc, const uint16_t* __restrict__ qlist, const Combo* tab,
-    const float* qcv, const FastCoef& fc, const AreaCoef& az, float cm_fast, float dt, float rdt, float t_inf,
-    int n_fast, int n_items, int H, int W, int Z, unsigned wq_magic, int tid) {
+__device__ __forceinline__ float resident_sweep(const float* __restrict__ in, float* __restrict__ out,
+                                                float* __restrict__ n3p, const SweepCtx& s, int tid) {
   constexpr int NT = kResidentThreads;
-  const int wq = W / V;
+  const int W = s.W, wq = W / V;
+  const float t_inf = s.t_inf;
   float lmax = 0.f;
-  for (int i = tid; i < n_fast; i += NT) {
-    const int base = (int)qlist[i] * V;
-    float c[V], up[V], dn[V], n3v[V], o[V];
-    load_f<V>(in + base, c);
-    load_f<V>(in + base - W, up);
-    load_f<V>(in + base + W, dn);
-    if constexpr (FIRST) {
-#pragma unroll
-      for (int e = 0; e < V; ++e) n3v[e] = div_rn(mul(cm_fast, c[e]), dt, rdt);
-      store_f<V>(n3p + base, n3v);
-    } else {
-      load_f<V>(n3p + base, n3v);
-    }
-    const float left = in[base - 1];
-    const float right = in[base + V];
-#pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const float t_jm = e == 0 ? left : c[e - 1];
-      const float t_jp = e == V - 1 ? right : c[e + 1];
-      o[e] = cv_update_fast(fc, t_jp, t_jm, up[e], dn[e], n3v[e]);
-      lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));                       // :851-853
-    }
-    store_f<V>(out + base, o);
-  }
-  const int n_slow = n_items - n_fast;
-  // slow vectors are dealt from the LAST thread downwards: the fast loop leaves the
-  // low thread ids with one more iteration, so this evens out the work per warp
-  // before the sweep barrier
-  for (int i = NT - 1 - tid; i < n_slow; i += NT) {
-    const int entry = (int)qlist[n_items - 1 - i];
+  for (int u = tid; u < s.n_items; u += NT) {
+    const int entry = (int)s.qlist[u];
     const int it = entry & 0x7FFF;
-    const bool has_q = (entry & 0x8000) != 0;
     const int base = it * V;
-    const int r = (int)__umulhi((unsigned)it, wq_magic);
-    const int q = it - r * wq;
-    float c[V], up[V], dn[V], n3v[V], o[V];
-    uint32_t d[V];
+    float c[V], o[V];
     load_f<V>(in + base, c);
-    load_d<V>(dsc + base, d);
-    if constexpr (FIRST) {
+    if (u < s.n_fast) {
+      float up[V], dn[V], n3v[V];
+      load_f<V>(in + base - W, up);
+      load_f<V>(in + base + W, dn);
+      if constexpr (FIRST) {
 #pragma unroll
-      for (int e = 0; e < V; ++e) n3v[e] = div_rn(mul(tab[d[e] & 31u].cm, c[e]), dt, rdt);
-      store_f<V>(n3p + base, n3v);
+        for (int e = 0; e < V; ++e) n3v[e] = div_rn(mul(s.cm_fast, c[e]), s.dt, s.rdt);
+        store_f<V>(n3p + base, n3v);
+      } else {
+        load_f<V>(n3p + base, n3v);
+      }
+      const float left = in[base - 1];
+      const float right = in[base + V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float t_jm = e == 0 ? left : c[e - 1];
+        const float t_jp = e == V - 1 ? right : c[e + 1];
+        o[e] = cv_update_fast(s.fc, t_jp, t_jm, up[e], dn[e], n3v[e]);
+      }
+    } else if (u < s.n_fm) {
+      // interior class, any material, maybe a diffuser: k1 = k2 = k3 = k4 = k/dx,
+      // hh = hv = 0 (x + 0 == x), uz = vz = z*dx; neighbours always in range
+      const bool has_q = (entry & 0x8000) != 0;
+      float up[V], dn[V], n3v[V];
+      uint32_t d[V];
+      MedCoef mc[V];
+      load_d<V>(s.dsc + base, d);
+      load_f<V>(in + base - W, up);
+      load_f<V>(in + base + W, dn);
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float4 m4 = s.mtab[(d[e] & kPackIdxMask) - SBX_CV_INTERIOR * kNumMaterials];
+        mc[e].kq = m4.x; mc[e].cm = m4.y; mc[e].den = m4.z; mc[e].rden = m4.w;
+      }
+      if constexpr (FIRST) {
+#pragma unroll
+        for (int e = 0; e < V; ++e) n3v[e] = div_rn(mul(mc[e].cm, c[e]), s.dt, s.rdt);
+        store_f<V>(n3p + base, n3v);
+      } else {
+        load_f<V>(n3p + base, n3v);
+      }
+      const float left = in[base - 1];
+      const float right = in[base + V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float t_jm = e == 0 ? left : c[e - 1];
+        const float t_jp = e == V - 1 ? right : c[e + 1];
+        float qv = 0.f;
+        if (has_q) qv = s.qcv[(d[e] & SBX_DESC_DIFFUSER) ? (int)(d[e] >> SBX_DESC_ZONE_SHIFT) : s.Z];
+        float n1 = add(mul(mc[e].kq, t_jp), mul(mc[e].kq, t_jm));
+        n1 = mul(s.az.full, n1);
+        float n2 = add(mul(mc[e].kq, dn[e]), mul(mc[e].kq, up[e]));
+        n2 = mul(s.az.full, n2);
+        const float num = add(add(add(n1, n2), n3v[e]), qv);
+        o[e] = div_rn(num, mc[e].den, mc[e].rden);
+      }
+    } else if (u < s.n_fme) {
+      // exterior space: T = T_inf (tf_simulator.py:847-849); its n3 is never read
+#pragma unroll
+      for (int e = 0; e < V; ++e) o[e] = t_inf;
     } else {
-      load_f<V>(n3p + base, n3v);
-    }
-    if (r > 0) load_f<V>(in + base - W, up); else fill<V>(up, t_inf);         // :642-644
-    if (r < H - 1) load_f<V>(in + base + W, dn); else fill<V>(dn, t_inf);     // :646
-    const float left = q > 0 ? in[base - 1] : t_inf;                          // :638-640
-    const float right = q < wq - 1 ? in[base + V] : t_inf;                    // :636
+      const bool has_q = (entry & 0x8000) != 0;
+      const int r = (int)__umulhi((unsigned)it, s.wq_magic);
+      const int q = it - r * wq;
+      float up[V], dn[V], n3v[V];
+      uint32_t d[V];
+      load_d<V>(s.dsc + base, d);
+      if constexpr (FIRST) {
 #pragma unroll
-    for (int e = 0; e < V; ++e) {
-      const float t_jm = e == 0 ? left : c[e - 1];
-      const float t_jp = e == V - 1 ? right : c[e + 1];
-      float qv = 0.f;
-      if (has_q) qv = qcv[(d[e] & SBX_DESC_DIFFUSER) ? (int)(d[e] >> SBX_DESC_ZONE_SHIFT) : Z];
-      o[e] = cv_update_packed(d[e], t_jp, t_jm, up[e], dn[e], n3v[e], qv, t_inf, az, tab);
-      lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));
+        for (int e = 0; e < V; ++e) n3v[e] = div_rn(mul(s.tab[d[e] & kPackIdxMask].cm, c[e]), s.dt, s.rdt);
+        store_f<V>(n3p + base, n3v);
+      } else {
+        load_f<V>(n3p + base, n3v);
+      }
+      if (r > 0) load_f<V>(in + base - W, up); else fill<V>(up, t_inf);         // :642-644
+      if (r < s.H - 1) load_f<V>(in + base + W, dn); else fill<V>(dn, t_inf);   // :646
+      const float left = q > 0 ? in[base - 1] : t_inf;                          // :638-640
+      const float right = q < wq - 1 ? in[base + V] : t_inf;                    // :636
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const float t_jm = e == 0 ? left : c[e - 1];
+        const float t_jp = e == V - 1 ? right : c[e + 1];
+        float qv = 0.f;
+        if (has_q) qv = s.qcv[(d[e] & SBX_DESC_DIFFUSER) ? (int)(d[e] >> SBX_DESC_ZONE_SHIFT) : s.Z];
+        o[e] = cv_update_packed(d[e], t_jp, t_jm, up[e], dn[e], n3v[e], qv, t_inf, s.az, s.tab);
+      }
     }
+#pragma unroll
+    for (int e = 0; e < V; ++e) lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));   // :851-853
     store_f<V>(out + base, o);
   }
   return lmax;
@@ -436,6 +536,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   float* n3p = reinterpret_cast<float*>(smem + L.off_n3);
   uint16_t* dsc = reinterpret_cast<uint16_t*>(smem + L.off_desc);
   uint16_t* qlist = reinterpret_cast<uint16_t*>(smem + L.off_list);
+  uint32_t* rlist = reinterpret_cast<uint32_t*>(smem + L.off_rlist);
   Combo* tab = reinterpret_cast<Combo*>(smem + L.off_hdr);
   float* qcv = reinterpret_cast<float*>(smem + L.off_hdr + sizeof(Combo) * kNumCombos);
   const float* scal = qcv + header_q_slots(Z);
@@ -454,6 +555,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   if (use_tma) {
     if (tid == 0) {
       mbar_init(bar, 1);
+      mbar_init(bar + 1, 1);
       mbar_expect_tx(bar, (uint32_t)(n_cv * 4 + n_cv * 2 + n_items * 2) + hdr_bytes);
       tma_load_1d(smem + L.off_hdr, gH, hdr_bytes, bar);
       tma_load_1d(bufA, gT, (uint32_t)(n_cv * 4), bar);
@@ -477,18 +579,35 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   if (use_tma) mbar_wait(bar, 0);
   SBX_PHASE(1);   // waiting for the TMA loads
   const float t_inf = scal[0];
-  const int n_fast = __float_as_int(scal[2]);
-  FastCoef fc;
+  // the zone-sum list is only needed after the sweeps: fetch it behind them
+  const int n_chunks = __float_as_int(scal[5]);
+  if (!p.fd_only && n_chunks > 0) {
+    const uint32_t* gR = p.rlist + (size_t)plan * p.rl_cap;
+    if (use_tma) {
+      if (tid == 0) {
+        mbar_expect_tx(bar + 1, (uint32_t)n_chunks * 128u);
+        tma_load_1d(rlist, gR, (uint32_t)n_chunks * 128u, bar + 1);
+      }
+    } else {
+      for (int i = tid; i < n_chunks * 32; i += NT) rlist[i] = gR[i];
+    }
+  }
+  SweepCtx sc;
+  sc.dsc = dsc; sc.qlist = qlist; sc.tab = tab; sc.qcv = qcv;
+  sc.mtab = reinterpret_cast<const float4*>(scal + 8);
+  sc.n_fast = __float_as_int(scal[2]);
+  sc.n_fm = __float_as_int(scal[3]);
+  sc.n_fme = __float_as_int(scal[4]);
   {
     const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + 0];
-    fc.kq = c.k1; fc.vz = c.vz; fc.den = c.den; fc.rden = c.rden;
+    sc.fc.kq = c.k1; sc.fc.vz = c.vz; sc.fc.den = c.den; sc.fc.rden = c.rden;
+    sc.cm_fast = c.cm;
   }
-  const float cm_fast = tab[SBX_CV_INTERIOR * kNumMaterials + 0].cm;
-  AreaCoef az;
-  az.full = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
-  az.half = tab[SBX_CV_CORNER_TL * kNumMaterials].vz;
-  const float rdt = __frcp_rn(p.dt);
-  const unsigned wq_magic = 0xFFFFFFFFu / (unsigned)(W / V) + 1u;   // it / wq for it < 2^16
+  sc.az.full = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
+  sc.az.half = tab[SBX_CV_CORNER_TL * kNumMaterials].vz;
+  sc.dt = p.dt; sc.rdt = __frcp_rn(p.dt); sc.t_inf = t_inf;
+  sc.n_items = n_items; sc.H = H; sc.W = W; sc.Z = Z;
+  sc.wq_magic = 0xFFFFFFFFu / (unsigned)(W / V) + 1u;   // it / wq for it < 2^16
 
   // ---- stage 2: Jacobi sweeps to convergence (simulator.py:348-364) ---------
   float* in = bufA;
@@ -499,12 +618,8 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   while (k < limit) {
     ++k;
     float lmax;
-    if (k == 1)
-      lmax = resident_sweep<V, true>(in, out, n3p, dsc, qlist, tab, qcv, fc, az, cm_fast, p.dt, rdt,
-                                     t_inf, n_fast, n_items, H, W, Z, wq_magic, tid);
-    else
-      lmax = resident_sweep<V, false>(in, out, n3p, dsc, qlist, tab, qcv, fc, az, cm_fast, p.dt, rdt,
-                                      t_inf, n_fast, n_items, H, W, Z, wq_magic, tid);
+    if (k == 1) lmax = resident_sweep<V, true>(in, out, n3p, sc, tid);
+    else lmax = resident_sweep<V, false>(in, out, n3p, sc, tid);
     // max|dT| <= threshold  <=>  no thread saw a delta above it (simulator.py:362);
     // the barrier doubles as the ping-pong hazard fence.
     const int above = __syncthreads_or(lmax > p.threshold);
@@ -533,60 +648,43 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   // block max of the last sweep (diagnostic SBX_F_MAX_DELTA)
   last_lmax = warp_max(last_lmax);
   if (lane == 0) wmax[warp] = last_lmax;
-  long long total = 0;
   long long* wbins = bins + (size_t)(warp + 1) * (Z + 1);   // warp-private bins
-  if (!p.fd_only) {
-    // Zone sums: every lane converts its vector to integers and the warp reduces
-    // them zone by zone with exact hardware integer REDUX (a warp's 32 vectors touch
-    // a handful of rooms).  The running sum of zone z lives in a REGISTER of lane
-    // z mod 32; shared memory is touched once per warp at the end.  No atomics in the
-    // common case (a shared-memory 64-bit atomic is a CAS loop on this hardware).
-    long long acc = 0;            // this lane's zone (lane, lane+32, ...: see flush below)
-    int acc_zone = lane;
-    for (int base_u = warp * 32; base_u < n_items; base_u += NT) {
-      const int it = base_u + lane;
-      int z1 = SBX_ZONE_NONE, z2 = SBX_ZONE_NONE, s1 = 0, s2 = 0;
-      if (it < n_items) {
-        float t[V];
-        uint32_t d[V];
-        load_f<V>(in + it * V, t);
-        load_d<V>(dsc + it * V, d);
+  if (!p.fd_only && n_chunks > 0) {
+    // Zone sums from the zone-grouped list: a warp's 32 entries belong to one zone,
+    // so the warp reduces its lanes' integers with exact hardware REDUX and the
+    // running sum of zone z lives in a REGISTER of lane z mod 32; shared memory is
+    // touched once per warp at the end.  No atomics (a shared-memory 64-bit atomic is
+    // a CAS loop on this hardware), no per-element zone decoding.
+    if (use_tma) mbar_wait(bar + 1, 0);
+    long long acc = 0;
+    int acc_zone = lane;          // the zone this lane currently accumulates
+    for (int chunk = warp; chunk < n_chunks; chunk += NW) {
+      const uint32_t en = rlist[chunk * 32 + lane];
+      float t[V];
+      load_f<V>(in + (en & 0xFFFFu) * V, t);
+      int sl = 0;
 #pragma unroll
-        for (int e = 0; e < V; ++e) {
-          const int v = to_fix32(t[e], t_inf);
-          const int ze = desc_zone(d[e]);
-          total += v;
-          if (ze == SBX_ZONE_NONE) continue;
-          if (z1 == SBX_ZONE_NONE || ze == z1) { z1 = ze; s1 += v; }
-          else if (z2 == SBX_ZONE_NONE || ze == z2) { z2 = ze; s2 += v; }   // room | wall | room
-          else fix_add(&bins[ze], (long long)v);      // 3 rooms in one vector: CTA-level row 0, atomic
+      for (int e = 0; e < V; ++e)
+        if (en & (0x10000u << e)) sl += to_fix32(t[e], t_inf);
+      const long long sum = warp_sum_i32(sl);
+      const int z0 = (int)(__shfl_sync(0xffffffffu, en, 0) >> 20);
+      if (lane == (z0 & 31)) {
+        if (z0 != acc_zone) {          // only with more than 32 zones
+          wbins[acc_zone] += acc;      // warp-private, this lane owns zones = lane mod 32
+          acc_zone = z0;
+          acc = 0;
         }
-      }
-      unsigned todo1 = __ballot_sync(0xffffffffu, z1 != SBX_ZONE_NONE);
-      unsigned todo2 = __ballot_sync(0xffffffffu, z2 != SBX_ZONE_NONE);
-      while (todo1 | todo2) {
-        const int z0 = todo1 ? __shfl_sync(0xffffffffu, z1, __ffs(todo1) - 1)
-                             : __shfl_sync(0xffffffffu, z2, __ffs(todo2) - 1);
-        const bool m1 = (z1 == z0), m2 = (z2 == z0);
-        const long long sum = warp_sum_i32((m1 ? s1 : 0) + (m2 ? s2 : 0));
-        todo1 &= ~__ballot_sync(0xffffffffu, m1);
-        todo2 &= ~__ballot_sync(0xffffffffu, m2);
-        if (lane == (z0 & 31)) {
-          if (z0 != acc_zone) {          // only with more than 32 zones
-            wbins[acc_zone] += acc;      // warp-private, this lane owns zones = lane mod 32
-            acc_zone = z0;
-            acc = 0;
-          }
-          acc += sum;
-        }
+        acc += sum;
       }
     }
     __syncwarp();
-    if (acc_zone < Z && acc != 0) wbins[acc_zone] += acc;
-    __syncwarp();
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
-    if (lane == 0) wbins[Z] = total;
+    if (acc_zone <= Z && acc != 0) wbins[acc_zone] += acc;
+  } else if (!p.fd_only) {
+    // generic loop (plans whose zone-sum list does not fit): per-CV atomics
+    for (int i = tid; i < n_cv; i += NT) {
+      const int zs = desc_zone(dsc[i]);
+      fix_add(&bins[zs == SBX_ZONE_NONE ? Z : zs], (long long)to_fix32(in[i], t_inf));
+    }
   }
   __syncthreads();
   SBX_PHASE(4);   // convection gather (if any) + zone / grid sums
@@ -603,11 +701,18 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     // k_post through zone_sum[b, 0..Z]
     long long* zs = p.zone_sum + (size_t)b * (Z + 1);
     if (tid == 0) p.zone_ref[b] = t_inf;
-    for (int i = tid; i <= Z; i += NT) {
-      long long acc = 0;
+    if (warp == 0) {
+      long long grid = 0;            // slot Z collected the CVs outside every zone
+      for (int i = lane; i <= Z; i += 32) {
+        long long acc = 0;
 #pragma unroll
-      for (int w = 0; w <= NW; ++w) acc += bins[(size_t)w * (Z + 1) + i];
-      zs[i] = acc;
+        for (int w = 0; w <= NW; ++w) acc += bins[(size_t)w * (Z + 1) + i];
+        if (i < Z) zs[i] = acc;
+        grid += acc;
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) grid += __shfl_xor_sync(0xffffffffu, grid, o);
+      if (lane == 0) zs[Z] = grid;
     }
   }
   if (use_tma && tid == 0) tma_store_wait();

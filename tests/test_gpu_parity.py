@@ -172,6 +172,41 @@ def test_env_rollout_matches_oracle(path, plan_name, histogram):
     env.close()
 
 
+def _strip_rooms_plan(h=64, w=96):
+  """One-CV-wide rooms separated by one-CV walls: every 4-CV vector touches two rooms
+  and a wall, so the resident kernel's zone-sum list overflows its capacity and the
+  generic per-CV loop runs instead."""
+  plan = np.full((h, w), 2, dtype=np.int64)
+  plan[2:h - 2, 2:w - 2] = 1
+  for c in range(3, w - 3, 2):
+    plan[3:h - 3, c] = 0
+  return plan
+
+
+@pytest.mark.parametrize("path", list(PATHS))
+def test_many_rooms_per_vector(path):
+  sc = S.Scenario(floor_plan=_strip_rooms_plan(), buffer_from_walls=0, cv_size_cm=20.0)
+  cp = sc.compiled()
+  assert cp.n_zones == 45
+  B, N = 2, 6
+  env = S.make_env(sc, n_envs=B, plans=cp, kernel_path=PATHS[path])
+  try:
+    oracles = [S.make_oracle(sc, cp) for _ in range(B)]
+    ts = env.reset()
+    for o in oracles:
+      o.reset()
+    _compare_step(env, oracles, ts, B, cp, -1)
+    rng = np.random.default_rng(5)
+    for step in range(N):
+      a = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+      ts = env.step(a)
+      for b, o in enumerate(oracles):
+        o.step(a[b])
+      _compare_step(env, oracles, ts, B, cp, step)
+  finally:
+    env.close()
+
+
 def test_episode_boundaries_and_auto_reset():
   """step_type / discount sequence and the auto-reset of environment.py:1252, 1313-1368."""
   n = 5

@@ -46,6 +46,7 @@ struct sbx_env {
   int n_sms = 0;
   int resident_ctas_per_sm = 0;
   size_t resident_smem = 0;
+  CUtensorMap tmap_t;            // [B, H, W] temperature field, box [1, H, P] (k_resident_step)
   size_t gs_smem = 0;
   Params P;
   // host-level episode state
@@ -255,6 +256,31 @@ int run_stream_sweeps(sbx_handle h, cudaStream_t st) {
   return SBX_OK;
 }
 
+// Tensor map of the [B, H, W] fp32 temperature field with a [1, H, P] box (P > W:
+// the extra columns are zero-filled on load, clipped on store).  The driver entry
+// point is resolved through the runtime, so libsbx does not link libcuda.
+int make_plane_tensor_map(sbx_handle h, float* base, int B, int H, int W, int P) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
+                                  CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
+                                  CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  cudaError_t e = cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres);
+  if (e != cudaSuccess || qres != cudaDriverEntryPointSuccess || !fn)
+    return fail(h, SBX_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
+  const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
+  const cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
+  const cuuint32_t box[3] = {(cuuint32_t)P, (cuuint32_t)H, 1};
+  const cuuint32_t estride[3] = {1, 1, 1};
+  const CUresult r = reinterpret_cast<EncodeTiled>(fn)(
+      &h->tmap_t, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstride, box, estride,
+      CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
+      CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) return fail(h, SBX_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
+  return SBX_OK;
+}
+
 int prepare_plans(sbx_handle h, cudaStream_t st) {
   if (!h->plans_dirty) return SBX_OK;
   const Params& p = h->P;
@@ -292,8 +318,8 @@ int run_resident(sbx_handle h, cudaStream_t st) {
     k_build_header<<<(unsigned)((p.B + wpb - 1) / wpb), wpb * 32, 0, st>>>(p);
     if (int rc = launch_check(h, "k_build_header")) return rc;
   }
-  if (h->V == 4) k_resident_step<4><<<p.B, kResidentThreads, h->resident_smem, st>>>(p);
-  else k_resident_step<1><<<p.B, kResidentThreads, h->resident_smem, st>>>(p);
+  if (h->V == 4) k_resident_step<4><<<p.B, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
+  else k_resident_step<1><<<p.B, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
   return launch_check(h, "k_resident_step");
 }
 
@@ -411,12 +437,12 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   h->V = (c.width % 4 == 0) ? 4 : 1;
 
   // path selection
-  const ResidentLayout L = resident_layout((int)N, (int)Z, h->V);
+  const ResidentGeom L = resident_geom(c.height, c.width, (int)Z, h->V);
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
-  const bool fits = L.total <= (size_t)max_optin && N / h->V <= 32767;
+  const bool fits = L.total <= max_optin && L.plane_cv / h->V <= 32767;
   if (c.kernel_path == SBX_PATH_RESIDENT && !fits) {
-    fail(h, SBX_E_INVALID, "resident path needs %zu B of shared memory per CTA; device allows %d", L.total, max_optin);
+    fail(h, SBX_E_INVALID, "resident path needs %d B of shared memory per CTA; device allows %d", L.total, max_optin);
     return bail(SBX_E_INVALID);
   }
   h->path = (c.kernel_path == SBX_PATH_AUTO) ? (fits ? SBX_PATH_RESIDENT : SBX_PATH_STREAMING) : c.kernel_path;
@@ -445,6 +471,7 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
 
   Params& p = h->P;
   memset(&p, 0, sizeof(p));
+  p.geom = L;
   fill_params(h);
 #define ALLOC(field, type, count)                                           \
   do {                                                                      \
@@ -458,12 +485,11 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.zone_ncv, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.zone_ndiff, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.obs_zone_order, int32_t, (size_t)c.n_plans * Z);
-  ALLOC(p.desc_packed, uint16_t, (size_t)c.n_plans * N);
-  ALLOC(p.qlist, uint16_t, (size_t)c.n_plans * (N / h->V));
+  ALLOC(p.desc_packed, uint16_t, (size_t)c.n_plans * p.geom.desc_stride);
+  ALLOC(p.qlist, uint16_t, (size_t)c.n_plans * p.geom.list_stride);
   ALLOC(p.n_fast, int32_t, (size_t)c.n_plans * 4);
   ALLOC(p.hdr, unsigned char, B * header_bytes((int)Z));
-  p.rl_cap = reduce_list_capacity((int)(N / h->V), (int)Z);
-  ALLOC(p.rlist, uint32_t, (size_t)c.n_plans * p.rl_cap);
+  ALLOC(p.rlist, uint32_t, (size_t)c.n_plans * p.geom.rl_cap);
   ALLOC(p.rl_chunks, int32_t, (size_t)c.n_plans);
   ALLOC(p.reset_temps, float, (size_t)c.n_reset * N);
   ALLOC(p.initial_temp, float, B);
@@ -483,6 +509,10 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   const int n_tbuf = h->path == SBX_PATH_RESIDENT ? 1 : 3;
   for (int i = 0; i < n_tbuf; ++i) ALLOC(p.tbuf[i], float, B * N);
   for (int i = n_tbuf; i < 3; ++i) p.tbuf[i] = p.tbuf[0];
+  memset(&h->tmap_t, 0, sizeof(h->tmap_t));
+  if (h->path == SBX_PATH_RESIDENT && p.geom.use_tmap) {
+    if (int rc = make_plane_tensor_map(h, p.tbuf[0], (int)B, c.height, c.width, p.geom.P)) return bail(rc);
+  }
   ALLOC(p.cur, uint8_t, B);
   ALLOC(p.zone_mean, float, B * Z);
   ALLOC(p.global_mean, float, B);

@@ -14,6 +14,7 @@
 //     at the points where the reference stores them in proto `float` fields.
 #pragma once
 
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -46,8 +47,20 @@ struct __align__(16) Combo {
 // packed descriptor bits (k_prepare_plan): combo index | half-U | diffuser | half-V | zone
 constexpr uint32_t kPackIdxMask = 31u, kPackHalfU = 0x20u, kPackHalfV = 0x80u;
 
+struct ResidentGeom {
+  int P, Pq;            // row pitch in CVs / in vectors
+  int plane_cv;         // H * P
+  unsigned pq_magic;    // slot / Pq == umulhi(slot, pq_magic) for slot < 2^16
+  int rl_cap;           // zone-sum list capacity (entries)
+  int use_tmap;         // temperature plane moved by one tensor-map TMA op (else one bulk copy per row)
+  int desc_stride;      // global stride of a plan's packed descriptor plane (u16), 16 B multiple
+  int list_stride;      // global stride of a plan's vector list (u16), 16 B multiple
+  int off_a, off_b, off_n3, off_desc, off_list, off_rlist, off_hdr, off_bins, off_wmax, off_bar, total;
+};
+
 // Everything a kernel needs; passed by value.
 struct Params {
+  ResidentGeom geom;
   // sizes
   int B, H, W, Z, n_plans, n_weather, n_reset, n_occ_zones, T_rows;
   int obs_mode, D, n_actions;
@@ -80,7 +93,6 @@ struct Params {
   int32_t* n_fast;           // [P,4] sizes of the FAST / MEDIUM / EXT / SLOW vector lists
   uint32_t* rlist;           // [P, rl_cap] zone-sum list (k_prepare_reduce)
   int32_t* rl_chunks;        // [P] warps' worth of entries in it, -1 = does not fit
-  int rl_cap;
   unsigned char* hdr;        // [B, header_bytes(Z)] per-building solve header (k_build_header)
   const float* reset_temps;  // [n_reset,H,W]
   const float* initial_temp; // [B]

@@ -109,11 +109,32 @@ __device__ __forceinline__ void tma_load_1d(void* smem_dst, const void* gmem_src
       "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
       : "memory");
 }
-__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+// Tiled (tensor-map) copies of one building's [H, W] temperature plane.  The box is
+// [1, H, P] with P > W: the out-of-range columns are zero-filled on load and clipped
+// on store, which gives the pitched shared-memory rows (ResidentGeom) in ONE
+// transaction per plane (SASS UTMALDG / UTMASTG).
+__device__ __forceinline__ void tma_load_plane(void* smem_dst, const void* tmap, int b, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];" ::
+          "r"(smem_u32(smem_dst)),
+      "l"(tmap), "r"(smem_u32(bar)), "r"(0), "r"(0), "r"(b)
+      : "memory");
+}
+__device__ __forceinline__ void tma_store_plane(const void* tmap, int b, const void* smem_src) {
+  asm volatile("cp.async.bulk.tensor.3d.global.shared::cta.bulk_group [%0, {%2, %3, %4}], [%1];" ::"l"(tmap),
+               "r"(smem_u32(smem_src)), "r"(0), "r"(0), "r"(b)
+               : "memory");
+}
+// generic-proxy writes (made visible by the preceding CTA barrier) -> async proxy
+__device__ __forceinline__ void tma_store_fence() {
   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_src, uint32_t bytes) {
   asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
 __device__ __forceinline__ void tma_store_wait() {
@@ -135,11 +156,17 @@ __host__ __device__ inline size_t header_bytes(int Z) {
   return sizeof(Combo) * kNumCombos + header_q_slots(Z) * 4 + 32 + 48;
 }
 
-struct ResidentLayout {
-  size_t off_a, off_b, off_n3, off_desc, off_list, off_rlist, off_hdr, off_bins, off_wmax,
-      off_bar, total;
-};
-
+// Shared-memory geometry of k_resident_step, computed once on the host and passed
+// in Params (constant bank -> uniform registers; nothing is recomputed per thread).
+//
+// Rows are stored with a pitch of P CVs, P/V ODD: vector (r, q) lives in slot
+// r * Pq + q, so the 16-byte bank group of a vector, slot mod 8, rotates from row to
+// row.  The vector lists skip whole columns (walls); with the natural pitch
+// (W/4 = 24 for the 64x96 benchmark grids) the skipped columns would empty some
+// residue classes, the 8 lanes of a quarter-warp could not all hit different bank
+// groups, and 128-bit shared-memory accesses replayed 1.5-1.9x (measured with ncu);
+// with the rotated pitch every residue class is equally populated and the
+// accesses are conflict-free.
 // Capacity (entries) of a plan's zone-sum list: one entry per (vector, zone) pair --
 // a vector straddling a wall contributes two or three -- plus each zone segment
 // padded to a whole warp.  Plans that need more fall back to a generic loop.
@@ -147,22 +174,33 @@ __host__ __device__ inline int reduce_list_capacity(int n_items, int Z) {
   return ((n_items + n_items / 2 + 31) & ~31) + 32 * (Z + 1);
 }
 
-__host__ __device__ inline ResidentLayout resident_layout(int n_cv, int Z, int V) {
-  ResidentLayout L;
-  auto al = [](size_t v) { return (v + 15) & ~(size_t)15; };
+__host__ inline ResidentGeom resident_geom(int H, int W, int Z, int V) {
+  ResidentGeom g;
+  const int wq = W / V;
+  g.Pq = (V == 4 && (wq % 2) == 0) ? wq + 1 : wq;
+  g.P = g.Pq * V;
+  g.plane_cv = H * g.P;
+  g.pq_magic = 0xFFFFFFFFu / (unsigned)g.Pq + 1u;
+  g.rl_cap = reduce_list_capacity(H * wq, Z);
+  g.desc_stride = (g.plane_cv + 7) & ~7;
+  g.list_stride = (H * wq + 7) & ~7;
+  // one tensor-map box per plane (box dims <= 256); otherwise one bulk copy per row
+  g.use_tmap = (V == 4 && g.P <= 256 && H <= 256) ? 1 : 0;
+  auto al = [](size_t v) { return (int)((v + 15) & ~(size_t)15); };
+  auto al128 = [](size_t v) { return (int)((v + 127) & ~(size_t)127); };
   size_t o = 0;
-  L.off_a = o; o = al(o + (size_t)n_cv * 4);
-  L.off_b = o; o = al(o + (size_t)n_cv * 4);
-  L.off_n3 = o; o = al(o + (size_t)n_cv * 4);
-  L.off_desc = o; o = al(o + (size_t)n_cv * 2);
-  L.off_list = o; o = al(o + (size_t)(n_cv / V) * 2);
-  L.off_rlist = o; o = al(o + (size_t)reduce_list_capacity(n_cv / V, Z) * 4);
-  L.off_hdr = o; o = al(o + header_bytes(Z));
-  L.off_bins = o; o = al(o + (size_t)(Z + 1) * 8 * (kResidentThreads / 32 + 1));
-  L.off_wmax = o; o = al(o + 32 * 4);
-  L.off_bar = o; o = al(o + 16);
-  L.total = o;
-  return L;
+  g.off_a = (int)o; o = al128(o + (size_t)g.plane_cv * 4);
+  g.off_b = (int)o; o = al128(o + (size_t)g.plane_cv * 4);
+  g.off_n3 = (int)o; o = al(o + (size_t)g.plane_cv * 4);
+  g.off_desc = (int)o; o = al(o + (size_t)g.desc_stride * 2);
+  g.off_list = (int)o; o = al(o + (size_t)g.list_stride * 2);
+  g.off_rlist = (int)o; o = al(o + (size_t)g.rl_cap * 4);
+  g.off_hdr = (int)o; o = al(o + header_bytes(Z));
+  g.off_bins = (int)o; o = al(o + (size_t)(Z + 1) * 8 * (kResidentThreads / 32 + 1));
+  g.off_wmax = (int)o; o = al(o + 32 * 4);
+  g.off_bar = (int)o; o = al(o + 16);
+  g.total = (int)o;
+  return g;
 }
 
 // Accumulates V consecutive CVs into per-zone shared bins (fixed point) + grid total.
@@ -241,8 +279,9 @@ __global__ void __launch_bounds__(128) k_build_header(const Params p) {
 //   SLOW    everything else (boundary classes): generic, table-driven.
 // Bit 15 of a MEDIUM / SLOW entry says the vector holds a diffuser CV.
 //
-// Order inside each list: (rank within the vector's index-mod-8 class, index mod
-// 8), i.e. every aligned group of 8 entries holds 8 different residues mod 8, so the
+// Entries are shared-memory vector SLOTS (row * Pq + column, see ResidentGeom).
+// Order inside each list: (rank within the vector's slot-mod-8 class, slot mod 8),
+// i.e. every aligned group of 8 entries holds 8 different residues mod 8, so the
 // 8 lanes of a quarter-warp touch 8 different 16-byte bank groups and the 128-bit
 // shared-memory accesses of the sweep stay conflict-free although the lists skip
 // vectors.  One CTA per plan; ranks are computed by counting smaller keys (O(n^2)
@@ -257,11 +296,17 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan(const Params p) {
   uint32_t* key = reinterpret_cast<uint32_t*>(smem_prep);
   uint16_t* key1 = reinterpret_cast<uint16_t*>(key + n_items);
   __shared__ int s_count[4];
+  const ResidentGeom& g = p.geom;
+  const int wq = p.W / V;
   const uint16_t* raw = p.desc + (size_t)plan * n_cv;
-  uint16_t* packed = p.desc_packed + (size_t)plan * n_cv;
-  uint16_t* qlist = p.qlist + (size_t)plan * n_items;
+  uint16_t* packed = p.desc_packed + (size_t)plan * g.desc_stride;
+  uint16_t* qlist = p.qlist + (size_t)plan * g.list_stride;
   if (tid < 4) s_count[tid] = 0;
-  for (int i = tid; i < n_cv; i += kPrepThreads) packed[i] = (uint16_t)repack_desc(raw[i]);
+  for (int i = tid; i < g.desc_stride; i += kPrepThreads) {     // padded rows (pitch P)
+    const int r = i / g.P, j = i - r * g.P;
+    packed[i] = (r < p.H && j < p.W) ? (uint16_t)repack_desc(raw[r * p.W + j]) : (uint16_t)0;
+  }
+  for (int i = n_items + tid; i < g.list_stride; i += kPrepThreads) qlist[i] = 0;
   __syncthreads();
   // key1 = list | residue
   for (int it = tid; it < n_items; it += kPrepThreads) {
@@ -273,7 +318,8 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan(const Params p) {
       ext = ext && (desc_class(d) == SBX_CV_EXTERIOR);
     }
     const int kind = fast ? kListFast : interior ? kListMedium : ext ? kListExt : kListSlow;
-    key1[it] = (uint16_t)((kind << 3) | (it & 7));
+    const int slot = (it / wq) * g.Pq + it % wq;       // where the vector lives in shared memory
+    key1[it] = (uint16_t)((kind << 3) | (slot & 7));
     atomicAdd(&s_count[kind], 1);
   }
   __syncthreads();
@@ -281,7 +327,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan(const Params p) {
   for (int it = tid; it < n_items; it += kPrepThreads) {
     const uint32_t k1 = key1[it];
     int m = 0;
-    for (int j = (it & 7); j < it; j += 8) m += (key1[j] == k1) ? 1 : 0;   // same residue only
+    for (int j = 0; j < it; ++j) m += (key1[j] == k1) ? 1 : 0;
     key[it] = ((k1 >> 3) << 18) | ((uint32_t)m << 3) | (k1 & 7u);
   }
   __syncthreads();
@@ -292,7 +338,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan(const Params p) {
     for (int j = 0; j < n_items; ++j) rank += (key[j] < k2) ? 1 : 0;
     bool diff = false;
     for (int e = 0; e < V; ++e) diff = diff || (raw[it * V + e] & SBX_DESC_DIFFUSER);
-    qlist[rank] = (uint16_t)(it | (diff ? 0x8000 : 0));
+    qlist[rank] = (uint16_t)(((it / wq) * g.Pq + it % wq) | (diff ? 0x8000 : 0));
   }
   if (tid < 4) p.n_fast[plan * 4 + tid] = s_count[tid];
 }
@@ -314,7 +360,8 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_reduce(const Params p)
   int* start = cnt + (Z + 1);                           // [Z+1]
   __shared__ int s_total;
   const uint16_t* raw = p.desc + (size_t)plan * n_cv;
-  uint32_t* rl = p.rlist + (size_t)plan * p.rl_cap;
+  uint32_t* rl = p.rlist + (size_t)plan * p.geom.rl_cap;
+  const int wq = p.W / V, Pq = p.geom.Pq;
   for (int i = tid; i <= Z; i += kPrepThreads) cnt[i] = 0;
   __syncthreads();
   for (int it = tid; it < n_items; it += kPrepThreads) {
@@ -343,7 +390,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_reduce(const Params p)
   }
   __syncthreads();
   const int total = s_total;
-  if (total > p.rl_cap) {            // pathological plan: k_resident_step takes its generic loop
+  if (total > p.geom.rl_cap) {       // pathological plan: k_resident_step takes its generic loop
     if (tid == 0) p.rl_chunks[plan] = -1;
     return;
   }
@@ -366,7 +413,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_reduce(const Params p)
         const int zs = desc_zone(raw[it * V + e]);
         if ((zs == SBX_ZONE_NONE ? (uint32_t)Z : (uint32_t)zs) == slot) mask |= 1u << e;
       }
-      rl[start[slot] + rank] = (uint32_t)it | (mask << 16) | (slot << 20);
+      rl[start[slot] + rank] = (uint32_t)((it / wq) * Pq + it % wq) | (mask << 16) | (slot << 20);
     }
   }
   if (tid == 0) p.rl_chunks[plan] = total / 32;
@@ -392,19 +439,19 @@ struct SweepCtx {
   FastCoef fc;
   AreaCoef az;
   float cm_fast, dt, rdt, t_inf;
-  int n_fast, n_fm, n_fme, n_items, H, W, Z;
-  unsigned wq_magic;
+  int n_fast, n_fm, n_fme, n_items, H, P, Pq, wq, Z;
+  unsigned pq_magic;
 };
 template <int V, bool FIRST>
 __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, float* __restrict__ out,
                                                 float* __restrict__ n3p, const SweepCtx& s, int tid) {
   constexpr int NT = kResidentThreads;
-  const int W = s.W, wq = W / V;
+  const int W = s.P, wq = s.wq;      // W: row pitch in CVs
   const float t_inf = s.t_inf;
   float lmax = 0.f;
   for (int u = tid; u < s.n_items; u += NT) {
     const int entry = (int)s.qlist[u];
-    const int it = entry & 0x7FFF;
+    const int it = entry & 0x7FFF;     // vector slot
     const int base = it * V;
     float c[V], o[V];
     load_f<V>(in + base, c);
@@ -470,8 +517,8 @@ __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, fl
       for (int e = 0; e < V; ++e) o[e] = t_inf;
     } else {
       const bool has_q = (entry & 0x8000) != 0;
-      const int r = (int)__umulhi((unsigned)it, s.wq_magic);
-      const int q = it - r * wq;
+      const int r = (int)__umulhi((unsigned)it, s.pq_magic);
+      const int q = it - r * s.Pq;
       float up[V], dn[V], n3v[V];
       uint32_t d[V];
       load_d<V>(s.dsc + base, d);
@@ -518,7 +565,7 @@ __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, fl
 #endif
 
 template <int V>
-__global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Params p) {
+__global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Params p, const __grid_constant__ CUtensorMap tmap_t) {
   extern __shared__ __align__(128) unsigned char smem[];
 #ifdef SBX_PROFILE_PHASES
   long long phase_t0__ = clock64();
@@ -530,7 +577,8 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   const int n_cv = H * W;
   const int n_items = n_cv / V;
   const int plan = p.n_plans == 1 ? 0 : b;
-  const ResidentLayout L = resident_layout(n_cv, Z, V);
+  const ResidentGeom& L = p.geom;
+  const int P = L.P;                                   // row pitch (CVs) in shared memory
   float* bufA = reinterpret_cast<float*>(smem + L.off_a);
   float* bufB = reinterpret_cast<float*>(smem + L.off_b);
   float* n3p = reinterpret_cast<float*>(smem + L.off_n3);
@@ -545,25 +593,33 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem + L.off_bar);
 
   float* gT = p.tbuf[0] + (size_t)b * n_cv;
-  const uint16_t* gD = p.desc_packed + (size_t)plan * n_cv;
-  const uint16_t* gL = p.qlist + (size_t)plan * n_items;
+  const uint16_t* gD = p.desc_packed + (size_t)plan * L.desc_stride;
+  const uint16_t* gL = p.qlist + (size_t)plan * L.list_stride;
   const uint32_t hdr_bytes = (uint32_t)header_bytes(Z);
   const unsigned char* gH = p.hdr + (size_t)b * hdr_bytes;
-  const bool use_tma = (n_cv % 8) == 0 && (n_items % 8) == 0;
+  constexpr bool use_tma = (V == 4);     // rows are 16-byte multiples
 
   // ---- stage 0: start the bulk loads (TMA, one mbarrier) ----------------------
-  if (use_tma) {
-    if (tid == 0) {
-      mbar_init(bar, 1);
-      mbar_init(bar + 1, 1);
-      mbar_expect_tx(bar, (uint32_t)(n_cv * 4 + n_cv * 2 + n_items * 2) + hdr_bytes);
-      tma_load_1d(smem + L.off_hdr, gH, hdr_bytes, bar);
-      tma_load_1d(bufA, gT, (uint32_t)(n_cv * 4), bar);
-      tma_load_1d(dsc, gD, (uint32_t)(n_cv * 2), bar);
-      tma_load_1d(qlist, gL, (uint32_t)(n_items * 2), bar);
+  // The temperature rows go to their pitched positions: one bulk copy per row,
+  // issued by the lanes of warp 0.
+  if constexpr (use_tma) {
+    if (warp == 0) {
+      if (lane == 0) {
+        mbar_init(bar, 1);
+        mbar_init(bar + 1, 1);
+        mbar_expect_tx(bar, (uint32_t)((L.use_tmap ? L.plane_cv : n_cv) * 4 + L.desc_stride * 2 +
+                                       L.list_stride * 2) + hdr_bytes);
+        tma_load_1d(smem + L.off_hdr, gH, hdr_bytes, bar);
+        if (L.use_tmap) tma_load_plane(bufA, &tmap_t, b, bar);
+        tma_load_1d(dsc, gD, (uint32_t)(L.desc_stride * 2), bar);
+        tma_load_1d(qlist, gL, (uint32_t)(L.list_stride * 2), bar);
+      }
+      __syncwarp();
+      if (!L.use_tmap)
+        for (int r = lane; r < H; r += 32) tma_load_1d(bufA + r * P, gT + r * W, (uint32_t)(W * 4), bar);
     }
   } else {
-    for (int i = tid; i < n_cv; i += NT) {
+    for (int i = tid; i < n_cv; i += NT) {      // V == 1: P == W
       bufA[i] = gT[i];
       dsc[i] = gD[i];
     }
@@ -576,14 +632,14 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   for (int i = tid; i < (Z + 1) * (NW + 1); i += NT) bins[i] = 0;
   __syncthreads();
   SBX_PHASE(0);   // launch .. TMA issued
-  if (use_tma) mbar_wait(bar, 0);
+  if constexpr (use_tma) mbar_wait(bar, 0);
   SBX_PHASE(1);   // waiting for the TMA loads
   const float t_inf = scal[0];
   // the zone-sum list is only needed after the sweeps: fetch it behind them
   const int n_chunks = __float_as_int(scal[5]);
   if (!p.fd_only && n_chunks > 0) {
-    const uint32_t* gR = p.rlist + (size_t)plan * p.rl_cap;
-    if (use_tma) {
+    const uint32_t* gR = p.rlist + (size_t)plan * L.rl_cap;
+    if constexpr (use_tma) {
       if (tid == 0) {
         mbar_expect_tx(bar + 1, (uint32_t)n_chunks * 128u);
         tma_load_1d(rlist, gR, (uint32_t)n_chunks * 128u, bar + 1);
@@ -606,8 +662,8 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   sc.az.full = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
   sc.az.half = tab[SBX_CV_CORNER_TL * kNumMaterials].vz;
   sc.dt = p.dt; sc.rdt = __frcp_rn(p.dt); sc.t_inf = t_inf;
-  sc.n_items = n_items; sc.H = H; sc.W = W; sc.Z = Z;
-  sc.wq_magic = 0xFFFFFFFFu / (unsigned)(W / V) + 1u;   // it / wq for it < 2^16
+  sc.n_items = n_items; sc.H = H; sc.P = P; sc.Pq = L.Pq; sc.wq = W / V; sc.Z = Z;
+  sc.pq_magic = L.pq_magic;
 
   // ---- stage 2: Jacobi sweeps to convergence (simulator.py:348-364) ---------
   float* in = bufA;
@@ -634,14 +690,26 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   // the stochastic convection model, pre-composed on the host into a gather map
   if (p.conv_perm != nullptr && !p.fd_only) {
     const int32_t* perm = p.conv_perm + (size_t)b * n_cv;
-    for (int i = tid; i < n_cv; i += NT) out[i] = in[perm[i]];
+    for (int i = tid; i < n_cv; i += NT) {
+      const int src = perm[i];
+      const int r = i / W, rs = src / W;
+      out[r * P + (i - r * W)] = in[rs * P + (src - rs * W)];
+    }
     __syncthreads();
     float* tmp = in; in = out; out = tmp;
   }
 
   // ---- stage 3: write back + zone / grid sums ---------------------------------
-  if (use_tma) {
-    if (tid == 0) tma_store_1d(gT, in, (uint32_t)(n_cv * 4));
+  if constexpr (use_tma) {
+    if (warp == 0) {
+      tma_store_fence();
+      if (L.use_tmap) {
+        if (lane == 0) tma_store_plane(&tmap_t, b, in);
+      } else {
+        for (int r = lane; r < H; r += 32) tma_store_1d(gT + r * W, in + r * P, (uint32_t)(W * 4));
+      }
+      tma_store_commit();
+    }
   } else {
     for (int i = tid; i < n_cv; i += NT) gT[i] = in[i];
   }
@@ -655,7 +723,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     // running sum of zone z lives in a REGISTER of lane z mod 32; shared memory is
     // touched once per warp at the end.  No atomics (a shared-memory 64-bit atomic is
     // a CAS loop on this hardware), no per-element zone decoding.
-    if (use_tma) mbar_wait(bar + 1, 0);
+    if constexpr (use_tma) mbar_wait(bar + 1, 0);
     long long acc = 0;
     int acc_zone = lane;          // the zone this lane currently accumulates
     for (int chunk = warp; chunk < n_chunks; chunk += NW) {
@@ -682,8 +750,9 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   } else if (!p.fd_only) {
     // generic loop (plans whose zone-sum list does not fit): per-CV atomics
     for (int i = tid; i < n_cv; i += NT) {
-      const int zs = desc_zone(dsc[i]);
-      fix_add(&bins[zs == SBX_ZONE_NONE ? Z : zs], (long long)to_fix32(in[i], t_inf));
+      const int r = i / W, idx = r * P + (i - r * W);
+      const int zs = desc_zone(dsc[idx]);
+      fix_add(&bins[zs == SBX_ZONE_NONE ? Z : zs], (long long)to_fix32(in[idx], t_inf));
     }
   }
   __syncthreads();
@@ -715,7 +784,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
       if (lane == 0) zs[Z] = grid;
     }
   }
-  if (use_tma && tid == 0) tma_store_wait();
+  if (use_tma && warp == 0) tma_store_wait();
 }
 
 

@@ -29,6 +29,8 @@ def _plans():
       "small_24x34": (S.small_plan(), 2),
       "odd_23x31": (S.small_plan(23, 31), 2),
       "rand_64x96": (floorplan.random_floor_plan(rng).astype(np.int64), 3),
+      # wider than a TMA tensor-map box (256): the resident kernel copies row by row
+      "wide_12x320": (S.small_plan(12, 320), 1),
   }
 
 

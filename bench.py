@@ -41,7 +41,7 @@ UNIT = "env-steps/s"
 def parse_args():
   ap = argparse.ArgumentParser()
   ap.add_argument("--gpus", type=int, default=1)
-  ap.add_argument("--steps", type=int, default=40)
+  ap.add_argument("--steps", type=int, default=200)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", choices=["sbx", "reference"], default="sbx")
   ap.add_argument("--workload", choices=["randomized", "office"], default="randomized")
@@ -58,6 +58,8 @@ def parse_args():
   ap.add_argument("--convergence-threshold", type=float, default=0.1,
                   help="experiments only; BASELINE uses 0.1 K (sim_config.gin:161)")
   ap.add_argument("--iteration-limit", type=int, default=100)
+  ap.add_argument("--chunks", type=int, default=0,
+                  help="SBX_OPT_PIPELINE_CHUNKS override (0 = the library's choice)")
   return ap.parse_args()
 
 
@@ -90,7 +92,7 @@ class ClockSampler(threading.Thread):
           self.samples.append(parts)
       except Exception:  # pylint: disable=broad-except
         pass
-      self._stop_evt.wait(0.2)
+      self._stop_evt.wait(0.05)
 
   def stop(self):
     self._stop_evt.set()
@@ -130,7 +132,7 @@ def build_env(args, rank, local_rank):
   from sbsim_b200 import floorplan, workloads
   path = {"auto": sbx.PATH_AUTO, "streaming": sbx.PATH_STREAMING,
           "resident": sbx.PATH_RESIDENT}[args.path]
-  episode = args.warmup + args.steps * 2 + 8
+  episode = args.warmup + args.steps + 16
   if args.workload == "randomized":
     n = args.envs_per_gpu or 32768
     env, wl = workloads.make_randomized_env(
@@ -170,6 +172,9 @@ def run_sbx(args):
     dist.init_process_group("nccl", device_id=dev)
 
   env, wl, cfg_desc = build_env(args, rank, local_rank)
+  if args.chunks > 0:
+    from sbsim_b200 import _lib
+    env.handle.set_option(_lib.OPT_PIPELINE_CHUNKS, args.chunks)
   B = env.batch_size
   D = env.observation_spec().shape[0]
   A = env.action_spec().shape[0]
@@ -229,17 +234,37 @@ def run_sbx(args):
   mean_sweeps = sweeps / float(B * K)
   value = world * B * K / (max_ms / 1e3)
 
+  # ---- kernel-timing pass: CUDA events recorded by the library around every solve
+  # launch, on the stream the kernel is launched on (sbx_timing_begin / _end) ----
+  # The SAME trajectory again (reset, same actions: the step is deterministic, so the
+  # sweep counts are identical to the value pass), this time with the events on.
+  env.reset_device(obs, rew, st, dis, stream=sptr)
+  for i in range(W):
+    one_step(i)
+  barrier()
+  info1b = env.handle.info()
+  env.handle.timing_begin()
+  for i in range(K):
+    one_step(W + i)
+  barrier()
+  tm = env.handle.timing_end()
+  solve_ms = tm.solve_ms / max(tm.n_steps, 1)           # all solve launches of one step
+  timed_step_ms = tm.step_ms / max(tm.n_steps, 1)
+  info2 = env.handle.info()
+  sweeps_t = int(info2.sweeps_total - info1b.sweeps_total) / float(B * max(tm.n_steps, 1))
+
   # ---- end-to-end through the public host API (e2e) ----
   e2e = None
   if not args.no_e2e:
     a_host = (np.random.default_rng(4000 + rank).uniform(-1, 1, (W + K, B, A))
               .astype(np.float32))
-    for i in range(3):
+    env.reset()
+    for i in range(W):
       env.step(a_host[i])
     barrier()
     t0 = time.perf_counter()
     for i in range(K):
-      ts = env.step(a_host[3 + i])
+      ts = env.step(a_host[W + i])
     torch.cuda.synchronize(dev)
     el = time.perf_counter() - t0
     t = torch.tensor([el], device=dev, dtype=torch.float64)
@@ -260,17 +285,17 @@ def run_sbx(args):
   desc_bytes = 2 if len(env.building.plans) > 1 else 0
   bytes_step = algorithmic_bytes_per_env_step(n_cv, Z, D, A, desc_bytes, mean_sweeps, resident)
   peak, peak_src = measured_peak_gbs()
+  # achieved = algorithmic bytes of one step's solve launches / their measured duration
+  bytes_step_t = algorithmic_bytes_per_env_step(n_cv, Z, D, A, desc_bytes, sweeps_t, resident)
+  bytes_launch = bytes_step_t * B
+  launch_ms = solve_ms
+  achieved = bytes_launch / (launch_ms / 1e3) / 1e9
   if resident:
-    kernel = "k_resident_step (whole step, one launch)"
-    launch_ms = statistics.mean(per_step_ms)
-    bytes_launch = bytes_step * B
-    achieved = bytes_launch / (launch_ms / 1e3) / 1e9
+    kernel = ("k_resident_step (the whole diffusion solve of every building; %d launch(es) per "
+              "step, one per pipelined share of the batch)" % tm.n_chunks)
   else:
-    kernel = "k_sweep (one Jacobi sweep of every active building)"
-    # sweeps dominate the step; the per-launch figure is the step's bytes over its time
-    launch_ms = statistics.mean(per_step_ms)
-    bytes_launch = bytes_step * B
-    achieved = bytes_launch / (launch_ms / 1e3) / 1e9
+    kernel = "k_sweep (one Jacobi sweep of every active building per launch; %.2f launches per step)" % (
+        tm.n_solve_launches / max(tm.n_steps, 1))
   traffic = None
   try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this B
     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -282,9 +307,13 @@ def run_sbx(args):
   roofline = {"bound": "hbm", "kernel": kernel, "achieved": achieved, "peak": peak,
               "unit": "GB/s", "frac": achieved / peak, "peak_source": peak_src,
               "traffic": traffic, "algorithmic_bytes_per_launch": bytes_launch,
-              "algorithmic_bytes_per_env_step": bytes_step,
-              "mean_sweeps_per_step": mean_sweeps,
-              "launch_ms": launch_ms}
+              "algorithmic_bytes_per_env_step": bytes_step_t,
+              "mean_sweeps_per_step": sweeps_t,
+              "launch_ms": launch_ms, "timed_steps": int(tm.n_steps),
+              "timing": "cudaEvent pairs around each solve launch on its stream (sbx_timing_*)",
+              # the same bytes over the WHOLE step (HVAC prologue / epilogue included)
+              "step_ms": timed_step_ms, "kernel_share_of_step": launch_ms / timed_step_ms,
+              "frac_whole_step": bytes_step * B / (statistics.mean(per_step_ms) / 1e3) / 1e9 / peak}
 
   # ---- CPU baseline beside it (rank 0, N=1 only) ----
   cpu = None

@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SBX_ABI_VERSION 2
+#define SBX_ABI_VERSION 3
 
 #define SBX_OK 0
 #define SBX_E_INVALID (-1)   /* bad argument / config                      */
@@ -280,6 +280,25 @@ int sbx_fd_step(sbx_handle h, const double* ambient, const double* convection);
  * straight between the caller's arrays and the device (no staging memcpy). */
 int sbx_host_alloc(size_t bytes, void** out);
 int sbx_host_free(void* p);
+
+/* Tuning knobs (new, no reference counterpart). */
+#define SBX_OPT_PIPELINE_CHUNKS 1 /* resident Jacobi path: shares of the batch a step is pipelined over (1 = one launch per kernel) */
+int sbx_set_option(sbx_handle h, int option, int64_t value);
+
+/* In-library timing with CUDA events on the streams the kernels are launched on:
+ * between sbx_timing_begin and sbx_timing_end every sbx_step records an event pair
+ * around the whole step and around each diffusion-solve launch (k_resident_step /
+ * k_resident_gs / every k_sweep).  sbx_timing_end synchronises and sums them. */
+typedef struct {
+  int64_t n_steps;          /* steps recorded */
+  int64_t n_solve_launches; /* solve-kernel launches recorded */
+  double step_ms;           /* sum over steps of (step end - step begin) */
+  double solve_ms;          /* sum over launches of the solve kernel's duration */
+  int32_t n_chunks;         /* SBX_OPT_PIPELINE_CHUNKS in effect */
+  int32_t reserved;
+} sbx_timing;
+int sbx_timing_begin(sbx_handle h);
+int sbx_timing_end(sbx_handle h, sbx_timing* out);
 
 /* Blocks until all work queued by this handle has finished. */
 int sbx_sync(sbx_handle h);

@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SBX_LIB: developer override used to A/B kernel variants (profiles/); same ABI, same checks
 LIB_PATH = os.environ.get("SBX_LIB") or os.path.join(_HERE, "lib", "libsbx.so")
 
-ABI_VERSION = 2
+ABI_VERSION = 3
+OPT_PIPELINE_CHUNKS = 1
 OK = 0
 MAX_ACTIONS = 3
 MAX_HIST_BINS = 32
@@ -129,10 +130,18 @@ class SbxInfo(C.Structure):
   ]
 
 
+class SbxTiming(C.Structure):
+  _fields_ = [
+      ("n_steps", C.c_int64), ("n_solve_launches", C.c_int64), ("step_ms", C.c_double),
+      ("solve_ms", C.c_double), ("n_chunks", C.c_int32), ("reserved", C.c_int32),
+  ]
+
+
 EXPORTS = (
     "sbx_create", "sbx_destroy", "sbx_last_error", "sbx_get_info", "sbx_upload",
     "sbx_download", "sbx_reset", "sbx_step", "sbx_reset_host", "sbx_step_host",
     "sbx_fd_step", "sbx_sync", "sbx_abi_info", "sbx_host_alloc", "sbx_host_free",
+    "sbx_set_option", "sbx_timing_begin", "sbx_timing_end",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -168,6 +177,9 @@ def load() -> C.CDLL:
   lib.sbx_abi_info.argtypes = [C.POINTER(C.c_int32), C.POINTER(sz), C.POINTER(sz)]
   lib.sbx_host_alloc.argtypes = [sz, C.POINTER(vp)]
   lib.sbx_host_free.argtypes = [vp]
+  lib.sbx_set_option.argtypes = [vp, C.c_int, C.c_int64]
+  lib.sbx_timing_begin.argtypes = [vp]
+  lib.sbx_timing_end.argtypes = [vp, C.POINTER(SbxTiming)]
   for name in EXPORTS:
     if name != "sbx_last_error":
       getattr(lib, name).restype = C.c_int
@@ -279,3 +291,15 @@ class Handle:
 
   def sync(self):
     self._check(self._lib.sbx_sync(self._h), "sbx_sync")
+
+  def set_option(self, option: int, value: int):
+    self._check(self._lib.sbx_set_option(self._h, int(option), C.c_int64(int(value))),
+                "sbx_set_option")
+
+  def timing_begin(self):
+    self._check(self._lib.sbx_timing_begin(self._h), "sbx_timing_begin")
+
+  def timing_end(self) -> SbxTiming:
+    out = SbxTiming()
+    self._check(self._lib.sbx_timing_end(self._h, C.byref(out)), "sbx_timing_end")
+    return out

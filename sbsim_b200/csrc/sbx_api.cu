@@ -20,6 +20,7 @@
 
 #include <new>
 #include <string>
+#include <vector>
 
 #include "../../include/sbx.h"
 #include "sbx_kernels.cuh"
@@ -36,6 +37,8 @@ struct DevBuf {
 };
 
 }  // namespace
+
+constexpr int SBX_MAX_CHUNKS = 8;
 
 struct sbx_env {
   sbx_config cfg;
@@ -82,6 +85,18 @@ struct sbx_env {
   float* h_discount = nullptr;
   int32_t* h_n_active = nullptr; // pinned
   cudaStream_t stream = nullptr; // handle-owned stream for *_host calls and uploads
+  // Resident path, large batches: the step is cut into `n_chunks` contiguous shares
+  // of the batch.  The small HVAC kernels run on a high-priority stream, the solves
+  // on a low-priority one, chained by events, so that the epilogue of share c fills
+  // SM slots while share c+1 is still solving (see do_step).
+  int n_chunks = 1;
+  cudaStream_t s_hi = nullptr, s_lo = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaEvent_t ev_pre[SBX_MAX_CHUNKS] = {}, ev_solve[SBX_MAX_CHUNKS] = {};
+  // sbx_timing_begin / sbx_timing_end: CUDA events around every step and every solve launch
+  int timing_on = 0;
+  std::vector<cudaEvent_t> t_step, t_solve;   // pairs (begin, end)
+  size_t t_step_used = 0, t_solve_used = 0;
   std::string err;
 };
 
@@ -205,8 +220,10 @@ void fill_params(sbx_handle h) {
 
 // launch helpers --------------------------------------------------------------
 
-int pre_post_smem(const sbx_handle h, int warps) {
-  return warps * (3 * h->cfg.n_zones + 64 + h->cfg.n_zones) * (int)sizeof(double);
+// lanes per building in k_pre / k_post: 8 (four buildings per warp) for plans with few zones
+int hvac_group(const sbx_handle h) { return h->cfg.n_zones <= 16 ? 8 : 32; }
+int pre_post_smem(const sbx_handle h, int groups) {
+  return groups * (3 * h->cfg.n_zones + 64 + h->cfg.n_zones) * (int)sizeof(double);
 }
 
 int launch_check(sbx_handle h, const char* what) {
@@ -226,26 +243,57 @@ int launch_zone_reduce(sbx_handle h, cudaStream_t st) {
   return launch_check(h, "k_zone_reduce");
 }
 
+// timing events (sbx_timing_begin .. sbx_timing_end)
+int timing_record(sbx_handle h, std::vector<cudaEvent_t>& pool, size_t& used, cudaStream_t st) {
+  if (!h->timing_on) return SBX_OK;
+  if (used == pool.size()) {
+    cudaEvent_t e;
+    CUDA_TRY(h, cudaEventCreate(&e));
+    pool.push_back(e);
+  }
+  CUDA_TRY(h, cudaEventRecord(pool[used++], st));
+  return SBX_OK;
+}
+
+int launch_pre(sbx_handle h, cudaStream_t st) {
+  const Params& p = h->P;
+  const int G = hvac_group(h), bpc = 128 / G;          // buildings per CTA
+  const unsigned grid = (unsigned)((p.b_end - p.b_begin + bpc - 1) / bpc);
+  if (G == 8) k_pre<8><<<grid, 128, pre_post_smem(h, bpc), st>>>(p, h->carry);
+  else k_pre<32><<<grid, 128, pre_post_smem(h, bpc), st>>>(p, h->carry);
+  return launch_check(h, "k_pre");
+}
+
 int launch_post(sbx_handle h, cudaStream_t st, int is_reset) {
   const Params& p = h->P;
-  const int wpb = 4;
-  const unsigned grid = (unsigned)((p.B + wpb - 1) / wpb);
-  k_post<<<grid, wpb * 32, pre_post_smem(h, wpb), st>>>(p, h->carry, is_reset);
+  const int G = hvac_group(h), bpc = 128 / G;
+  const unsigned grid = (unsigned)((p.b_end - p.b_begin + bpc - 1) / bpc);
+  if (G == 8) k_post<8><<<grid, 128, pre_post_smem(h, bpc), st>>>(p, h->carry, is_reset);
+  else k_post<32><<<grid, 128, pre_post_smem(h, bpc), st>>>(p, h->carry, is_reset);
   return launch_check(h, "k_post");
 }
 
 // Streaming Jacobi loop: one launch per sweep + convergence poll.
 int run_stream_sweeps(sbx_handle h, cudaStream_t st) {
   const Params& p = h->P;
+  if (h->plans_dirty) {
+    const size_t total = (size_t)p.n_plans * p.H * p.W;
+    const unsigned g = (unsigned)((total + 256 * 8 - 1) / (256 * 8));
+    k_pack_stream<<<g > 0 ? g : 1, 256, 0, st>>>(p);
+    if (int rc = launch_check(h, "k_pack_stream")) return rc;
+    h->plans_dirty = 0;
+  }
   const unsigned gb = (unsigned)((p.B + 255) / 256);
   k_activate<<<gb, 256, 0, st>>>(p);
   if (int rc = launch_check(h, "k_activate")) return rc;
   const StreamTiling tl = stream_tiling(p.H, p.W, h->V);
   const unsigned grid = (unsigned)((size_t)tl.tiles * p.B);
   for (int k = 1; k <= p.iteration_limit; ++k) {
+    if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
     if (h->V == 4) k_sweep<4><<<grid, kStreamThreads, 0, st>>>(p, k);
     else k_sweep<1><<<grid, kStreamThreads, 0, st>>>(p, k);
     if (int rc = launch_check(h, "k_sweep")) return rc;
+    if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(p.n_active, 0, sizeof(int32_t), st));
     k_check<<<gb, 256, 0, st>>>(p, k);
     if (int rc = launch_check(h, "k_check")) return rc;
@@ -306,21 +354,27 @@ int prepare_plans(sbx_handle h, cudaStream_t st) {
   return SBX_OK;
 }
 
-int run_resident(sbx_handle h, cudaStream_t st) {
-  if (h->cfg.solver == SBX_SOLVER_GAUSS_SEIDEL) {
-    k_resident_gs<<<h->P.B, kGsThreads, h->gs_smem, st>>>(h->P);
-    return launch_check(h, "k_resident_gs");
-  }
-  if (int rc = prepare_plans(h, st)) return rc;
+// The solve of buildings [p.b_begin, p.b_end).  `with_header`: the per-building solve
+// header has not been built by k_pre (sbx_fd_step, which has no HVAC prologue).
+int run_resident(sbx_handle h, cudaStream_t st, bool with_header) {
   const Params& p = h->P;
-  {
+  if (h->cfg.solver == SBX_SOLVER_GAUSS_SEIDEL) {
+    if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
+    k_resident_gs<<<p.B, kGsThreads, h->gs_smem, st>>>(p);
+    if (int rc = launch_check(h, "k_resident_gs")) return rc;
+    return timing_record(h, h->t_solve, h->t_solve_used, st);
+  }
+  if (with_header) {
     const int wpb = 4;
-    k_build_header<<<(unsigned)((p.B + wpb - 1) / wpb), wpb * 32, 0, st>>>(p);
+    k_build_header<<<(unsigned)((p.b_end - p.b_begin + wpb - 1) / wpb), wpb * 32, 0, st>>>(p);
     if (int rc = launch_check(h, "k_build_header")) return rc;
   }
-  if (h->V == 4) k_resident_step<4><<<p.B, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
-  else k_resident_step<1><<<p.B, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
-  return launch_check(h, "k_resident_step");
+  const unsigned grid = (unsigned)(p.b_end - p.b_begin);
+  if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
+  if (h->V == 4) k_resident_step<4><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
+  else k_resident_step<1><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
+  if (int rc = launch_check(h, "k_resident_step")) return rc;
+  return timing_record(h, h->t_solve, h->t_solve_used, st);
 }
 
 int do_reset(sbx_handle h, float* obs, float* reward, int32_t* step_type, float* discount,
@@ -330,6 +384,7 @@ int do_reset(sbx_handle h, float* obs, float* reward, int32_t* step_type, float*
   p.time_index = 0; p.step_count = 0;
   p.therm_seen = h->therm_seen; p.prev_comfort = h->prev_comfort;
   p.action = nullptr; p.obs = obs; p.reward = reward; p.step_type = step_type; p.discount_out = discount;
+  p.b_begin = 0; p.b_end = p.B; p.build_hdr = 0;
   const unsigned gb = (unsigned)((p.B + 255) / 256);
   k_reset_state<<<gb, 256, 0, st>>>(p);
   if (int rc = launch_check(h, "k_reset_state")) return rc;
@@ -355,13 +410,49 @@ int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_
   p.therm_seen = h->therm_seen; p.prev_comfort = h->prev_comfort;
   p.action = action; p.obs = obs; p.reward = reward; p.step_type = step_type; p.discount_out = discount;
   p.conv_perm = h->conv_pending ? h->conv_perm : nullptr;
-  {
-    const int wpb = 4;
-    const unsigned grid = (unsigned)((p.B + wpb - 1) / wpb);
-    k_pre<<<grid, wpb * 32, pre_post_smem(h, wpb), st>>>(p, h->carry);
-    if (int rc = launch_check(h, "k_pre")) return rc;
+  p.b_begin = 0; p.b_end = p.B; p.build_hdr = 0;
+  const bool jacobi_resident = h->path == SBX_PATH_RESIDENT && h->cfg.solver == SBX_SOLVER_TF_JACOBI;
+  if (jacobi_resident) if (int rc = prepare_plans(h, st)) return rc;
+  if (int rc = timing_record(h, h->t_step, h->t_step_used, st)) return rc;
+  if (jacobi_resident && h->n_chunks > 1) {
+    // Pipelined step.  hi: pre(0) .. pre(n-1), post(0) .. post(n-1);  lo: solve(0) ..
+    // solve(n-1);  solve(c) waits for pre(c), post(c) for solve(c).  The solves keep
+    // every SM busy back to back; the HVAC kernels of the other shares run in the SM
+    // slots that free up (high stream priority), instead of serialising before and
+    // after one monolithic solve.
+    const int n = h->n_chunks;
+    auto range = [&](int c) {
+      p.b_begin = (int)((int64_t)p.B * c / n);
+      p.b_end = (int)((int64_t)p.B * (c + 1) / n);
+    };
+    CUDA_TRY(h, cudaEventRecord(h->ev_fork, st));
+    CUDA_TRY(h, cudaStreamWaitEvent(h->s_hi, h->ev_fork, 0));
+    p.build_hdr = 1;
+    for (int c = 0; c < n; ++c) {
+      range(c);
+      if (int rc = launch_pre(h, h->s_hi)) return rc;
+      CUDA_TRY(h, cudaEventRecord(h->ev_pre[c], h->s_hi));
+    }
+    for (int c = 0; c < n; ++c) {
+      range(c);
+      CUDA_TRY(h, cudaStreamWaitEvent(h->s_lo, h->ev_pre[c], 0));
+      if (int rc = run_resident(h, h->s_lo, false)) return rc;
+      CUDA_TRY(h, cudaEventRecord(h->ev_solve[c], h->s_lo));
+    }
+    for (int c = 0; c < n; ++c) {
+      range(c);
+      CUDA_TRY(h, cudaStreamWaitEvent(h->s_hi, h->ev_solve[c], 0));
+      if (int rc = launch_post(h, h->s_hi, 0)) return rc;
+    }
+    CUDA_TRY(h, cudaEventRecord(h->ev_join, h->s_hi));
+    CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));
+    p.b_begin = 0; p.b_end = p.B; p.build_hdr = 0;
+  } else {
+    p.build_hdr = jacobi_resident ? 1 : 0;
+    if (int rc = launch_pre(h, st)) return rc;
+    p.build_hdr = 0;
     if (h->path == SBX_PATH_RESIDENT) {
-      if (int rc = run_resident(h, st)) return rc;      // solve + zone sums, one launch
+      if (int rc = run_resident(h, st, false)) return rc;      // solve + zone sums, one launch
     } else {
       if (int rc = run_stream_sweeps(h, st)) return rc;
       if (p.conv_perm) {
@@ -376,6 +467,7 @@ int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_
     }
     if (int rc = launch_post(h, st, 0)) return rc;
   }
+  if (int rc = timing_record(h, h->t_step, h->t_step_used, st)) return rc;
   p.conv_perm = nullptr;
   h->conv_pending = 0;
   // host mirror of Thermostat._previous_timestamp (thermostat.py:147) and of the
@@ -486,6 +578,7 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.zone_ndiff, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.obs_zone_order, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.desc_packed, uint16_t, (size_t)c.n_plans * p.geom.desc_stride);
+  ALLOC(p.desc_spk, uint16_t, h->path == SBX_PATH_STREAMING ? (size_t)c.n_plans * N : 1);
   ALLOC(p.qlist, uint16_t, (size_t)c.n_plans * p.geom.list_stride);
   ALLOC(p.n_fast, int32_t, (size_t)c.n_plans * 4);
   ALLOC(p.hdr, unsigned char, B * header_bytes((int)Z));
@@ -556,6 +649,16 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
     if (e == cudaSuccess) e = cudaMemcpy(h->d_obs_var, c.obs_variance, sizeof(c.obs_variance), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaMemcpy(h->d_hist_bins, c.hist_bins, sizeof(c.hist_bins), cudaMemcpyHostToDevice);
     if (e == cudaSuccess) e = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
+    int prio_lo = 0, prio_hi = 0;
+    if (e == cudaSuccess) e = cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->s_hi, cudaStreamNonBlocking, prio_hi);
+    if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->s_lo, cudaStreamNonBlocking, prio_lo);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming);
+    for (int i = 0; i < SBX_MAX_CHUNKS && e == cudaSuccess; ++i) {
+      e = cudaEventCreateWithFlags(&h->ev_pre[i], cudaEventDisableTiming);
+      if (e == cudaSuccess) e = cudaEventCreateWithFlags(&h->ev_solve[i], cudaEventDisableTiming);
+    }
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_action, sizeof(float) * B * (c.n_actions > 0 ? c.n_actions : 1));
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_obs, sizeof(float) * B * h->D);
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_reward, sizeof(float) * B);
@@ -564,6 +667,11 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
     if (e == cudaSuccess) e = cudaMallocHost(&h->h_n_active, sizeof(int32_t));
     if (e != cudaSuccess) { fail(h, SBX_E_CUDA, "host-side setup failed: %s", cudaGetErrorString(e)); return bail(SBX_E_CUDA); }
   }
+  // One launch per kernel by default: measured on B200 (32768 x 64x96), pipelining the
+  // step over 2 / 4 / 8 shares of the batch (SBX_OPT_PIPELINE_CHUNKS) is 3 / 7 / 14 % slower
+  // than the monolithic step -- the cross-stream event hand-offs cost more than the
+  // exposed HVAC kernels they hide.  The option stays for callers with other shapes.
+  h->n_chunks = 1;
   h->h_comfort = new (std::nothrow) uint8_t[T]();
   if (!h->h_comfort) { fail(h, SBX_E_NOMEM, "out of host memory"); return bail(SBX_E_NOMEM); }
   *out = h;
@@ -580,6 +688,16 @@ int sbx_destroy(sbx_handle h) {
   cudaFreeHost(h->h_action); cudaFreeHost(h->h_obs); cudaFreeHost(h->h_reward);
   cudaFreeHost(h->h_step_type); cudaFreeHost(h->h_discount); cudaFreeHost(h->h_n_active);
   if (h->stream) cudaStreamDestroy(h->stream);
+  if (h->s_hi) cudaStreamDestroy(h->s_hi);
+  if (h->s_lo) cudaStreamDestroy(h->s_lo);
+  if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+  if (h->ev_join) cudaEventDestroy(h->ev_join);
+  for (int i = 0; i < SBX_MAX_CHUNKS; ++i) {
+    if (h->ev_pre[i]) cudaEventDestroy(h->ev_pre[i]);
+    if (h->ev_solve[i]) cudaEventDestroy(h->ev_solve[i]);
+  }
+  for (cudaEvent_t e : h->t_step) cudaEventDestroy(e);
+  for (cudaEvent_t e : h->t_solve) cudaEventDestroy(e);
   delete[] h->h_comfort;
   delete h;
   return SBX_OK;
@@ -828,8 +946,13 @@ int sbx_fd_step(sbx_handle h, const double* ambient, const double* convection) {
   p.time_index = 0;
   p.action = nullptr; p.obs = nullptr; p.reward = nullptr; p.step_type = nullptr; p.discount_out = nullptr;
   int rc;
-  if (h->path == SBX_PATH_RESIDENT) rc = run_resident(h, h->stream);
-  else rc = run_stream_sweeps(h, h->stream);
+  p.b_begin = 0; p.b_end = p.B; p.build_hdr = 0;
+  if (h->path == SBX_PATH_RESIDENT) {
+    rc = h->cfg.solver == SBX_SOLVER_TF_JACOBI ? prepare_plans(h, h->stream) : SBX_OK;
+    if (!rc) rc = run_resident(h, h->stream, true);
+  } else {
+    rc = run_stream_sweeps(h, h->stream);
+  }
   p.fd_only = 0;
   if (rc) return rc;
   CUDA_TRY(h, cudaStreamSynchronize(h->stream));
@@ -845,6 +968,51 @@ int sbx_host_alloc(size_t bytes, void** out) {
 
 int sbx_host_free(void* p) {
   if (p) cudaFreeHost(p);
+  return SBX_OK;
+}
+
+int sbx_set_option(sbx_handle h, int option, int64_t value) {
+  if (!h) return fail(h, SBX_E_INVALID, "null handle");
+  switch (option) {
+    case SBX_OPT_PIPELINE_CHUNKS:
+      if (value < 1 || value > SBX_MAX_CHUNKS || value > h->cfg.n_envs)
+        return fail(h, SBX_E_INVALID, "SBX_OPT_PIPELINE_CHUNKS must be in [1, min(%d, n_envs)]", SBX_MAX_CHUNKS);
+      if (h->path != SBX_PATH_RESIDENT || h->cfg.solver != SBX_SOLVER_TF_JACOBI) value = 1;
+      h->n_chunks = (int)value;
+      return SBX_OK;
+    default:
+      return fail(h, SBX_E_INVALID, "unknown option %d", option);
+  }
+}
+
+int sbx_timing_begin(sbx_handle h) {
+  if (!h) return fail(h, SBX_E_INVALID, "null handle");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  h->t_step_used = h->t_solve_used = 0;
+  h->timing_on = 1;
+  return SBX_OK;
+}
+
+int sbx_timing_end(sbx_handle h, sbx_timing* out) {
+  if (!h || !out) return fail(h, SBX_E_INVALID, "null argument");
+  CUDA_TRY(h, cudaSetDevice(h->device));
+  CUDA_TRY(h, cudaDeviceSynchronize());
+  h->timing_on = 0;
+  memset(out, 0, sizeof(*out));
+  auto sum = [&](const std::vector<cudaEvent_t>& pool, size_t used, double* ms, int64_t* n) -> int {
+    for (size_t i = 0; i + 1 < used; i += 2) {
+      float t = 0.f;
+      CUDA_TRY(h, cudaEventElapsedTime(&t, pool[i], pool[i + 1]));
+      *ms += (double)t;
+      ++*n;
+    }
+    return SBX_OK;
+  };
+  if (int rc = sum(h->t_step, h->t_step_used, &out->step_ms, &out->n_steps)) return rc;
+  if (int rc = sum(h->t_solve, h->t_solve_used, &out->solve_ms, &out->n_solve_launches)) return rc;
+  out->n_chunks = h->n_chunks;
+  h->t_step_used = h->t_solve_used = 0;
   return SBX_OK;
 }
 

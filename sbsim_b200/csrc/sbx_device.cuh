@@ -89,6 +89,7 @@ struct Params {
   const int32_t* zone_ndiff; // [P,Z]
   const int32_t* obs_zone_order;  // [P,Z]
   uint16_t* desc_packed;     // [P,H,W] combo index | diffuser | zone (k_prepare_plan)
+  uint16_t* desc_spk;        // [P,H,W] the same packing at the natural pitch W (streaming path)
   uint16_t* qlist;           // [P,H*W/V] fast vectors from the front, slow from the back
   int32_t* n_fast;           // [P,4] sizes of the FAST / MEDIUM / EXT / SLOW vector lists
   uint32_t* rlist;           // [P, rl_cap] zone-sum list (k_prepare_reduce)
@@ -147,6 +148,8 @@ struct Params {
   const double* fd_ambient;     // [B]
   const double* fd_convection;  // [B]
   // per call
+  int b_begin, b_end;        // buildings [b_begin, b_end) are this launch's share of the batch
+  int build_hdr;             // k_pre also builds the resident solve header of its buildings
   int time_index;            // s: this step simulates [t_s, t_s + dt)
   int step_count;
   int episode_steps;
@@ -324,6 +327,53 @@ __device__ __forceinline__ float cv_update_fast(const FastCoef& f, float t_jp, f
   return div_rn(num, f.den, f.rden);
 }
 
+// ---------------------------------------------------------------------------
+// Packed fp32 pairs (sm_100 FMUL2 / FADD2 / FFMA2): one instruction issues two
+// IEEE round-to-nearest fp32 operations, element by element exactly like the scalar
+// instruction.  The resident kernel is issue-bound, so the FAST path (uniform
+// coefficients) runs its arithmetic on pairs of neighbouring CVs.
+// ---------------------------------------------------------------------------
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pack2(float lo, float hi) {
+  f32x2 r;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+  return r;
+}
+__device__ __forceinline__ void unpack2(f32x2 v, float& lo, float& hi) {
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ f32x2 mul2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) {
+  f32x2 r;
+  asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b));
+  return r;
+}
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) {
+  f32x2 r;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+  return r;
+}
+// div_rn on pairs; nb = -b (negation is exact, so fma(q, -b, a) == fma(-q, b, a))
+__device__ __forceinline__ f32x2 div_rn2(f32x2 a, f32x2 nb, f32x2 y) {
+  f32x2 q = mul2(a, y);
+  f32x2 r = fma2(q, nb, a);
+  q = fma2(r, y, q);
+  r = fma2(q, nb, a);
+  return fma2(r, y, q);
+}
+struct FastCoef2 {
+  f32x2 kq, vz, nden, rden, cm, ndt, rdt;
+};
+
 // Zone / grid sums are accumulated as integers: each temperature enters as
 // round((T - T_ref) * 2^16), T_ref a per-building reference (the ambient
 // temperature in the resident kernel, 0 elsewhere).  For fp32 temperatures >= 128 K
@@ -356,9 +406,13 @@ __device__ __forceinline__ float warp_max(float v) {
 }
 
 // ---------------------------------------------------------------------------
-// HVAC / observation / reward: executed by ONE WARP per building, lanes over
-// zones for the per-zone algebra, lane 0 for the sequential device sums (the
-// reference accumulates zone by zone in dict order, simulator_flexible_floor_plan.py:165-183).
+// HVAC / observation / reward: executed by a GROUP of G lanes per building (G = 32:
+// one warp per building; G = 8: four buildings per warp, for plans with few zones --
+// these kernels are issue-bound and a warp instruction costs the same with 8 or 32
+// useful lanes).  Lanes of the group stride over zones for the per-zone algebra,
+// lane 0 of the group does the sequential device sums (the reference accumulates zone
+// by zone in dict order, simulator_flexible_floor_plan.py:165-183).  `lane` is the lane
+// index INSIDE the group, `amask` the warp's lanes that own a building (whole groups).
 // `sh` is per-building scratch in shared memory: 3*Z + 64 doubles.
 // ---------------------------------------------------------------------------
 
@@ -383,7 +437,8 @@ __device__ inline double supply_air(double mixed, double heat_sp, double cool_sp
 // setup_step_sim + set_action + the VAV/AHU/boiler part of execute_step_sim.
 // Everything here depends only on PRE-step temperatures (Q4/Q5 of SURVEY.md
 // Appendix B), so it runs before the diffusion solve.
-__device__ inline PreOut hvac_pre(const Params& p, int b, int plan, int lane,
+template <int G>
+__device__ inline PreOut hvac_pre(const Params& p, int b, int plan, int lane, unsigned amask,
                                   const float* zone_mean /*[Z] pre-step*/, float global_mean,
                                   double* sh /*3*Z*/) {
   const int Z = p.Z;
@@ -416,7 +471,7 @@ __device__ inline PreOut hvac_pre(const Params& p, int b, int plan, int lane,
   double* sh_flow = sh;
   double* sh_reheat = sh + Z;
   double* sh_zs = sh + 2 * Z;
-  for (int zi = lane; zi < Z; zi += 32) {
+  for (int zi = lane; zi < Z; zi += G) {
     double flow = 0, reheat = 0, zs = 0;
     if (ncv[zi] > 0) {
       const double zt = (double)zone_mean[zi];
@@ -464,7 +519,7 @@ __device__ inline PreOut hvac_pre(const Params& p, int b, int plan, int lane,
     sh_reheat[zi] = reheat;
     p.pre_zone_mean[(size_t)b * Z + zi] = zone_mean[zi];
   }
-  __syncwarp();
+  __syncwarp(amask);
   PreOut o;
   o.supply_air = sup;
   o.ahu_heat_sp = heat_sp;
@@ -498,12 +553,12 @@ __device__ inline PreOut hvac_pre(const Params& p, int b, int plan, int lane,
     dg[SBX_DIAG_RETURN_WATER] = o.return_water;
   }
   // broadcast lane 0's sums
-  o.ahu_flow = __shfl_sync(0xffffffffu, o.ahu_flow, 0);
-  o.boiler_flow = __shfl_sync(0xffffffffu, o.boiler_flow, 0);
-  o.return_water = __shfl_sync(0xffffffffu, o.return_water, 0);
-  o.ahu_count = __shfl_sync(0xffffffffu, o.ahu_count, 0);
-  o.boiler_count = __shfl_sync(0xffffffffu, o.boiler_count, 0);
-  __syncwarp();
+  o.ahu_flow = __shfl_sync(amask, o.ahu_flow, 0, G);
+  o.boiler_flow = __shfl_sync(amask, o.boiler_flow, 0, G);
+  o.return_water = __shfl_sync(amask, o.return_water, 0, G);
+  o.ahu_count = __shfl_sync(amask, o.ahu_count, 0, G);
+  o.boiler_count = __shfl_sync(amask, o.boiler_count, 0, G);
+  __syncwarp(amask);
   return o;
 }
 
@@ -526,7 +581,8 @@ __device__ inline float normalize(const Params& p, int field, double native) {
 // Observation pack + reward.  `post_zone_mean` / `post_global_mean` are the
 // fresh (post-solve) means; `is_reset` selects the restart TimeStep of
 // Environment._reset (environment.py:1165-1212).
-__device__ inline void hvac_post(const Params& p, int b, int plan, int lane, bool is_reset,
+template <int G>
+__device__ inline void hvac_post(const Params& p, int b, int plan, int lane, unsigned amask, bool is_reset,
                                  const float* pre_zone_mean, const float* post_zone_mean,
                                  float post_global_mean, const Carry& cy, double* sh /*3*Z*/) {
   const int Z = p.Z;
@@ -585,7 +641,7 @@ __device__ inline void hvac_post(const Params& p, int b, int plan, int lane, boo
   if (obs) {
     if (p.obs_mode == SBX_OBS_RAW) {
       const int32_t* order = p.obs_zone_order + (size_t)plan * Z;
-      for (int slot = lane; slot < Z; slot += 32) {
+      for (int slot = lane; slot < Z; slot += G) {
         const int zi = order[slot];
         float v0 = 0.f, v1 = 0.f, v2 = 0.f;
         if (zi >= 0 && ncv[zi] > 0) {
@@ -610,14 +666,14 @@ __device__ inline void hvac_post(const Params& p, int b, int plan, int lane, boo
       // Lanes cooperate per measurement through shared counters.
       float* cnt = reinterpret_cast<float*>(sh + 3 * Z);  // 64 doubles = room for 3*SBX_MAX_HIST_BINS floats
       const int total_bins = p.n_hist_bins[0] + p.n_hist_bins[1] + p.n_hist_bins[2];
-      for (int i = lane; i < total_bins; i += 32) cnt[i] = 0.f;
-      __syncwarp();
+      for (int i = lane; i < total_bins; i += G) cnt[i] = 0.f;
+      __syncwarp(amask);
       int base = 0;
       float nz = 0.f;
       for (int f = 0; f < 3; ++f) {
         const int nb = p.n_hist_bins[f];
         const double* bins = p.hist_bins + f * SBX_MAX_HIST_BINS;
-        for (int zi = lane; zi < Z; zi += 32) {
+        for (int zi = lane; zi < Z; zi += G) {
           if (ncv[zi] <= 0) continue;
           double native;
           if (f == 0) {
@@ -637,11 +693,11 @@ __device__ inline void hvac_post(const Params& p, int b, int plan, int lane, boo
         }
         base += nb;
       }
-      __syncwarp();
+      __syncwarp(amask);
 #pragma unroll
-      for (int o = 16; o > 0; o >>= 1) nz += __shfl_xor_sync(0xffffffffu, nz, o);
-      for (int i = lane; i < total_bins; i += 32) obs[12 + i] = fdiv(cnt[i], nz);
-      __syncwarp();
+      for (int o = G / 2; o > 0; o >>= 1) nz += __shfl_xor_sync(amask, nz, o);
+      for (int i = lane; i < total_bins; i += G) obs[12 + i] = fdiv(cnt[i], nz);
+      __syncwarp(amask);
       n_hist_total = total_bins;
     }
     if (lane == 0) {
@@ -668,7 +724,7 @@ __device__ inline void hvac_post(const Params& p, int b, int plan, int lane, boo
   const double w_cool = f32r(comfort1 ? p.comfort_cool : p.eco_cool);
   const double dts = (double)p.dt;
   double prod = 0.0, occ_sum = 0.0;
-  for (int zi = lane; zi < Z; zi += 32) {
+  for (int zi = lane; zi < Z; zi += G) {
     if (ncv[zi] <= 0) continue;
     const double occ = f32r(p.occ_reward[(size_t)s1 * p.n_occ_zones + (p.n_occ_zones == 1 ? 0 : zi)]);
     const double t = (double)post_zone_mean[zi];
@@ -681,9 +737,9 @@ __device__ inline void hvac_post(const Params& p, int b, int plan, int lane, boo
     occ_sum += occ;
   }
 #pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    prod += __shfl_xor_sync(0xffffffffu, prod, o);
-    occ_sum += __shfl_xor_sync(0xffffffffu, occ_sum, o);
+  for (int o = G / 2; o > 0; o >>= 1) {
+    prod += __shfl_xor_sync(amask, prod, o);
+    occ_sum += __shfl_xor_sync(amask, occ_sum, o);
   }
   if (lane == 0) {
     // RewardInfo (simulator_flexible_floor_plan.py:238-283), each field -> proto float

@@ -236,11 +236,8 @@ __device__ __forceinline__ uint32_t repack_desc(uint32_t d) {
 constexpr uint32_t kFastDesc = SBX_CV_INTERIOR | (0u << SBX_DESC_MATERIAL_SHIFT);  // interior, air, no diffuser
 
 // Warp per building: coefficient table + per-zone heat + scalars -> hdr[b].
-__global__ void __launch_bounds__(128) k_build_header(const Params p) {
-  const int wpb = blockDim.x / 32;
-  const int b = blockIdx.x * wpb + (threadIdx.x >> 5);
-  const int lane = threadIdx.x & 31;
-  if (b >= p.B) return;
+template <int G>
+__device__ __forceinline__ void build_header(const Params& p, int b, int lane, unsigned amask) {
   const int Z = p.Z;
   const int plan = p.n_plans == 1 ? 0 : b;
   unsigned char* h8 = p.hdr + (size_t)b * header_bytes(Z);
@@ -249,8 +246,8 @@ __global__ void __launch_bounds__(128) k_build_header(const Params p) {
   float* scal = qcv + header_q_slots(Z);
   const float t_inf = (float)env_ambient(p, b, p.time_index);   // tf_simulator.py:785
   const float h = (float)env_convection(p, b);
-  build_combo_table(tab, p, plan, b, h, t_inf, lane, 32);
-  for (int zi = lane; zi < (int)header_q_slots(Z); zi += 32)
+  build_combo_table(tab, p, plan, b, h, t_inf, lane, G);
+  for (int zi = lane; zi < (int)header_q_slots(Z); zi += G)
     qcv[zi] = zi < Z ? p.qcv[(size_t)b * Z + zi] : 0.f;
   if (lane == 0) {
     const int n_f = p.n_fast[plan * 4 + 0], n_m = p.n_fast[plan * 4 + 1], n_e = p.n_fast[plan * 4 + 2];
@@ -262,11 +259,17 @@ __global__ void __launch_bounds__(128) k_build_header(const Params p) {
     scal[5] = __int_as_float(p.rl_chunks[plan]);
     scal[6] = scal[7] = 0.f;
   }
-  __syncwarp();
+  __syncwarp(amask);
   if (lane < kNumMaterials) {
     const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + lane];
     reinterpret_cast<float4*>(scal + 8)[lane] = make_float4(c.k1, c.cm, c.den, c.rden);
   }
+}
+__global__ void __launch_bounds__(128) k_build_header(const Params p) {
+  const int wpb = blockDim.x / 32;
+  const int b = p.b_begin + blockIdx.x * wpb + (threadIdx.x >> 5);
+  if (b >= p.b_end) return;
+  build_header<32>(p, b, threadIdx.x & 31, 0xffffffffu);
 }
 
 // Once per uploaded plan: repack the descriptors and sort the plan's vectors
@@ -437,6 +440,7 @@ struct SweepCtx {
   const float4* mtab;
   const float* qcv;
   FastCoef fc;
+  FastCoef2 fc2;
   AreaCoef az;
   float cm_fast, dt, rdt, t_inf;
   int n_fast, n_fm, n_fme, n_items, H, P, Pq, wq, Z;
@@ -456,6 +460,66 @@ __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, fl
     float c[V], o[V];
     load_f<V>(in + base, c);
     if (u < s.n_fast) {
+      if constexpr (V == 4) {
+        // packed pairs (e0,e1), (e2,e3); same operations, same order as cv_update_fast
+        const float4 up4 = *reinterpret_cast<const float4*>(in + base - W);
+        const float4 dn4 = *reinterpret_cast<const float4*>(in + base + W);
+        const float left = in[base - 1];
+        const float right = in[base + V];
+        const FastCoef2& f = s.fc2;
+        const f32x2 c01 = pack2(c[0], c[1]), c23 = pack2(c[2], c[3]);
+        f32x2 n3a, n3b;
+        if constexpr (FIRST) {
+          n3a = div_rn2(mul2(f.cm, c01), f.ndt, f.rdt);
+          n3b = div_rn2(mul2(f.cm, c23), f.ndt, f.rdt);
+          float4 st4;
+          unpack2(n3a, st4.x, st4.y);
+          unpack2(n3b, st4.z, st4.w);
+          *reinterpret_cast<float4*>(n3p + base) = st4;
+        } else {
+          const float4 n4 = *reinterpret_cast<const float4*>(n3p + base);
+          n3a = pack2(n4.x, n4.y);
+          n3b = pack2(n4.z, n4.w);
+        }
+        // horizontal: kq*T(j+1) + kq*T(j-1); every product is used by two CVs
+        float m0, m1, m2, m3;
+        unpack2(mul2(f.kq, c01), m0, m1);
+        unpack2(mul2(f.kq, c23), m2, m3);
+        const float ml = mul(s.fc.kq, left), mr = mul(s.fc.kq, right);
+        f32x2 n1a = pack2(add(m1, ml), add(m2, m0));
+        f32x2 n1b = pack2(add(m3, m1), add(mr, m2));
+        n1a = mul2(f.vz, n1a);
+        n1b = mul2(f.vz, n1b);
+        // vertical: kq*T(i+1) + kq*T(i-1).  ptxas contracts add.rn.f32x2 of a
+        // mul.rn.f32x2 result into FFMA2 (even with --fmad=false; it leaves scalar
+        // add.rn alone), which would drop a rounding: every sum that consumes a packed
+        // PRODUCT is therefore taken with scalar adds on the halves.
+        float a0, a1, a2, a3, b0, b1, b2, b3;
+        unpack2(mul2(f.kq, pack2(dn4.x, dn4.y)), a0, a1);
+        unpack2(mul2(f.kq, pack2(dn4.z, dn4.w)), a2, a3);
+        unpack2(mul2(f.kq, pack2(up4.x, up4.y)), b0, b1);
+        unpack2(mul2(f.kq, pack2(up4.z, up4.w)), b2, b3);
+        const f32x2 n2a = mul2(f.vz, pack2(add(a0, b0), add(a1, b1)));
+        const f32x2 n2b = mul2(f.vz, pack2(add(a2, b2), add(a3, b3)));
+        float p0, p1, p2, p3, q0, q1, q2, q3;
+        unpack2(n1a, p0, p1);
+        unpack2(n1b, p2, p3);
+        unpack2(n2a, q0, q1);
+        unpack2(n2b, q2, q3);
+        const f32x2 suma = pack2(add(p0, q0), add(p1, q1));
+        const f32x2 sumb = pack2(add(p2, q2), add(p3, q3));
+        const f32x2 oa = div_rn2(add2(suma, n3a), f.nden, f.rden);
+        const f32x2 ob = div_rn2(add2(sumb, n3b), f.nden, f.rden);
+        unpack2(oa, o[0], o[1]);
+        unpack2(ob, o[2], o[3]);
+        float d0, d1, d2, d3;
+        unpack2(sub2(oa, c01), d0, d1);
+        unpack2(sub2(ob, c23), d2, d3);
+        lmax = fmaxf(fmaxf(lmax, fabsf(d0)), fabsf(d1));
+        lmax = fmaxf(fmaxf(lmax, fabsf(d2)), fabsf(d3));
+        store_f<V>(out + base, o);
+        continue;
+      } else {
       float up[V], dn[V], n3v[V];
       load_f<V>(in + base - W, up);
       load_f<V>(in + base + W, dn);
@@ -473,6 +537,7 @@ __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, fl
         const float t_jm = e == 0 ? left : c[e - 1];
         const float t_jp = e == V - 1 ? right : c[e + 1];
         o[e] = cv_update_fast(s.fc, t_jp, t_jm, up[e], dn[e], n3v[e]);
+      }
       }
     } else if (u < s.n_fm) {
       // interior class, any material, maybe a diffuser: k1 = k2 = k3 = k4 = k/dx,
@@ -570,7 +635,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
 #ifdef SBX_PROFILE_PHASES
   long long phase_t0__ = clock64();
 #endif
-  const int b = blockIdx.x;
+  const int b = p.b_begin + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   constexpr int NT = kResidentThreads, NW = NT / 32;
   const int H = p.H, W = p.W, Z = p.Z;
@@ -662,6 +727,10 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   sc.az.full = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
   sc.az.half = tab[SBX_CV_CORNER_TL * kNumMaterials].vz;
   sc.dt = p.dt; sc.rdt = __frcp_rn(p.dt); sc.t_inf = t_inf;
+  sc.fc2.kq = pack2(sc.fc.kq, sc.fc.kq); sc.fc2.vz = pack2(sc.fc.vz, sc.fc.vz);
+  sc.fc2.nden = pack2(-sc.fc.den, -sc.fc.den); sc.fc2.rden = pack2(sc.fc.rden, sc.fc.rden);
+  sc.fc2.cm = pack2(sc.cm_fast, sc.cm_fast);
+  sc.fc2.ndt = pack2(-sc.dt, -sc.dt); sc.fc2.rdt = pack2(sc.rdt, sc.rdt);
   sc.n_items = n_items; sc.H = H; sc.P = P; sc.Pq = L.Pq; sc.wq = W / V; sc.Z = Z;
   sc.pq_magic = L.pq_magic;
 
@@ -987,7 +1056,18 @@ __device__ __forceinline__ void sweep_buffers(int cur, int k, int& in, int& out)
   out = (k & 1) ? s0 : s1;
 }
 
+// Once per uploaded plan (streaming path): descriptors repacked as combo index |
+// half-U | diffuser | half-V | zone (see repack_desc), natural pitch W.
+__global__ void k_pack_stream(const Params p) {
+  const size_t total = (size_t)p.n_plans * p.H * p.W;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (size_t)gridDim.x * blockDim.x)
+    p.desc_spk[i] = (uint16_t)repack_desc(p.desc[i]);
+}
+
 // One Jacobi sweep of every still-active building.  Sweep index k is 1-based.
+// Every class of CV runs the same instruction stream (cv_update_packed): warps that
+// mix interior / wall / boundary / exterior CVs do not diverge.
 template <int V>
 __global__ void __launch_bounds__(kStreamThreads) k_sweep(const Params p, const int k) {
   __shared__ Combo tab[kNumCombos];
@@ -1006,14 +1086,19 @@ __global__ void __launch_bounds__(kStreamThreads) k_sweep(const Params p, const 
   build_combo_table(tab, p, plan, b, h, t_inf, tid, kStreamThreads);
   for (int i = tid; i < Z; i += kStreamThreads) qcv[i] = p.qcv[(size_t)b * Z + i];
   __syncthreads();
+  AreaCoef az;
+  az.full = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
+  az.half = tab[SBX_CV_CORNER_TL * kNumMaterials].vz;
+  const float dt = p.dt, rdt = __frcp_rn(p.dt);
 
   const int cur = p.cur[b];
   int bi, bo;
   sweep_buffers(cur, k, bi, bo);
+  const bool first = k == 1;            // T_est is T_prev itself: one load serves both
   const float* __restrict__ tin = p.tbuf[bi] + (size_t)b * n_cv;
   const float* __restrict__ tprev = p.tbuf[cur] + (size_t)b * n_cv;
   float* __restrict__ tout = p.tbuf[bo] + (size_t)b * n_cv;
-  const uint16_t* __restrict__ dsc = p.desc + (size_t)plan * n_cv;
+  const uint16_t* __restrict__ dsc = p.desc_spk + (size_t)plan * n_cv;
 
   const int c0 = (tx * 32 + lane) * V;
   const int r0 = (ty * (kStreamThreads / 32) + warp) * kStreamRowsPerWarp;
@@ -1024,33 +1109,44 @@ __global__ void __launch_bounds__(kStreamThreads) k_sweep(const Params p, const 
     float up[V], c[V], dn[V];
     fill<V>(up, t_inf);
     fill<V>(c, t_inf);
+    int off = r0 * W + c0;              // < 2^31: one building's grid
     if (col_ok) {
-      if (r0 > 0) load_f<V>(tin + (size_t)(r0 - 1) * W + c0, up);
-      load_f<V>(tin + (size_t)r0 * W + c0, c);
+      if (r0 > 0) load_f<V>(tin + off - W, up);
+      load_f<V>(tin + off, c);
     }
-    for (int r = r0; r < r1; ++r) {
+    for (int r = r0; r < r1; ++r, off += W) {
       fill<V>(dn, t_inf);
-      if (col_ok && r + 1 < H) load_f<V>(tin + (size_t)(r + 1) * W + c0, dn);
+      if (col_ok && r + 1 < H) load_f<V>(tin + off + W, dn);
       // horizontal neighbours: shuffle inside the warp, global load at its ends
       float left = __shfl_up_sync(0xffffffffu, c[V - 1], 1);
       float right = __shfl_down_sync(0xffffffffu, c[0], 1);
       if (col_ok) {
-        if (lane == 0) left = c0 > 0 ? tin[(size_t)r * W + c0 - 1] : t_inf;
-        if (lane == 31 || c0 + V >= W) right = c0 + V < W ? tin[(size_t)r * W + c0 + V] : t_inf;
+        if (lane == 0) left = c0 > 0 ? tin[off - 1] : t_inf;
+        if (lane == 31 || c0 + V >= W) right = c0 + V < W ? tin[off + V] : t_inf;
         float tp[V], o[V];
         uint32_t d[V];
-        load_f<V>(tprev + (size_t)r * W + c0, tp);
-        load_d<V>(dsc + (size_t)r * W + c0, d);
+        load_d<V>(dsc + off, d);
+        if (first) {
+#pragma unroll
+          for (int e = 0; e < V; ++e) tp[e] = c[e];
+        } else {
+          load_f<V>(tprev + off, tp);
+        }
+        uint32_t any_q = 0;
+#pragma unroll
+        for (int e = 0; e < V; ++e) any_q |= d[e];
+        any_q &= SBX_DESC_DIFFUSER;
 #pragma unroll
         for (int e = 0; e < V; ++e) {
           const float t_jm = e == 0 ? left : c[e - 1];
           const float t_jp = e == V - 1 ? right : c[e + 1];
-          const float n3 = fdiv(mul(cv_cm(d[e], tab), tp[e]), p.dt);
-          const float qv = (d[e] & SBX_DESC_DIFFUSER) ? qcv[desc_zone(d[e])] : 0.f;
-          o[e] = cv_update(d[e], t_jp, t_jm, up[e], dn[e], n3, qv, t_inf, tab);
+          const float n3 = div_rn(mul(tab[d[e] & kPackIdxMask].cm, tp[e]), dt, rdt);   // :743-749
+          float qv = 0.f;
+          if (any_q) qv = (d[e] & SBX_DESC_DIFFUSER) ? qcv[d[e] >> SBX_DESC_ZONE_SHIFT] : 0.f;
+          o[e] = cv_update_packed(d[e], t_jp, t_jm, up[e], dn[e], n3, qv, t_inf, az, tab);
           lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));
         }
-        store_f<V>(tout + (size_t)r * W + c0, o);
+        store_f<V>(tout + off, o);
       }
 #pragma unroll
       for (int e = 0; e < V; ++e) { up[e] = c[e]; c[e] = dn[e]; }
@@ -1093,6 +1189,11 @@ __global__ void k_activate(const Params p) {
 }
 
 // Zone sums + grid total of building.temp (building.py:845-871, simulator.py:408).
+// A thread keeps the running integer sum of its column group (V CVs x 8 rows: almost
+// always one zone) in registers; the warp then merges equal zones with exact hardware
+// REDUX on 16-bit pieces and ONE lane per zone touches the CTA's shared bins, so the
+// kernel is a plain bandwidth-bound read of the field (64-bit shared-memory atomics
+// are CAS loops on this hardware: one per CV run made this kernel 10x slower).
 template <int V>
 __global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) {
   __shared__ long long bins[kMaxZones + 1];
@@ -1110,16 +1211,60 @@ __global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) 
   const uint16_t* __restrict__ dsc = p.desc + (size_t)plan * n_cv;
   const int c0 = (tx * 32 + lane) * V;
   const int r0 = (ty * (kStreamThreads / 32) + warp) * kStreamRowsPerWarp;
-  long long total = 0;
+  long long total = 0;                 // every CV: the grid mean
+  long long run = 0;                   // CVs of zone `zc` seen by this thread
+  int zc = SBX_ZONE_NONE;
   if (c0 < W && r0 < H) {
-    const int r1 = min(r0 + kStreamRowsPerWarp, H);
-    for (int r = r0; r < r1; ++r) {
-      float tv[V];
-      uint32_t d[V];
-      load_f<V>(t + (size_t)r * W + c0, tv);
-      load_d<V>(dsc + (size_t)r * W + c0, d);
-      zone_accumulate<V>(tv, d, bins, total);
+    float tv[kStreamRowsPerWarp][V];
+    uint32_t d[kStreamRowsPerWarp][V];
+#pragma unroll
+    for (int i = 0; i < kStreamRowsPerWarp; ++i) {       // all loads in flight first
+      if (r0 + i < H) {
+        load_f<V>(t + (size_t)(r0 + i) * W + c0, tv[i]);
+        load_d<V>(dsc + (size_t)(r0 + i) * W + c0, d[i]);
+      }
     }
+#pragma unroll
+    for (int i = 0; i < kStreamRowsPerWarp; ++i) {
+      if (r0 + i < H) {
+        const int z0 = desc_zone(d[i][0]);
+        bool uniform = true;
+        long long s = 0;
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          uniform = uniform && desc_zone(d[i][e]) == z0;
+          s += to_fix(tv[i][e]);
+        }
+        total += s;
+        if (uniform) {
+          if (z0 != zc) {
+            if (zc != SBX_ZONE_NONE && run != 0) fix_add(&bins[zc], run);
+            zc = z0;
+            run = 0;
+          }
+          run += s;
+        } else {                        // vector straddling a wall: per CV
+#pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const int z = desc_zone(d[i][e]);
+            if (z != SBX_ZONE_NONE) fix_add(&bins[z], to_fix(tv[i][e]));
+          }
+        }
+      }
+    }
+  }
+  // merge the lanes' (zone, sum) pairs: one REDUX triple and one atomic per distinct zone
+  unsigned todo = __ballot_sync(0xffffffffu, zc != SBX_ZONE_NONE && run != 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int z = __shfl_sync(0xffffffffu, zc, leader);
+    const bool mine = ((todo >> lane) & 1u) && zc == z;
+    const long long v = mine ? run : 0;
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xFFFF));
+    const unsigned mid = __reduce_add_sync(0xffffffffu, (unsigned)((v >> 16) & 0xFFFF));
+    const int hi = __reduce_add_sync(0xffffffffu, (int)(v >> 32));
+    if (lane == leader) fix_add(&bins[z], ((long long)hi << 32) + ((long long)mid << 16) + (long long)lo);
+    todo &= ~__ballot_sync(0xffffffffu, mine);
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
@@ -1136,20 +1281,22 @@ struct CarryStore {
   int32_t ahu_count, boiler_count;
 };
 
-// HVAC prologue, warp per building (streaming path).
+// HVAC prologue; G lanes per building (see sbx_device.cuh), 128 threads per CTA.
+template <int G>
 __global__ void __launch_bounds__(128) k_pre(const Params p, CarryStore* carry) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int wpb = blockDim.x / 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * wpb + warp;
-  if (b >= p.B) return;
+  const int group = threadIdx.x / G, lane = threadIdx.x % G;
+  const int b = p.b_begin + blockIdx.x * (blockDim.x / G) + group;
+  const unsigned amask = __ballot_sync(0xffffffffu, b < p.b_end);
+  if (b >= p.b_end) return;
   const int Z = p.Z;
-  double* scratch = reinterpret_cast<double*>(smem) + (size_t)warp * (3 * Z + 64 + Z);
+  double* scratch = reinterpret_cast<double*>(smem) + (size_t)group * (3 * Z + 64 + Z);
   float* zpre = reinterpret_cast<float*>(scratch + 3 * Z + 64);
   const int plan = p.n_plans == 1 ? 0 : b;
-  for (int zi = lane; zi < Z; zi += 32) zpre[zi] = p.zone_mean[(size_t)b * Z + zi];
-  __syncwarp();
-  PreOut o = hvac_pre(p, b, plan, lane, zpre, p.global_mean[b], scratch);
+  if (p.build_hdr) build_header<G>(p, b, lane, amask);   // reads only last step's state
+  for (int zi = lane; zi < Z; zi += G) zpre[zi] = p.zone_mean[(size_t)b * Z + zi];
+  __syncwarp(amask);
+  PreOut o = hvac_pre<G>(p, b, plan, lane, amask, zpre, p.global_mean[b], scratch);
   if (lane == 0) {
     CarryStore c;
     c.ahu_flow = o.ahu_flow; c.boiler_flow = o.boiler_flow; c.return_water = o.return_water;
@@ -1158,23 +1305,24 @@ __global__ void __launch_bounds__(128) k_pre(const Params p, CarryStore* carry) 
   }
 }
 
-// Means from zone sums, then observation + reward; warp per building.
+// Means from zone sums, then observation + reward; G lanes per building.
+template <int G>
 __global__ void __launch_bounds__(128) k_post(const Params p, const CarryStore* carry,
                                               const int is_reset) {
   extern __shared__ __align__(128) unsigned char smem[];
-  const int wpb = blockDim.x / 32;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * wpb + warp;
-  if (b >= p.B) return;
+  const int group = threadIdx.x / G, lane = threadIdx.x % G;
+  const int b = p.b_begin + blockIdx.x * (blockDim.x / G) + group;
+  const unsigned amask = __ballot_sync(0xffffffffu, b < p.b_end);
+  if (b >= p.b_end) return;
   const int Z = p.Z;
-  double* scratch = reinterpret_cast<double*>(smem) + (size_t)warp * (3 * Z + 64 + Z);
+  double* scratch = reinterpret_cast<double*>(smem) + (size_t)group * (3 * Z + 64 + Z);
   float* zpre = reinterpret_cast<float*>(scratch + 3 * Z + 64);
   float* zpost = zpre + Z;
   const int plan = p.n_plans == 1 ? 0 : b;
   const int32_t* ncv = p.zone_ncv + (size_t)plan * Z;
   const long long* zs = p.zone_sum + (size_t)b * (Z + 1);
   const double ref = (double)p.zone_ref[b];
-  for (int zi = lane; zi < Z; zi += 32) {
+  for (int zi = lane; zi < Z; zi += G) {
     const int n = ncv[zi];
     const float m = n > 0 ? (float)(ref + from_fix(zs[zi]) / (double)n) : 0.f;
     zpost[zi] = m;
@@ -1187,14 +1335,14 @@ __global__ void __launch_bounds__(128) k_post(const Params p, const CarryStore* 
   }
   const float gmean = (float)(ref + from_fix(zs[Z]) / (double)((size_t)p.H * p.W));
   if (lane == 0) p.global_mean[b] = gmean;
-  __syncwarp();
+  __syncwarp(amask);
   Carry cy = {0, 0, 0, 0, 0};
   if (!is_reset) {
     const CarryStore c = carry[b];
     cy.ahu_flow = c.ahu_flow; cy.boiler_flow = c.boiler_flow; cy.return_water = c.return_water;
     cy.ahu_count = c.ahu_count; cy.boiler_count = c.boiler_count;
   }
-  hvac_post(p, b, plan, lane, is_reset != 0, zpre, zpost, gmean, cy, scratch);
+  hvac_post<G>(p, b, plan, lane, amask, is_reset != 0, zpre, zpost, gmean, cy, scratch);
 }
 
 // Environment._reset: building.reset + hvac.reset (building.py:784-792,

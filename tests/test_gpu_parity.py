@@ -12,7 +12,7 @@ import pandas as pd
 import pytest
 
 import sbsim_b200 as sbx
-from sbsim_b200 import _lib, floorplan
+from sbsim_b200 import _lib, floorplan, workloads
 import scenarios as S
 from oracle import tf_jacobi
 
@@ -368,3 +368,36 @@ def test_gauss_seidel_env_matches_unmodified_reference_fixture():
     np.testing.assert_allclose(t64[0], g["final_temp"], rtol=1e-6)
   finally:
     env.close()
+
+
+def test_pipelined_step_equals_single_launch_step_and_timing():
+  """SBX_OPT_PIPELINE_CHUNKS: cutting the step into shares of the batch that overlap on
+  two streams must not change a single bit; sbx_timing_* reports every step / solve."""
+  B = 96
+  wl = workloads.randomized(B, seed=5, n_layouts=24)
+  envs = []
+  try:
+    for chunks in (1, 3):
+      env, _ = workloads.make_randomized_env(B, workload=wl, episode_steps=16, histogram=True)
+      env.handle.set_option(_lib.OPT_PIPELINE_CHUNKS, chunks)
+      envs.append(env)
+    rng = np.random.default_rng(1)
+    ts = [e.reset() for e in envs]
+    np.testing.assert_array_equal(ts[0].observation, ts[1].observation)
+    for e in envs:
+      e.handle.timing_begin()
+    for _ in range(6):
+      a = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+      ts = [e.step(a) for e in envs]
+      np.testing.assert_array_equal(ts[0].observation, ts[1].observation)
+      np.testing.assert_array_equal(ts[0].reward, ts[1].reward)
+    t = [e.handle.timing_end() for e in envs]
+    assert [x.n_steps for x in t] == [6, 6]
+    assert [x.n_solve_launches for x in t] == [6, 18]
+    assert [x.n_chunks for x in t] == [1, 3]
+    assert all(0.0 < x.solve_ms <= x.step_ms * 1.5 for x in t)
+    np.testing.assert_array_equal(envs[0].handle.download("temp", (B, 64, 96)),
+                                  envs[1].handle.download("temp", (B, 64, 96)))
+  finally:
+    for e in envs:
+      e.close()

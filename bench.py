@@ -58,6 +58,8 @@ def parse_args():
   ap.add_argument("--convergence-threshold", type=float, default=0.1,
                   help="experiments only; BASELINE uses 0.1 K (sim_config.gin:161)")
   ap.add_argument("--iteration-limit", type=int, default=100)
+  ap.add_argument("--prefetch", type=int, default=-1,
+                  help="SBX_OPT_L2_PREFETCH_DISTANCE override (-1 = the library's choice)")
   ap.add_argument("--chunks", type=int, default=0,
                   help="SBX_OPT_PIPELINE_CHUNKS override (0 = the library's choice)")
   return ap.parse_args()
@@ -172,9 +174,11 @@ def run_sbx(args):
     dist.init_process_group("nccl", device_id=dev)
 
   env, wl, cfg_desc = build_env(args, rank, local_rank)
+  from sbsim_b200 import _lib
   if args.chunks > 0:
-    from sbsim_b200 import _lib
     env.handle.set_option(_lib.OPT_PIPELINE_CHUNKS, args.chunks)
+  if args.prefetch >= 0:
+    env.handle.set_option(_lib.OPT_L2_PREFETCH_DISTANCE, args.prefetch)
   B = env.batch_size
   D = env.observation_spec().shape[0]
   A = env.action_spec().shape[0]

@@ -21,8 +21,8 @@ for i in range(K):
   env.step_device(act[5 + i], obs, rew, st, dis)
 torch.cuda.synchronize()
 cyc = env.handle.download("phase_cycles", (8,)).astype(np.float64)
-names = ["prologue (consts, table)", "wait TMA load", "sweep 1 (+n3)", "sweeps 2..n", "reduce (+gather)",
-         "combine", "drain TMA store"]
+names = ["prologue (TMA issued)", "wait TMA load", "sweep 1 (+n3)", "sweeps 2..n", "store issue (+gather)",
+         "zone sums (warp 0)", "barrier after sums"]
 tot = cyc[:7].sum()
 for n, c in zip(names, cyc):
   print(f"{n:28s} {c / (B * K):9.0f} cycles/CTA  {100 * c / tot:5.1f}%")

@@ -18,6 +18,7 @@ LIB_PATH = os.environ.get("SBX_LIB") or os.path.join(_HERE, "lib", "libsbx.so")
 
 ABI_VERSION = 3
 OPT_PIPELINE_CHUNKS = 1
+OPT_L2_PREFETCH_DISTANCE = 2
 OK = 0
 MAX_ACTIONS = 3
 MAX_HIST_BINS = 32

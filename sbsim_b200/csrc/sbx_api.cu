@@ -672,6 +672,8 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   // than the monolithic step -- the cross-stream event hand-offs cost more than the
   // exposed HVAC kernels they hide.  The option stays for callers with other shapes.
   h->n_chunks = 1;
+  if (h->path == SBX_PATH_RESIDENT && c.solver == SBX_SOLVER_TF_JACOBI)
+    h->P.prefetch_dist = h->n_sms * (h->resident_ctas_per_sm > 0 ? h->resident_ctas_per_sm : 1);
   h->h_comfort = new (std::nothrow) uint8_t[T]();
   if (!h->h_comfort) { fail(h, SBX_E_NOMEM, "out of host memory"); return bail(SBX_E_NOMEM); }
   *out = h;
@@ -979,6 +981,10 @@ int sbx_set_option(sbx_handle h, int option, int64_t value) {
         return fail(h, SBX_E_INVALID, "SBX_OPT_PIPELINE_CHUNKS must be in [1, min(%d, n_envs)]", SBX_MAX_CHUNKS);
       if (h->path != SBX_PATH_RESIDENT || h->cfg.solver != SBX_SOLVER_TF_JACOBI) value = 1;
       h->n_chunks = (int)value;
+      return SBX_OK;
+    case SBX_OPT_L2_PREFETCH_DISTANCE:
+      if (value < 0 || value > h->cfg.n_envs) return fail(h, SBX_E_INVALID, "SBX_OPT_L2_PREFETCH_DISTANCE must be in [0, n_envs]");
+      h->P.prefetch_dist = (int)value;
       return SBX_OK;
     default:
       return fail(h, SBX_E_INVALID, "unknown option %d", option);

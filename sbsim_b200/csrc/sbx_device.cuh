@@ -150,6 +150,7 @@ struct Params {
   // per call
   int b_begin, b_end;        // buildings [b_begin, b_end) are this launch's share of the batch
   int build_hdr;             // k_pre also builds the resident solve header of its buildings
+  int prefetch_dist;         // resident solve: CTA b prefetches building b + prefetch_dist into L2 (0 = off)
   int time_index;            // s: this step simulates [t_s, t_s + dt)
   int step_count;
   int episode_steps;
@@ -293,6 +294,32 @@ __device__ __forceinline__ float cv_update_packed(uint32_t d, float t_jp, float 
   const float num = add(add(add(n1, n2), n3), q);       // :752-754
   const float t = div_rn(num, h.z, h.w);                // :843
   return idx < kNumMaterials ? t_inf : t;               // :847-849 (class EXTERIOR == 0)
+}
+
+// The same update in two halves (streaming path): the numerator without the heat input
+// (n1 + n2) + n3, then the division and the exterior override.
+__device__ __forceinline__ float cv_numerator_packed(uint32_t d, float t_jp, float t_jm, float t_im,
+                                                     float t_ip, float n3, const AreaCoef& az,
+                                                     const Combo* tab) {
+  const int idx = (int)(d & kPackIdxMask);
+  const float4* c4 = reinterpret_cast<const float4*>(tab + idx);
+  const float4 k = c4[0];
+  const float2 h = *reinterpret_cast<const float2*>(&c4[1]);
+  const float vz = (d & kPackHalfV) ? az.half : az.full;
+  const float uz = (d & kPackHalfU) ? az.half : az.full;
+  float n1 = add(mul(k.x, t_jp), mul(k.y, t_jm));
+  n1 = add(n1, h.x);
+  n1 = mul(vz, n1);
+  float n2 = add(mul(k.z, t_ip), mul(k.w, t_im));
+  n2 = add(n2, h.y);
+  n2 = mul(uz, n2);
+  return add(add(n1, n2), n3);
+}
+__device__ __forceinline__ float cv_divide_packed(uint32_t d, float num, float t_inf, const Combo* tab) {
+  const int idx = (int)(d & kPackIdxMask);
+  const float2 dr = *reinterpret_cast<const float2*>(&tab[idx].den);
+  const float t = div_rn(num, dr.x, dr.y);
+  return idx < kNumMaterials ? t_inf : t;
 }
 
 // same update from a raw descriptor (streaming path)

@@ -134,6 +134,10 @@ __device__ __forceinline__ void tma_store_1d(void* gmem_dst, const void* smem_sr
                "r"(smem_u32(smem_src)), "r"(bytes)
                : "memory");
 }
+// warms L2 with data a LATER CTA will fetch (no shared-memory destination, no completion)
+__device__ __forceinline__ void l2_prefetch(const void* gmem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(gmem_src), "r"(bytes) : "memory");
+}
 __device__ __forceinline__ void tma_store_commit() {
   asm volatile("cp.async.bulk.commit_group;" ::: "memory");
 }
@@ -693,6 +697,18 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
       reinterpret_cast<uint32_t*>(smem + L.off_hdr)[i] = reinterpret_cast<const uint32_t*>(gH)[i];
   }
 
+  // The CTA that will take over this SM slot works on building b + (CTAs in flight):
+  // pull its inputs into L2 now, so its own bulk loads do not wait on HBM (+2 % measured).
+  if (p.prefetch_dist > 0 && tid == 32 && b + p.prefetch_dist < p.b_end) {
+    const int bn = b + p.prefetch_dist;
+    l2_prefetch(p.tbuf[0] + (size_t)bn * n_cv, (uint32_t)(n_cv * 4) & ~15u);
+    l2_prefetch(p.hdr + (size_t)bn * hdr_bytes, hdr_bytes & ~15u);
+    if (p.n_plans != 1) {
+      l2_prefetch(p.desc_packed + (size_t)bn * L.desc_stride, (uint32_t)(L.desc_stride * 2));
+      l2_prefetch(p.qlist + (size_t)bn * L.list_stride, (uint32_t)(L.list_stride * 2));
+    }
+  }
+
   // ---- stage 1: zero the zone bins while the copies are in flight ---------------
   for (int i = tid; i < (Z + 1) * (NW + 1); i += NT) bins[i] = 0;
   __syncthreads();
@@ -786,6 +802,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   last_lmax = warp_max(last_lmax);
   if (lane == 0) wmax[warp] = last_lmax;
   long long* wbins = bins + (size_t)(warp + 1) * (Z + 1);   // warp-private bins
+  SBX_PHASE(4);   // convection gather (if any), store issued
   if (!p.fd_only && n_chunks > 0) {
     // Zone sums from the zone-grouped list: a warp's 32 entries belong to one zone,
     // so the warp reduces its lanes' integers with exact hardware REDUX and the
@@ -824,8 +841,9 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
       fix_add(&bins[zs == SBX_ZONE_NONE ? Z : zs], (long long)to_fix32(in[idx], t_inf));
     }
   }
+  SBX_PHASE(5);   // zone / grid sums of this warp
   __syncthreads();
-  SBX_PHASE(4);   // convection gather (if any) + zone / grid sums
+  SBX_PHASE(6);   // waiting for the other warps' sums
   if (tid == 0) {
     md = 0.f;
 #pragma unroll
@@ -1069,7 +1087,7 @@ __global__ void k_pack_stream(const Params p) {
 // Every class of CV runs the same instruction stream (cv_update_packed): warps that
 // mix interior / wall / boundary / exterior CVs do not diverge.
 template <int V>
-__global__ void __launch_bounds__(kStreamThreads) k_sweep(const Params p, const int k) {
+__global__ void __launch_bounds__(kStreamThreads, 4) k_sweep(const Params p, const int k) {
   __shared__ Combo tab[kNumCombos];
   __shared__ float qcv[kMaxZones + 1];
   const StreamTiling tl = stream_tiling(p.H, p.W, V);
@@ -1114,6 +1132,7 @@ __global__ void __launch_bounds__(kStreamThreads) k_sweep(const Params p, const 
       if (r0 > 0) load_f<V>(tin + off - W, up);
       load_f<V>(tin + off, c);
     }
+#pragma unroll 2
     for (int r = r0; r < r1; ++r, off += W) {
       fill<V>(dn, t_inf);
       if (col_ok && r + 1 < H) load_f<V>(tin + off + W, dn);
@@ -1141,9 +1160,17 @@ __global__ void __launch_bounds__(kStreamThreads) k_sweep(const Params p, const 
           const float t_jm = e == 0 ? left : c[e - 1];
           const float t_jp = e == V - 1 ? right : c[e + 1];
           const float n3 = div_rn(mul(tab[d[e] & kPackIdxMask].cm, tp[e]), dt, rdt);   // :743-749
-          float qv = 0.f;
-          if (any_q) qv = (d[e] & SBX_DESC_DIFFUSER) ? qcv[d[e] >> SBX_DESC_ZONE_SHIFT] : 0.f;
-          o[e] = cv_update_packed(d[e], t_jp, t_jm, up[e], dn[e], n3, qv, t_inf, az, tab);
+          o[e] = cv_numerator_packed(d[e], t_jp, t_jm, up[e], dn[e], n3, az, tab);
+        }
+        // + input_q (:754): only diffuser CVs have any, and x + 0 == x exactly
+        if (any_q) {
+#pragma unroll
+          for (int e = 0; e < V; ++e)
+            if (d[e] & SBX_DESC_DIFFUSER) o[e] = add(o[e], qcv[d[e] >> SBX_DESC_ZONE_SHIFT]);
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          o[e] = cv_divide_packed(d[e], o[e], t_inf, tab);
           lmax = fmaxf(lmax, fabsf(__fsub_rn(o[e], c[e])));
         }
         store_f<V>(tout + off, o);
@@ -1189,11 +1216,28 @@ __global__ void k_activate(const Params p) {
 }
 
 // Zone sums + grid total of building.temp (building.py:845-871, simulator.py:408).
-// A thread keeps the running integer sum of its column group (V CVs x 8 rows: almost
-// always one zone) in registers; the warp then merges equal zones with exact hardware
-// REDUX on 16-bit pieces and ONE lane per zone touches the CTA's shared bins, so the
-// kernel is a plain bandwidth-bound read of the field (64-bit shared-memory atomics
-// are CAS loops on this hardware: one per CV run made this kernel 10x slower).
+// A thread owns a column group (V CVs x 8 rows).  Its CVs belong to at most two zones
+// in all but pathological plans -- the zone of the group's first column and the zone of
+// its last column, with a wall (no zone) in between -- so it keeps TWO running integer
+// sums in registers, branch-free.  The warp then merges equal zones with exact hardware
+// REDUX on 16-bit pieces and ONE lane per zone touches the CTA's shared bins: the kernel
+// is a plain bandwidth-bound read of the field.  (64-bit shared-memory atomics are CAS
+// loops on this hardware; one per run of CVs made this kernel 10x slower.)
+__device__ __forceinline__ void warp_merge_zone_sums(int zc, long long run, long long* bins, int lane) {
+  unsigned todo = __ballot_sync(0xffffffffu, zc != SBX_ZONE_NONE && run != 0);
+  while (todo) {
+    const int leader = __ffs(todo) - 1;
+    const int z = __shfl_sync(0xffffffffu, zc, leader);
+    const bool mine = ((todo >> lane) & 1u) && zc == z;
+    const long long v = mine ? run : 0;
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xFFFF));
+    const unsigned mid = __reduce_add_sync(0xffffffffu, (unsigned)((v >> 16) & 0xFFFF));
+    const int hi = __reduce_add_sync(0xffffffffu, (int)(v >> 32));
+    if (lane == leader) fix_add(&bins[z], ((long long)hi << 32) + ((long long)mid << 16) + (long long)lo);
+    todo &= ~__ballot_sync(0xffffffffu, mine);
+  }
+}
+
 template <int V>
 __global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) {
   __shared__ long long bins[kMaxZones + 1];
@@ -1211,61 +1255,49 @@ __global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) 
   const uint16_t* __restrict__ dsc = p.desc + (size_t)plan * n_cv;
   const int c0 = (tx * 32 + lane) * V;
   const int r0 = (ty * (kStreamThreads / 32) + warp) * kStreamRowsPerWarp;
-  long long total = 0;                 // every CV: the grid mean
-  long long run = 0;                   // CVs of zone `zc` seen by this thread
-  int zc = SBX_ZONE_NONE;
+  long long total = 0;                       // every CV: the grid mean
+  long long runL = 0, runR = 0;              // CVs of zone zL / zR seen by this thread
+  int zL = SBX_ZONE_NONE, zR = SBX_ZONE_NONE;
   if (c0 < W && r0 < H) {
-    float tv[kStreamRowsPerWarp][V];
-    uint32_t d[kStreamRowsPerWarp][V];
-#pragma unroll
-    for (int i = 0; i < kStreamRowsPerWarp; ++i) {       // all loads in flight first
-      if (r0 + i < H) {
-        load_f<V>(t + (size_t)(r0 + i) * W + c0, tv[i]);
-        load_d<V>(dsc + (size_t)(r0 + i) * W + c0, d[i]);
+    const int nr = min(kStreamRowsPerWarp, H - r0);
+    const float* tp = t + (size_t)r0 * W + c0;
+    const uint16_t* dp = dsc + (size_t)r0 * W + c0;
+#pragma unroll 4
+    for (int i = 0; i < nr; ++i, tp += W, dp += W) {
+      float tv[V];
+      uint32_t d[V];
+      load_f<V>(tp, tv);
+      load_d<V>(dp, d);
+      const int z_first = desc_zone(d[0]), z_last = desc_zone(d[V - 1]);
+      // a horizontal wall crossed between rows: hand the finished sums over
+      if (z_first != zL && z_first != SBX_ZONE_NONE) {
+        if (zL != SBX_ZONE_NONE && runL != 0) fix_add(&bins[zL], runL);
+        zL = z_first;
+        runL = 0;
       }
-    }
-#pragma unroll
-    for (int i = 0; i < kStreamRowsPerWarp; ++i) {
-      if (r0 + i < H) {
-        const int z0 = desc_zone(d[i][0]);
-        bool uniform = true;
-        long long s = 0;
-#pragma unroll
-        for (int e = 0; e < V; ++e) {
-          uniform = uniform && desc_zone(d[i][e]) == z0;
-          s += to_fix(tv[i][e]);
-        }
-        total += s;
-        if (uniform) {
-          if (z0 != zc) {
-            if (zc != SBX_ZONE_NONE && run != 0) fix_add(&bins[zc], run);
-            zc = z0;
-            run = 0;
-          }
-          run += s;
-        } else {                        // vector straddling a wall: per CV
-#pragma unroll
-          for (int e = 0; e < V; ++e) {
-            const int z = desc_zone(d[i][e]);
-            if (z != SBX_ZONE_NONE) fix_add(&bins[z], to_fix(tv[i][e]));
-          }
-        }
+      if (z_last != zR && z_last != SBX_ZONE_NONE && z_last != zL) {
+        if (zR != SBX_ZONE_NONE && runR != 0) fix_add(&bins[zR], runR);
+        zR = z_last;
+        runR = 0;
       }
+      int sl = 0, sr = 0, sa = 0;            // int32: V CVs x T * 2^16 < 2^31 for T < 8191 K
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int z = desc_zone(d[e]);
+        const int v = __float2int_rn(__fmul_rn(tv[e], kFixScaleF));
+        sa += v;
+        if (z == zL) sl += v;
+        else if (z == zR) sr += v;
+        else if (z != SBX_ZONE_NONE) fix_add(&bins[z], (long long)v);   // third zone in V CVs
+      }
+      total += sa;
+      runL += sl;
+      runR += sr;
     }
   }
-  // merge the lanes' (zone, sum) pairs: one REDUX triple and one atomic per distinct zone
-  unsigned todo = __ballot_sync(0xffffffffu, zc != SBX_ZONE_NONE && run != 0);
-  while (todo) {
-    const int leader = __ffs(todo) - 1;
-    const int z = __shfl_sync(0xffffffffu, zc, leader);
-    const bool mine = ((todo >> lane) & 1u) && zc == z;
-    const long long v = mine ? run : 0;
-    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)(v & 0xFFFF));
-    const unsigned mid = __reduce_add_sync(0xffffffffu, (unsigned)((v >> 16) & 0xFFFF));
-    const int hi = __reduce_add_sync(0xffffffffu, (int)(v >> 32));
-    if (lane == leader) fix_add(&bins[z], ((long long)hi << 32) + ((long long)mid << 16) + (long long)lo);
-    todo &= ~__ballot_sync(0xffffffffu, mine);
-  }
+  // a slot whose zone is still NONE only ever collected CVs outside every zone
+  warp_merge_zone_sums(zL, runL, bins, lane);
+  warp_merge_zone_sums(zR, runR, bins, lane);
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
   if (lane == 0) fix_add(&bins[Z], total);

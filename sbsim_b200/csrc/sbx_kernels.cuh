@@ -426,6 +426,78 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_reduce(const Params p)
   if (tid == 0) p.rl_chunks[plan] = total / 32;
 }
 
+// One FAST vector (4 interior air CVs, no heat input) on packed fp32 pairs (e0,e1),
+// (e2,e3): the same operations in the same order as cv_update_fast.  Returns the
+// running max |dT|.
+template <bool FIRST>
+__device__ __forceinline__ float fast_vector4(const float* __restrict__ in, float* __restrict__ out,
+                                              float* __restrict__ n3p, int base, int W,
+                                              const FastCoef2& fc2, float kq1, float lmax) {
+  float c[4], o[4];
+  {
+    const float4 c4 = *reinterpret_cast<const float4*>(in + base);
+    c[0] = c4.x; c[1] = c4.y; c[2] = c4.z; c[3] = c4.w;
+  }
+    // packed pairs (e0,e1), (e2,e3); same operations, same order as cv_update_fast
+    const float4 up4 = *reinterpret_cast<const float4*>(in + base - W);
+    const float4 dn4 = *reinterpret_cast<const float4*>(in + base + W);
+    const float left = in[base - 1];
+    const float right = in[base + 4];
+    const FastCoef2& f = fc2;
+    const f32x2 c01 = pack2(c[0], c[1]), c23 = pack2(c[2], c[3]);
+    f32x2 n3a, n3b;
+    if constexpr (FIRST) {
+      n3a = div_rn2(mul2(f.cm, c01), f.ndt, f.rdt);
+      n3b = div_rn2(mul2(f.cm, c23), f.ndt, f.rdt);
+      float4 st4;
+      unpack2(n3a, st4.x, st4.y);
+      unpack2(n3b, st4.z, st4.w);
+      *reinterpret_cast<float4*>(n3p + base) = st4;
+    } else {
+      const float4 n4 = *reinterpret_cast<const float4*>(n3p + base);
+      n3a = pack2(n4.x, n4.y);
+      n3b = pack2(n4.z, n4.w);
+    }
+    // horizontal: kq*T(j+1) + kq*T(j-1); every product is used by two CVs
+    float m0, m1, m2, m3;
+    unpack2(mul2(f.kq, c01), m0, m1);
+    unpack2(mul2(f.kq, c23), m2, m3);
+    const float ml = mul(kq1, left), mr = mul(kq1, right);
+    f32x2 n1a = pack2(add(m1, ml), add(m2, m0));
+    f32x2 n1b = pack2(add(m3, m1), add(mr, m2));
+    n1a = mul2(f.vz, n1a);
+    n1b = mul2(f.vz, n1b);
+    // vertical: kq*T(i+1) + kq*T(i-1).  ptxas contracts add.rn.f32x2 of a
+    // mul.rn.f32x2 result into FFMA2 (even with --fmad=false; it leaves scalar
+    // add.rn alone), which would drop a rounding: every sum that consumes a packed
+    // PRODUCT is therefore taken with scalar adds on the halves.
+    float a0, a1, a2, a3, b0, b1, b2, b3;
+    unpack2(mul2(f.kq, pack2(dn4.x, dn4.y)), a0, a1);
+    unpack2(mul2(f.kq, pack2(dn4.z, dn4.w)), a2, a3);
+    unpack2(mul2(f.kq, pack2(up4.x, up4.y)), b0, b1);
+    unpack2(mul2(f.kq, pack2(up4.z, up4.w)), b2, b3);
+    const f32x2 n2a = mul2(f.vz, pack2(add(a0, b0), add(a1, b1)));
+    const f32x2 n2b = mul2(f.vz, pack2(add(a2, b2), add(a3, b3)));
+    float p0, p1, p2, p3, q0, q1, q2, q3;
+    unpack2(n1a, p0, p1);
+    unpack2(n1b, p2, p3);
+    unpack2(n2a, q0, q1);
+    unpack2(n2b, q2, q3);
+    const f32x2 suma = pack2(add(p0, q0), add(p1, q1));
+    const f32x2 sumb = pack2(add(p2, q2), add(p3, q3));
+    const f32x2 oa = div_rn2(add2(suma, n3a), f.nden, f.rden);
+    const f32x2 ob = div_rn2(add2(sumb, n3b), f.nden, f.rden);
+    unpack2(oa, o[0], o[1]);
+    unpack2(ob, o[2], o[3]);
+    float d0, d1, d2, d3;
+    unpack2(sub2(oa, c01), d0, d1);
+    unpack2(sub2(ob, c23), d2, d3);
+    lmax = fmaxf(fmaxf(lmax, fabsf(d0)), fabsf(d1));
+    lmax = fmaxf(fmaxf(lmax, fabsf(d2)), fabsf(d3));
+    *reinterpret_cast<float4*>(out + base) = make_float4(o[0], o[1], o[2], o[3]);
+  return lmax;
+}
+
 // Per-material coefficients of an interior-class CV (header, MEDIUM list)
 struct MedCoef {
   float kq, cm, den, rden;
@@ -457,7 +529,20 @@ __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, fl
   const int W = s.P, wq = s.wq;      // W: row pitch in CVs
   const float t_inf = s.t_inf;
   float lmax = 0.f;
-  for (int u = tid; u < s.n_items; u += NT) {
+  int u = tid;
+  if constexpr (V == 4) {
+    // Every thread's first two vectors are FAST when the list holds two rounds of them:
+    // run them as ONE instruction stream (two independent dependency chains), the
+    // sweeps being latency-bound at 8 warps per scheduler.
+    if (s.n_fast >= 2 * NT) {
+      const int base0 = ((int)s.qlist[u] & 0x7FFF) * V, base1 = ((int)s.qlist[u + NT] & 0x7FFF) * V;
+      const float l0 = fast_vector4<FIRST>(in, out, n3p, base0, W, s.fc2, s.fc.kq, 0.f);
+      const float l1 = fast_vector4<FIRST>(in, out, n3p, base1, W, s.fc2, s.fc.kq, 0.f);
+      lmax = fmaxf(l0, l1);
+      u += 2 * NT;
+    }
+  }
+  for (; u < s.n_items; u += NT) {
     const int entry = (int)s.qlist[u];
     const int it = entry & 0x7FFF;     // vector slot
     const int base = it * V;
@@ -465,63 +550,7 @@ __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, fl
     load_f<V>(in + base, c);
     if (u < s.n_fast) {
       if constexpr (V == 4) {
-        // packed pairs (e0,e1), (e2,e3); same operations, same order as cv_update_fast
-        const float4 up4 = *reinterpret_cast<const float4*>(in + base - W);
-        const float4 dn4 = *reinterpret_cast<const float4*>(in + base + W);
-        const float left = in[base - 1];
-        const float right = in[base + V];
-        const FastCoef2& f = s.fc2;
-        const f32x2 c01 = pack2(c[0], c[1]), c23 = pack2(c[2], c[3]);
-        f32x2 n3a, n3b;
-        if constexpr (FIRST) {
-          n3a = div_rn2(mul2(f.cm, c01), f.ndt, f.rdt);
-          n3b = div_rn2(mul2(f.cm, c23), f.ndt, f.rdt);
-          float4 st4;
-          unpack2(n3a, st4.x, st4.y);
-          unpack2(n3b, st4.z, st4.w);
-          *reinterpret_cast<float4*>(n3p + base) = st4;
-        } else {
-          const float4 n4 = *reinterpret_cast<const float4*>(n3p + base);
-          n3a = pack2(n4.x, n4.y);
-          n3b = pack2(n4.z, n4.w);
-        }
-        // horizontal: kq*T(j+1) + kq*T(j-1); every product is used by two CVs
-        float m0, m1, m2, m3;
-        unpack2(mul2(f.kq, c01), m0, m1);
-        unpack2(mul2(f.kq, c23), m2, m3);
-        const float ml = mul(s.fc.kq, left), mr = mul(s.fc.kq, right);
-        f32x2 n1a = pack2(add(m1, ml), add(m2, m0));
-        f32x2 n1b = pack2(add(m3, m1), add(mr, m2));
-        n1a = mul2(f.vz, n1a);
-        n1b = mul2(f.vz, n1b);
-        // vertical: kq*T(i+1) + kq*T(i-1).  ptxas contracts add.rn.f32x2 of a
-        // mul.rn.f32x2 result into FFMA2 (even with --fmad=false; it leaves scalar
-        // add.rn alone), which would drop a rounding: every sum that consumes a packed
-        // PRODUCT is therefore taken with scalar adds on the halves.
-        float a0, a1, a2, a3, b0, b1, b2, b3;
-        unpack2(mul2(f.kq, pack2(dn4.x, dn4.y)), a0, a1);
-        unpack2(mul2(f.kq, pack2(dn4.z, dn4.w)), a2, a3);
-        unpack2(mul2(f.kq, pack2(up4.x, up4.y)), b0, b1);
-        unpack2(mul2(f.kq, pack2(up4.z, up4.w)), b2, b3);
-        const f32x2 n2a = mul2(f.vz, pack2(add(a0, b0), add(a1, b1)));
-        const f32x2 n2b = mul2(f.vz, pack2(add(a2, b2), add(a3, b3)));
-        float p0, p1, p2, p3, q0, q1, q2, q3;
-        unpack2(n1a, p0, p1);
-        unpack2(n1b, p2, p3);
-        unpack2(n2a, q0, q1);
-        unpack2(n2b, q2, q3);
-        const f32x2 suma = pack2(add(p0, q0), add(p1, q1));
-        const f32x2 sumb = pack2(add(p2, q2), add(p3, q3));
-        const f32x2 oa = div_rn2(add2(suma, n3a), f.nden, f.rden);
-        const f32x2 ob = div_rn2(add2(sumb, n3b), f.nden, f.rden);
-        unpack2(oa, o[0], o[1]);
-        unpack2(ob, o[2], o[3]);
-        float d0, d1, d2, d3;
-        unpack2(sub2(oa, c01), d0, d1);
-        unpack2(sub2(ob, c23), d2, d3);
-        lmax = fmaxf(fmaxf(lmax, fabsf(d0)), fabsf(d1));
-        lmax = fmaxf(fmaxf(lmax, fabsf(d2)), fabsf(d3));
-        store_f<V>(out + base, o);
+        lmax = fast_vector4<FIRST>(in, out, n3p, base, W, s.fc2, s.fc.kq, lmax);
         continue;
       } else {
       float up[V], dn[V], n3v[V];

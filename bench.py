@@ -54,6 +54,8 @@ def parse_args():
   ap.add_argument("--cpu-sample-steps", type=int, default=24)
   ap.add_argument("--no-cpu-baseline", action="store_true")
   ap.add_argument("--no-e2e", action="store_true")
+  ap.add_argument("--others", type=int, default=1,
+                  help="also measure BASELINE.json's other single-GPU configurations (N=1 only)")
   ap.add_argument("--path", choices=["auto", "streaming", "resident"], default="auto")
   ap.add_argument("--convergence-threshold", type=float, default=0.1,
                   help="experiments only; BASELINE uses 0.1 K (sim_config.gin:161)")
@@ -161,6 +163,7 @@ def build_env(args, rank, local_rank):
 
 
 def run_sbx(args):
+  import copy
   import torch
   import torch.distributed as dist
   rank, local_rank, world = dist_env()
@@ -168,11 +171,36 @@ def run_sbx(args):
     raise SystemExit(f"WORLD_SIZE {world} != --gpus {args.gpus}")
   if not torch.cuda.is_available():
     raise SystemExit("bench.py needs a CUDA device; sbsim_b200 has no CPU fallback")
+  if args.warmup < 3:
+    raise SystemExit("--warmup must be >= 3")
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   if world > 1:
     dist.init_process_group("nccl", device_id=dev)
+  line = _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu=True)
+  # The other single-GPU configurations of BASELINE.json, measured briefly beside the
+  # headline (N=1 only): configs[1]'s size class (4096 copies of one 744x1004 plan,
+  # streaming path) and configs[2] (65536 randomised buildings on one GPU).
+  if world == 1 and args.others and args.workload == "randomized" and args.envs_per_gpu is None:
+    others = []
+    for wl_name, envs, steps in (("office", 4096, 20), ("randomized", 65536, 50)):
+      a2 = copy.copy(args)
+      a2.workload, a2.envs_per_gpu, a2.steps, a2.warmup = wl_name, envs, steps, 3
+      try:
+        l2 = _measure(a2, torch, dist, rank, local_rank, world, dev, with_cpu=False)
+        others.append({k: l2[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step",
+                                          "config", "gpu_launches", "roofline", "e2e") if k in l2})
+      except Exception as e:  # pylint: disable=broad-except
+        others.append({"config": {"workload": wl_name, "envs_per_gpu": envs},
+                       "error": f"{type(e).__name__}: {e}"})
+    line["other_configs"] = others
+  if rank == 0:
+    print(json.dumps(line), flush=True)
+  if world > 1:
+    dist.destroy_process_group()
 
+
+def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
   env, wl, cfg_desc = build_env(args, rank, local_rank)
   from sbsim_b200 import _lib
   if args.chunks > 0:
@@ -183,8 +211,6 @@ def run_sbx(args):
   D = env.observation_spec().shape[0]
   A = env.action_spec().shape[0]
   W, K = args.warmup, args.steps
-  if W < 3:
-    raise SystemExit("--warmup must be >= 3")
 
   gen = torch.Generator(device=dev)
   gen.manual_seed(3000 + rank)
@@ -225,7 +251,6 @@ def run_sbx(args):
     one_step(W + i)
     ev[i + 1].record(stream)
   barrier()
-  sampler.stop()
   info1 = env.handle.info()
   per_step_ms = [ev[i].elapsed_time(ev[i + 1]) for i in range(K)]
   total_ms = ev[0].elapsed_time(ev[K])
@@ -252,6 +277,7 @@ def run_sbx(args):
     one_step(W + i)
   barrier()
   tm = env.handle.timing_end()
+  sampler.stop()                      # sampled over both timed loops (value pass + event pass)
   solve_ms = tm.solve_ms / max(tm.n_steps, 1)           # all solve launches of one step
   timed_step_ms = tm.step_ms / max(tm.n_steps, 1)
   info2 = env.handle.info()
@@ -304,7 +330,8 @@ def run_sbx(args):
   try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this B
     with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
       tr = json.load(f).get(args.workload)
-    if tr and resident:
+    if tr and (resident or args.workload == "office"):
+      # per launch of the dominant kernel over all B buildings (streaming: one sweep >= 2)
       traffic = (tr["dram_bytes_read"] + tr["dram_bytes_write"]) * B / tr["launch_envs"]
   except Exception:  # pylint: disable=broad-except
     traffic = None
@@ -321,31 +348,30 @@ def run_sbx(args):
 
   # ---- CPU baseline beside it (rank 0, N=1 only) ----
   cpu = None
-  if rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "randomized":
+  if with_cpu and rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "randomized":
     cpu = cpu_baseline(args, wl, K=args.cpu_sample_steps)
 
-  if rank == 0:
-    line = {
-        "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
-        "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-        "config": dict(cfg_desc, global_envs=world * B,
-                       kernel_path="resident" if resident else "streaming",
-                       obs_dim=D, l2_policy="inputs larger than L2 (state %.0f MB per GPU)"
-                       % (B * n_cv * 4 / 1e6),
-                       allgather=bool(gathered is not None), episode_steps=288,
-                       time_step_sec=300),
-        "clocks": sampler.summary(), "gpu_launches": launches,
-        "roofline": roofline,
-    }
-    if e2e is not None:
-      line["e2e"] = e2e
-    if cpu is not None:
-      line["cpu_baseline"] = cpu
-    print(json.dumps(line), flush=True)
+  line = {
+      "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
+      "warmup": W, "ms_per_step": max_ms / K, "higher_is_better": True, "scaling": "weak",
+      "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+      "config": dict(cfg_desc, global_envs=world * B,
+                     kernel_path="resident" if resident else "streaming",
+                     obs_dim=D, l2_policy="inputs larger than L2 (state %.0f MB per GPU)"
+                     % (B * n_cv * 4 / 1e6),
+                     allgather=bool(gathered is not None), episode_steps=288,
+                     time_step_sec=300, mean_sweeps_per_step=mean_sweeps),
+      "clocks": sampler.summary(), "gpu_launches": launches,
+      "roofline": roofline,
+  }
+  if e2e is not None:
+    line["e2e"] = e2e
+  if cpu is not None:
+    line["cpu_baseline"] = cpu
   env.close()
-  if world > 1:
-    dist.destroy_process_group()
+  del env, actions, obs, rew, st, dis
+  torch.cuda.empty_cache()
+  return line
 
 
 def _oracle_specs(wl, n, episode_steps):

@@ -182,7 +182,10 @@ enum {
   SBX_F_COMFORT = 22,      /* u8  [T]     SetpointSchedule.is_comfort_mode(t_s) */
   SBX_F_COMFORT_SOON = 23, /* u8  [T]     is_comfort_mode(t_s + 60 min) environment.py:946-951 */
   SBX_F_OCC_REWARD = 24,   /* f64 [T,Zo]  average_zone_occupancy(zone, t_s, t_s + dt) */
-  SBX_F_OCC_OBS = 25,      /* i32 [T]     SimulatorBuilding.num_occupants at t_s */
+  SBX_F_OCC_OBS = 25,      /* i32 [T]     SimulatorBuilding.num_occupants at t_s, ONE count for every env (replayed tables) */
+  SBX_F_OCC_OBS_ZONE = 30, /* f64 [T,Zo]  average_zone_occupancy(zone, t_s - 5 min, t_s) (simulator_building.py:305-315).
+                              Once uploaded, num_occupants is int(sum over the zones the BUILDING has), in zone order:
+                              what batches of buildings with different zone counts need; supersedes SBX_F_OCC_OBS */
   SBX_F_PRICE_ELEC = 26,   /* f64 [T]     USD / (W s) at hour(t_s), weekday/weekend table */
   SBX_F_CARBON_ELEC = 27,  /* f64 [T]     kg / (W s) at hour(t_s) */
   SBX_F_PRICE_GAS = 28,    /* f64 [T]     USD / J at month(t_s) */

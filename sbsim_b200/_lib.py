@@ -52,6 +52,7 @@ FIELDS = {
     "ambient": (20, np.float64), "convection": (21, np.float64),
     "comfort": (22, np.uint8), "comfort_soon": (23, np.uint8),
     "occ_reward": (24, np.float64), "occ_obs": (25, np.int32),
+    "occ_obs_zone": (30, np.float64),
     "price_elec": (26, np.float64), "carbon_elec": (27, np.float64),
     "price_gas": (28, np.float64), "time_features": (29, np.float64),
     "temp": (40, np.float32), "zone_mean": (41, np.float32),

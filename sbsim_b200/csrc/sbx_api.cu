@@ -60,7 +60,7 @@ struct sbx_env {
   int conv_pending = 0;          // a permutation was uploaded for the next step
   uint8_t* h_comfort = nullptr;  // host copy of the comfort table (for prev_comfort)
   // device allocations
-  DevBuf all[64];
+  DevBuf all[128];
   int n_all = 0;
   int64_t device_bytes = 0;
   int64_t launches = 0;
@@ -131,7 +131,7 @@ int dev_alloc(sbx_handle h, T** out, size_t count, bool zero = true) {
     e = cudaMemset(p, 0, bytes);
     if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaMemset failed: %s", cudaGetErrorString(e));
   }
-  if (h->n_all >= 64) return fail(h, SBX_E_INVALID, "too many allocations");
+  if (h->n_all >= 128) return fail(h, SBX_E_INVALID, "too many allocations");
   h->all[h->n_all].p = p;
   h->all[h->n_all].bytes = bytes;
   ++h->n_all;
@@ -592,6 +592,7 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.comfort_soon, uint8_t, T);
   ALLOC(p.occ_reward, double, T * c.n_occ_zones);
   ALLOC(p.occ_obs, int32_t, T);
+  ALLOC(p.occ_obs_zone, double, T * c.n_occ_zones);
   ALLOC(p.price_e, double, T);
   ALLOC(p.carbon_e, double, T);
   ALLOC(p.price_g, double, T);
@@ -746,6 +747,7 @@ static int field_info(sbx_handle h, int field, FieldInfo* fi) {
     F(SBX_F_COMFORT_SOON, p.comfort_soon, T, uint8_t, true);
     F(SBX_F_OCC_REWARD, p.occ_reward, T * c.n_occ_zones, double, true);
     F(SBX_F_OCC_OBS, p.occ_obs, T, int32_t, true);
+    F(SBX_F_OCC_OBS_ZONE, p.occ_obs_zone, T * c.n_occ_zones, double, true);
     F(SBX_F_PRICE_ELEC, p.price_e, T, double, true);
     F(SBX_F_CARBON_ELEC, p.carbon_e, T, double, true);
     F(SBX_F_PRICE_GAS, p.price_g, T, double, true);
@@ -826,6 +828,8 @@ int sbx_upload(sbx_handle h, int field, const void* src, size_t nbytes) {
     CUDA_TRY(h, cudaDeviceSynchronize());
   }
   if (field == SBX_F_COMFORT) memcpy(h->h_comfort, src, nbytes);
+  if (field == SBX_F_OCC_OBS_ZONE) h->P.occ_obs_per_env = 1;
+  if (field == SBX_F_OCC_OBS) h->P.occ_obs_per_env = 0;
   if (field == SBX_F_PLAN_DESC) h->plans_dirty = 1;
   return SBX_OK;
 }

@@ -104,6 +104,8 @@ struct Params {
   const uint8_t* comfort_soon;
   const double* occ_reward;  // [T,Zo]
   const int32_t* occ_obs;    // [T]
+  const double* occ_obs_zone;  // [T,Zo]
+  int occ_obs_per_env;       // occ_obs_zone was uploaded: count the building's own zones
   const double* price_e;
   const double* carbon_e;
   const double* price_g;
@@ -733,7 +735,14 @@ __device__ inline void hvac_post(const Params& p, int b, int plan, int lane, uns
       o[0] = (float)tf[0]; o[1] = (float)tf[1]; o[2] = (float)tf[2]; o[3] = (float)tf[3];
       o[4] = (float)p.comfort[s1];
       o[5] = (float)p.comfort_soon[s1];
-      o[6] = (float)(((double)p.occ_obs[s1] - p.occ_norm) / (p.occ_norm + 1));  // environment.py:952-956
+      double n_occ = (double)p.occ_obs[s1];
+      if (p.occ_obs_per_env) {       // int(sum_z occupancy(z, t - 5 min, t)) simulator_building.py:305-315
+        double acc = 0.0;
+        for (int zi = 0; zi < Z; ++zi)
+          if (ncv[zi] > 0) acc += p.occ_obs_zone[(size_t)s1 * p.n_occ_zones + (p.n_occ_zones == 1 ? 0 : zi)];
+        n_occ = (double)(long long)acc;
+      }
+      o[6] = (float)((n_occ - p.occ_norm) / (p.occ_norm + 1));  // environment.py:952-956
     }
   }
   if (is_reset) {

@@ -351,13 +351,15 @@ class Environment:
     h.upload("comfort", sched.table(ts))
     soon = pd.Timedelta(60, unit="minute")
     h.upload("comfort_soon", sched.table([t + soon for t in ts]))
-    occ_r, occ_o = exogenous.occupancy_tables(
+    occ_r, occ_o, occ_z = exogenous.occupancy_tables(
         b.occupancy, b.zone_ids or ["zone_id_0"], ts, b.time_step_sec,
         per_zone=self._cfg.n_occ_zones > 1)
     if occ_r.shape[0] < T or occ_o.shape[0] < T:
       raise ValueError("occupancy tables shorter than the episode")
     h.upload("occ_reward", occ_r[:T])
     h.upload("occ_obs", occ_o[:T])
+    if occ_z is not None:      # per-building count of the zones each plan really has
+      h.upload("occ_obs_zone", occ_z[:T])
     pe, ce, pg = exogenous.energy_tables(self.reward_function.electricity_energy_cost,
                                          self.reward_function.natural_gas_energy_cost, ts)
     h.upload("price_elec", pe)

@@ -293,35 +293,40 @@ class TableOccupancy:
 
 def occupancy_tables(occupancy, zone_ids: Sequence[str], timestamps, time_step_sec: float,
                      per_zone: bool):
-  """Returns (occ_reward [T, Zo], occ_obs [T]).
+  """Returns (occ_reward [T, Zo], occ_obs [T], occ_obs_zone [T, Zo] or None).
 
   occ_reward[s, z] = average_zone_occupancy(zone z, t_s, t_s + dt)
       (simulator_flexible_floor_plan.py:206-210, evaluated at the post-step time)
   occ_obs[s] = int(sum_z average_zone_occupancy(z, t_s - 5 min, t_s))
-      (simulator_building.py:305-315)
+      (simulator_building.py:305-315), summed over `zone_ids`
+  occ_obs_zone[s, z] = the terms of that sum: the device adds up the zones each
+      building actually has (batches of buildings with different zone counts)
   """
   if isinstance(occupancy, TableOccupancy):
-    return occupancy.reward_table, occupancy.obs_table
+    return occupancy.reward_table, occupancy.obs_table, None
   dt = pd.Timedelta(time_step_sec, unit="s")
   five = pd.Timedelta(5, unit="minute")
   zo = len(zone_ids) if per_zone else 1
   rew = np.zeros((len(timestamps), zo), dtype=np.float64)
   obs = np.zeros(len(timestamps), dtype=np.int32)
+  obs_zone = np.zeros((len(timestamps), zo), dtype=np.float64)
   for s, ts in enumerate(timestamps):
     if per_zone:
       for z, zid in enumerate(zone_ids):
         rew[s, z] = occupancy.average_zone_occupancy(zid, ts, ts + dt)
+        obs_zone[s, z] = occupancy.average_zone_occupancy(zid, ts - five, ts)
       n = 0.0
-      for zid in zone_ids:
-        n += occupancy.average_zone_occupancy(zid, ts - five, ts)
+      for z in range(len(zone_ids)):
+        n += obs_zone[s, z]
     else:
       rew[s, 0] = occupancy.average_zone_occupancy(zone_ids[0], ts, ts + dt)
       one = occupancy.average_zone_occupancy(zone_ids[0], ts - five, ts)
+      obs_zone[s, 0] = one
       n = 0.0
       for _ in zone_ids:
         n += one
     obs[s] = int(n)
-  return rew, obs
+  return rew, obs, obs_zone
 
 
 # ----------------------------------------------------------------------------

@@ -71,7 +71,8 @@ def test_occupancy_and_energy_tables_match_oracle():
   occ = sbx.StepFunctionOccupancy(pd.Timedelta(9, unit="h"), pd.Timedelta(17, unit="h"), 1.0, 0.1)
   o = oex.StepFunctionOccupancy(pd.Timedelta(9, unit="h"), pd.Timedelta(17, unit="h"), 1.0, 0.1)
   zones = ["zone_id_1", "zone_id_2", "zone_id_3"]
-  rew, obs = exogenous.occupancy_tables(occ, zones, ts, 300.0, per_zone=False)
+  rew, obs, obs_zone = exogenous.occupancy_tables(occ, zones, ts, 300.0, per_zone=False)
+  assert obs_zone.shape == (600, 1)
   dt = pd.Timedelta(300, unit="s")
   five = pd.Timedelta(5, unit="minute")
   for s in range(0, 600, 7):
@@ -80,6 +81,7 @@ def test_occupancy_and_energy_tables_match_oracle():
     for _ in zones:
       n += o.average_zone_occupancy("z", ts[s] - five, ts[s])
     assert obs[s] == int(n)
+    assert obs_zone[s, 0] == o.average_zone_occupancy("z", ts[s] - five, ts[s])
   pe, ce, pg = exogenous.energy_tables(sbx.ElectricityEnergyCost(), sbx.NaturalGasEnergyCost(), ts)
   oe, og = oex.ElectricityEnergyCost(), oex.NaturalGasEnergyCost()
   for s in range(0, 600, 11):

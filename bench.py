@@ -85,7 +85,37 @@ class ClockSampler(threading.Thread):
     self.samples = []
     self._stop_evt = threading.Event()
 
+  def _nvml_loop(self) -> bool:
+    """NVML sampling (~0.1 ms per query instead of ~0.3 s per nvidia-smi process)."""
+    try:
+      import pynvml
+      pynvml.nvmlInit()
+      visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+      index = int(visible.split(",")[self.index]) if visible else self.index
+      dev = pynvml.nvmlDeviceGetHandleByIndex(index)
+      bits = {"hw_slowdown": pynvml.nvmlClocksThrottleReasonHwSlowdown,
+              "hw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonHwThermalSlowdown,
+              "sw_thermal_slowdown": pynvml.nvmlClocksThrottleReasonSwThermalSlowdown,
+              "sw_power_cap": pynvml.nvmlClocksThrottleReasonSwPowerCap}
+      mx = pynvml.nvmlDeviceGetMaxClockInfo(dev, pynvml.NVML_CLOCK_SM)
+    except Exception:  # pylint: disable=broad-except
+      return False
+    while not self._stop_evt.is_set():
+      try:
+        sm = pynvml.nvmlDeviceGetClockInfo(dev, pynvml.NVML_CLOCK_SM)
+        reasons = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(dev)
+        power = pynvml.nvmlDeviceGetPowerUsage(dev) / 1000.0
+        flags = ["Active" if reasons & bits[n] else "Not Active"
+                 for n in ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")]
+        self.samples.append([str(sm), str(mx), str(power)] + flags)
+      except Exception:  # pylint: disable=broad-except
+        pass
+      self._stop_evt.wait(0.01)
+    return True
+
   def run(self):
+    if self._nvml_loop():
+      return
     while not self._stop_evt.is_set():
       try:
         out = subprocess.run(

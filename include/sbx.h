@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SBX_ABI_VERSION 3
+#define SBX_ABI_VERSION 4
 
 #define SBX_OK 0
 #define SBX_E_INVALID (-1)   /* bad argument / config                      */
@@ -54,6 +54,10 @@ extern "C" {
 #define SBX_ACT_BOILER_SETPOINT 0
 #define SBX_ACT_AHU_COOLING_SETPOINT 1
 #define SBX_ACT_AHU_HEATING_SETPOINT 2
+
+/* reward functions */
+#define SBX_REWARD_REGRET 0        /* SetpointEnergyCarbonRegretFunction  reward/setpoint_energy_carbon_regret.py:142-291 */
+#define SBX_REWARD_ENERGY_CARBON 1 /* SetpointEnergyCarbonRewardFunction  reward/setpoint_energy_carbon_reward.py:127-190 */
 
 /* observation layouts (environment.py:698-812) */
 #define SBX_OBS_RAW 0       /* 9 + 3 + 3*Z + 7 */
@@ -132,6 +136,12 @@ typedef struct {
   double productivity_midpoint_delta, productivity_decay_stiffness;
   double productivity_weight, energy_cost_weight, carbon_emission_weight;
   double gas_carbon_rate; /* kg / J  natural_gas_energy_cost.py:67-71 */
+  /* SBX_REWARD_ENERGY_CARBON only (setpoint_energy_carbon_reward.py:103-125); it also uses
+   * max_productivity_personhour_usd, the two productivity_* shape parameters,
+   * energy_cost_weight and carbon_emission_weight (= carbon_cost_weight) from above */
+  double carbon_cost_factor, reward_normalizer_shift, reward_normalizer_scale;
+  int32_t reward_kind; /* SBX_REWARD_* */
+  int32_t reserved_reward;
   /* ---- environment (environment.py:355-514) ---- */
   double discount_factor;
   double occupancy_normalization_constant;

@@ -55,6 +55,7 @@ class RewardResponse:                       # smart_control_reward.proto:53-85
   normalized_productivity_regret: float
   normalized_energy_cost: float
   normalized_carbon_emission: float
+  carbon_cost: float = 0.0
 
 
 class SetpointEnergyCarbonRegretFunction:
@@ -134,3 +135,54 @@ class SetpointEnergyCarbonRegretFunction:
         normalized_energy_cost=f32(n_cost),
         normalized_carbon_emission=f32(n_carbon),
     )
+
+
+class SetpointEnergyCarbonRewardFunction(SetpointEnergyCarbonRegretFunction):
+  """/root/reference/smart_control/reward/setpoint_energy_carbon_reward.py:103-190:
+  productivity - w_e * (electricity + gas cost) - w_c * carbon cost, shifted and scaled.
+  Shares the zone-productivity logistic with the regret function (base:54-123)."""
+
+  def __init__(self, max_productivity_personhour_usd, productivity_midpoint_delta,
+               productivity_decay_stiffness, electricity_energy_cost,
+               natural_gas_energy_cost, energy_cost_weight, carbon_cost_weight,
+               carbon_cost_factor, reward_normalizer_shift=0.0, reward_normalizer_scale=1.0):
+    self.pmax = max_productivity_personhour_usd
+    self.delta = productivity_midpoint_delta
+    self.stiff = productivity_decay_stiffness
+    self.elec = electricity_energy_cost
+    self.gas = natural_gas_energy_cost
+    self.v = energy_cost_weight
+    self.w = carbon_cost_weight
+    self.factor = carbon_cost_factor
+    self.shift = reward_normalizer_shift
+    self.scale = reward_normalizer_scale
+
+  def compute_reward(self, info: RewardInfo) -> RewardResponse:   # :127-190
+    start, end = info.start_timestamp, info.end_timestamp
+    dt = (end - start).total_seconds()
+    productivity = 0.0
+    total_occ = 0.0
+    for z in info.zones:                                         # base:54-81
+      total_occ += z.average_occupancy
+      productivity += self._zone_productivity(
+          z.heating_setpoint_temperature, z.cooling_setpoint_temperature,
+          z.zone_air_temperature, dt, z.average_occupancy)
+    elec_rate = (info.blower_electrical_energy_rate
+                 + np.abs(info.air_conditioning_electrical_energy_rate)
+                 + info.pump_electrical_energy_rate)             # base:125-148
+    cost_e = self.elec.cost(start, end, elec_rate)               # :141-150
+    carb_e = self.elec.carbon(start, end, elec_rate)
+    gas_rate = info.natural_gas_heating_energy_rate              # :152-164
+    cost_g = self.gas.cost(start, end, gas_rate)
+    carb_g = self.gas.carbon(start, end, gas_rate)
+    combined = carb_e + carb_g
+    carbon_cost = f32(combined * self.factor)                    # :174-176 proto float, read back below
+    raw = productivity - self.v * (cost_e + cost_g) - self.w * carbon_cost   # :178-183
+    value = (raw - self.shift) / self.scale                      # :185-187
+    return RewardResponse(
+        agent_reward_value=f32(value), productivity_reward=f32(productivity),
+        electricity_energy_cost=f32(cost_e), natural_gas_energy_cost=f32(cost_g),
+        carbon_emitted=f32(combined), total_occupancy=f32(total_occ),
+        productivity_regret=0.0, normalized_productivity_regret=0.0,
+        normalized_energy_cost=0.0, normalized_carbon_emission=0.0,
+        carbon_cost=carbon_cost)

@@ -11,6 +11,7 @@ from sbsim_b200._lib import (LIB_PATH, PATH_AUTO, PATH_RESIDENT, PATH_STREAMING,
 from sbsim_b200.config import (ActionConfig, AirHandler, Boiler, BoundedActionNormalizer,
                                FloorPlanBasedHvac, HistogramReducer,
                                SetpointEnergyCarbonRegretFunction,
+                               SetpointEnergyCarbonRewardFunction,
                                StandardScoreObservationNormalizer)
 from sbsim_b200.convection import StochasticConvectionSimulator
 from sbsim_b200.environment import BatchedWeather, Environment, SimulatorBuilding
@@ -26,6 +27,7 @@ __all__ = [
     "FloorPlanBasedHvac", "HistogramReducer", "LIB_PATH", "MaterialProperties",
     "NaturalGasEnergyCost", "PATH_AUTO", "PATH_RESIDENT", "PATH_STREAMING",
     "ReplayWeatherController", "SbxLibraryError", "SetpointEnergyCarbonRegretFunction",
+    "SetpointEnergyCarbonRewardFunction",
     "SetpointSchedule", "SimulatorBuilding", "StandardScoreObservationNormalizer",
     "StepFunctionOccupancy", "StochasticConvectionSimulator", "TableOccupancy", "WeatherController", "compile_plan",
 ]

@@ -16,7 +16,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SBX_LIB: developer override used to A/B kernel variants (profiles/); same ABI, same checks
 LIB_PATH = os.environ.get("SBX_LIB") or os.path.join(_HERE, "lib", "libsbx.so")
 
-ABI_VERSION = 3
+ABI_VERSION = 4
+REWARD_REGRET, REWARD_ENERGY_CARBON = 0, 1
 OPT_PIPELINE_CHUNKS = 1
 OPT_L2_PREFETCH_DISTANCE = 2
 OK = 0
@@ -111,6 +112,9 @@ class SbxConfig(C.Structure):
       ("productivity_decay_stiffness", C.c_double),
       ("productivity_weight", C.c_double), ("energy_cost_weight", C.c_double),
       ("carbon_emission_weight", C.c_double), ("gas_carbon_rate", C.c_double),
+      ("carbon_cost_factor", C.c_double), ("reward_normalizer_shift", C.c_double),
+      ("reward_normalizer_scale", C.c_double), ("reward_kind", C.c_int32),
+      ("reserved_reward", C.c_int32),
       ("discount_factor", C.c_double), ("occupancy_normalization_constant", C.c_double),
       ("n_actions", C.c_int32), ("action_target", C.c_int32 * MAX_ACTIONS),
       ("action_min", C.c_double * MAX_ACTIONS), ("action_max", C.c_double * MAX_ACTIONS),
@@ -218,6 +222,18 @@ class PinnedArray:
         self._ptr = C.c_void_p()
     except Exception:  # pylint: disable=broad-except
       pass
+
+
+def pinned_time_step_arrays(batch: int, obs_dim: int):
+  """(observation [B,D] f32, reward [B] f32, step_type [B] i32, discount [B] f32) as views
+  of ONE page-locked block, in that order and back to back: sbx_step_host / sbx_reset_host
+  then move all four outputs with a single device-to-host DMA."""
+  block = PinnedArray((batch * (obs_dim + 3),), np.float32)
+  flat = block.array
+  o = batch * obs_dim
+  views = (flat[:o].reshape(batch, obs_dim), flat[o:o + batch],
+           flat[o + batch:o + 2 * batch].view(np.int32), flat[o + 2 * batch:o + 3 * batch])
+  return block, views
 
 
 class Handle:

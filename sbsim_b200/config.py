@@ -90,6 +90,22 @@ class SetpointEnergyCarbonRegretFunction:
     assert self.max_productivity_personhour_usd > self.min_productivity_personhour_usd
 
 
+@dataclasses.dataclass
+class SetpointEnergyCarbonRewardFunction:
+  """reward/setpoint_energy_carbon_reward.py:103-125: productivity minus weighted energy
+  cost and carbon cost, shifted and scaled (no regret normalisation, no rate caps)."""
+  max_productivity_personhour_usd: float
+  productivity_midpoint_delta: float
+  productivity_decay_stiffness: float
+  electricity_energy_cost: exogenous.ElectricityEnergyCost
+  natural_gas_energy_cost: exogenous.NaturalGasEnergyCost
+  energy_cost_weight: float
+  carbon_cost_weight: float
+  carbon_cost_factor: float
+  reward_normalizer_shift: float = 0.0
+  reward_normalizer_scale: float = 1.0
+
+
 class BoundedActionNormalizer:
   """Maps the agent's [-1, 1] onto [min_native_value, max_native_value]."""
 

@@ -168,7 +168,9 @@ int validate(const sbx_config& c) {
   if (c.solver != SBX_SOLVER_TF_JACOBI && c.solver != SBX_SOLVER_GAUSS_SEIDEL) return fail(nullptr, SBX_E_INVALID, "bad solver");
   if (c.discount_factor <= 0 || c.discount_factor > 1) return fail(nullptr, SBX_E_INVALID, "Discount factor must be in (0,1]");  // environment.py:446
   if (c.ahu_init_cooling_setpoint <= c.ahu_init_heating_setpoint) return fail(nullptr, SBX_E_INVALID, "cooling_air_temp_setpoint must greater than heating_air_temp_setpoint");  // air_handler.py:62-66
-  if (c.max_productivity_personhour_usd <= c.min_productivity_personhour_usd) return fail(nullptr, SBX_E_INVALID, "max productivity must exceed min productivity");
+  if (c.reward_kind != SBX_REWARD_REGRET && c.reward_kind != SBX_REWARD_ENERGY_CARBON) return fail(nullptr, SBX_E_INVALID, "bad reward_kind");
+  if (c.reward_kind == SBX_REWARD_REGRET && c.max_productivity_personhour_usd <= c.min_productivity_personhour_usd) return fail(nullptr, SBX_E_INVALID, "max productivity must exceed min productivity");
+  if (c.reward_kind == SBX_REWARD_ENERGY_CARBON && c.reward_normalizer_scale == 0.0) return fail(nullptr, SBX_E_INVALID, "reward_normalizer_scale must not be 0");
   return SBX_OK;
 }
 
@@ -213,6 +215,8 @@ void fill_params(sbx_handle h) {
   p.delta = c.productivity_midpoint_delta; p.stiff = c.productivity_decay_stiffness;
   p.wu = c.productivity_weight; p.wv = c.energy_cost_weight; p.ww = c.carbon_emission_weight;
   p.gas_carbon = c.gas_carbon_rate;
+  p.carbon_cost_factor = c.carbon_cost_factor; p.reward_shift = c.reward_normalizer_shift;
+  p.reward_scale = c.reward_normalizer_scale; p.reward_kind = c.reward_kind;
   p.discount = c.discount_factor; p.occ_norm = c.occupancy_normalization_constant;
   p.episode_steps = c.episode_steps;
   p.fd_only = 0;
@@ -637,10 +641,11 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(h->fd_ambient, double, B);
   ALLOC(h->fd_convection, double, B);
   ALLOC(h->d_action, float, B * (c.n_actions > 0 ? c.n_actions : 1));
-  ALLOC(h->d_obs, float, B * h->D);
-  ALLOC(h->d_reward, float, B);
-  ALLOC(h->d_step_type, int32_t, B);
-  ALLOC(h->d_discount, float, B);
+  // one block, [obs | reward | step_type | discount]: one DMA moves a whole TimeStep
+  ALLOC(h->d_obs, float, B * (h->D + 3));
+  h->d_reward = h->d_obs + B * h->D;
+  h->d_step_type = reinterpret_cast<int32_t*>(h->d_reward + B);
+  h->d_discount = h->d_reward + 2 * B;
 #undef ALLOC
   p.obs_mean = h->d_obs_mean; p.obs_var = h->d_obs_var; p.hist_bins = h->d_hist_bins;
   p.obs_inv_std = nullptr;
@@ -901,6 +906,13 @@ static int d2h(sbx_handle h, void* user, void* stage, const void* dev, size_t by
 
 static int copy_out(sbx_handle h, float* obs, float* reward, int32_t* step_type, float* discount) {
   const size_t B = h->cfg.n_envs;
+  // caller buffers laid out like the device block and page-locked: a single copy
+  if (obs && reward && step_type && discount && reward == obs + B * h->D &&
+      (void*)step_type == (void*)(reward + B) && discount == reward + 2 * B && is_pinned(obs)) {
+    CUDA_TRY(h, cudaMemcpyAsync(obs, h->d_obs, sizeof(float) * B * (h->D + 3), cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return SBX_OK;
+  }
   bool s_obs = false, s_rew = false, s_st = false, s_dis = false;
   if (obs) if (int rc = d2h(h, obs, h->h_obs, h->d_obs, sizeof(float) * B * h->D, &s_obs)) return rc;
   if (reward) if (int rc = d2h(h, reward, h->h_reward, h->d_reward, sizeof(float) * B, &s_rew)) return rc;

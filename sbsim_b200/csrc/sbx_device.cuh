@@ -80,6 +80,8 @@ struct Params {
   double vav_max_flow, vav_max_reheat;
   // reward
   double pmax, pmin, emax, gmax, delta, stiff, wu, wv, ww, gas_carbon;
+  double carbon_cost_factor, reward_shift, reward_scale;
+  int reward_kind;
   double discount, occ_norm;
   // static per plan
   const uint16_t* desc;      // [P,H,W]
@@ -792,22 +794,40 @@ __device__ inline void hvac_post(const Params& p, int b, int plan, int lane, uns
     gas = f32r(gas);
     const double pump = f32r(cy.boiler_flow * kWaterDensity * kGravity * p.boiler_head / p.boiler_eff);
 
-    const double max_p = p.pmax * occ_sum * dts / 3600.0;
-    const double min_p = p.pmin * occ_sum * dts / 3600.0;
-    const double actual = fmax(prod, min_p);
-    const double regret = occ_sum > 0.0 ? (actual - min_p) / (max_p - min_p) - 1.0 : 0.0;
-    const double e_rate = fmin(blower + fabs(ac) + pump, p.emax);
-    const double g_rate = fmin(gas, p.gmax);
     const double pe = p.price_e[s1], ce = p.carbon_e[s1], pg = p.price_g[s1];
-    const double cost_e = pe * fabs(e_rate) * dts, cost_e_max = pe * fabs(p.emax) * dts;
-    const double carb_e = ce * fabs(e_rate) * dts, carb_e_max = ce * fabs(p.emax) * dts;
-    const double g_pos = g_rate < 0.0 ? 0.0 : g_rate;
-    const double cost_g = pg * (g_pos * dts), cost_g_max = pg * (p.gmax * dts);
-    const double carb_g = p.gas_carbon * (g_pos * dts), carb_g_max = p.gas_carbon * (p.gmax * dts);
-    const double n_cost = (cost_e + cost_g) / (cost_e_max + cost_g_max);
-    const double n_carbon = (carb_e + carb_g) / (carb_e_max + carb_g_max);
-    const double raw = regret * p.wu - n_cost * p.wv - n_carbon * p.ww;
-    const float value = (float)(raw / (p.wu + p.wv + p.ww));
+    double regret = 0.0, n_cost = 0.0, n_carbon = 0.0, actual = prod;
+    float value;
+    if (p.reward_kind == SBX_REWARD_ENERGY_CARBON) {
+      // SetpointEnergyCarbonRewardFunction (setpoint_energy_carbon_reward.py:127-190):
+      // uncapped rates, absolute costs, carbon cost read back from a proto float
+      const double e_rate = blower + fabs(ac) + pump;   // base:125-148
+      const double cost_e = pe * fabs(e_rate) * dts;
+      const double carb_e = ce * fabs(e_rate) * dts;
+      const double g_pos = gas < 0.0 ? 0.0 : gas;
+      const double cost_g = pg * (g_pos * dts);
+      const double carb_g = p.gas_carbon * (g_pos * dts);
+      const double carbon_cost = f32r((carb_e + carb_g) * p.carbon_cost_factor);   // :174-176
+      const double raw = prod - p.wv * (cost_e + cost_g) - p.ww * carbon_cost;    // :178-183
+      value = (float)((raw - p.reward_shift) / p.reward_scale);                   // :185-187
+      n_cost = cost_e + cost_g;          // diagnostics: absolute USD / kg here
+      n_carbon = carb_e + carb_g;
+    } else {
+      const double max_p = p.pmax * occ_sum * dts / 3600.0;
+      const double min_p = p.pmin * occ_sum * dts / 3600.0;
+      actual = fmax(prod, min_p);
+      regret = occ_sum > 0.0 ? (actual - min_p) / (max_p - min_p) - 1.0 : 0.0;
+      const double e_rate = fmin(blower + fabs(ac) + pump, p.emax);
+      const double g_rate = fmin(gas, p.gmax);
+      const double cost_e = pe * fabs(e_rate) * dts, cost_e_max = pe * fabs(p.emax) * dts;
+      const double carb_e = ce * fabs(e_rate) * dts, carb_e_max = ce * fabs(p.emax) * dts;
+      const double g_pos = g_rate < 0.0 ? 0.0 : g_rate;
+      const double cost_g = pg * (g_pos * dts), cost_g_max = pg * (p.gmax * dts);
+      const double carb_g = p.gas_carbon * (g_pos * dts), carb_g_max = p.gas_carbon * (p.gmax * dts);
+      n_cost = (cost_e + cost_g) / (cost_e_max + cost_g_max);
+      n_carbon = (carb_e + carb_g) / (carb_e_max + carb_g_max);
+      const double raw = regret * p.wu - n_cost * p.wv - n_carbon * p.ww;
+      value = (float)(raw / (p.wu + p.wv + p.ww));
+    }
     const bool ended = p.step_count >= p.episode_steps;  // environment.py:1365-1368
     if (p.reward) p.reward[b] = value;
     if (p.step_type) p.step_type[b] = ended ? SBX_STEP_LAST : SBX_STEP_MID;

@@ -257,15 +257,27 @@ class Environment:
     cfg.vav_max_air_flow_rate = b.hvac.vav_max_air_flow_rate
     cfg.vav_reheat_max_water_flow_rate = b.hvac.vav_reheat_max_water_flow_rate
     rf = reward_function
-    cfg.max_productivity_personhour_usd = rf.max_productivity_personhour_usd
-    cfg.min_productivity_personhour_usd = rf.min_productivity_personhour_usd
-    cfg.max_electricity_rate = rf.max_electricity_rate
-    cfg.max_natural_gas_rate = rf.max_natural_gas_rate
-    cfg.productivity_midpoint_delta = rf.productivity_midpoint_delta
-    cfg.productivity_decay_stiffness = rf.productivity_decay_stiffness
-    cfg.productivity_weight = rf.productivity_weight
-    cfg.energy_cost_weight = rf.energy_cost_weight
-    cfg.carbon_emission_weight = rf.carbon_emission_weight
+    if isinstance(rf, config_lib.SetpointEnergyCarbonRewardFunction):
+      cfg.reward_kind = _lib.REWARD_ENERGY_CARBON
+      cfg.max_productivity_personhour_usd = rf.max_productivity_personhour_usd
+      cfg.productivity_midpoint_delta = rf.productivity_midpoint_delta
+      cfg.productivity_decay_stiffness = rf.productivity_decay_stiffness
+      cfg.energy_cost_weight = rf.energy_cost_weight
+      cfg.carbon_emission_weight = rf.carbon_cost_weight
+      cfg.carbon_cost_factor = rf.carbon_cost_factor
+      cfg.reward_normalizer_shift = rf.reward_normalizer_shift
+      cfg.reward_normalizer_scale = rf.reward_normalizer_scale
+    else:
+      cfg.reward_kind = _lib.REWARD_REGRET
+      cfg.max_productivity_personhour_usd = rf.max_productivity_personhour_usd
+      cfg.min_productivity_personhour_usd = rf.min_productivity_personhour_usd
+      cfg.max_electricity_rate = rf.max_electricity_rate
+      cfg.max_natural_gas_rate = rf.max_natural_gas_rate
+      cfg.productivity_midpoint_delta = rf.productivity_midpoint_delta
+      cfg.productivity_decay_stiffness = rf.productivity_decay_stiffness
+      cfg.productivity_weight = rf.productivity_weight
+      cfg.energy_cost_weight = rf.energy_cost_weight
+      cfg.carbon_emission_weight = rf.carbon_emission_weight
     cfg.gas_carbon_rate = rf.natural_gas_energy_cost.carbon_rate
     cfg.discount_factor = self.discount_factor
     cfg.occupancy_normalization_constant = self._occupancy_normalization_constant
@@ -295,9 +307,13 @@ class Environment:
     # Outputs land in page-locked host buffers (direct DMA, no staging memcpy).
     # Two sets alternate, so the arrays of a returned TimeStep stay valid until the
     # next-but-one reset()/step() call; copy them to keep them longer.
-    self._pinned = [[_lib.PinnedArray((B, D), np.float32), _lib.PinnedArray((B,), np.float32),
-                     _lib.PinnedArray((B,), np.int32), _lib.PinnedArray((B,), np.float32)]
-                    for _ in range(2)]
+    # two alternating sets; each set is ONE pinned block so a step's outputs come back
+    # in a single DMA (sbx_step_host recognises back-to-back buffers)
+    self._pinned_blocks, self._pinned = [], []
+    for _ in range(2):
+      block, views = _lib.pinned_time_step_arrays(B, D)
+      self._pinned_blocks.append(block)
+      self._pinned.append(views)
     self._pinned_action = _lib.PinnedArray((B, max(len(targets), 1)), np.float32)
     self._flip = 0
     self._bind_outputs()
@@ -428,8 +444,7 @@ class Environment:
     return self._handle
 
   def _bind_outputs(self):
-    self._obs, self._reward, self._step_type, self._discount = (
-        p.array for p in self._pinned[self._flip])
+    self._obs, self._reward, self._step_type, self._discount = self._pinned[self._flip]
 
   def _time_step(self) -> specs.TimeStep:
     ts = specs.TimeStep(step_type=self._step_type, reward=self._reward,

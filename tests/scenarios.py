@@ -78,6 +78,7 @@ class Scenario:
   discount: float = 0.9
   occupancy_norm: float = 3.0
   histogram: bool = False
+  reward: str = "regret"          # or "energy_carbon" (setpoint_energy_carbon_reward.py)
   schedule_tz: str = "UTC"
   occupancy: str = "step"      # "step" | "const"
   convection: Optional[tuple] = None   # (p, distance, seed) of StochasticConvectionSimulator
@@ -125,9 +126,12 @@ def make_oracle(sc: Scenario, cp: Optional[floorplan.CompiledPlan] = None,
                                                convection_coefficient=sc.convection_coefficient),
       schedule=ohvac.SetpointSchedule(6, 19, (294, 297), (289, 298), time_zone=sc.schedule_tz),
       occupancy=occ,
-      reward_function=orew.SetpointEnergyCarbonRegretFunction(
+      reward_function=(orew.SetpointEnergyCarbonRewardFunction(
+          300.0, 0.5, 4.3, oex.ElectricityEnergyCost(), oex.NaturalGasEnergyCost(),
+          1.5, 2.0, 0.3, 25.0, 400.0) if sc.reward == "energy_carbon" else
+                       orew.SetpointEnergyCarbonRegretFunction(
           300.0, 100.0, 160000, 400000, 0.5, 4.3, oex.ElectricityEnergyCost(),
-          oex.NaturalGasEnergyCost(), 0.2, 0.4, 0.4),
+          oex.NaturalGasEnergyCost(), 0.2, 0.4, 0.4)),
       solver=solver, time_step_sec=sc.time_step_sec,
       convergence_threshold=sc.convergence_threshold, iteration_limit=sc.iteration_limit,
       initial_temp=sc.initial_temp if initial_temp is None else initial_temp,
@@ -166,9 +170,14 @@ def make_env(sc: Scenario, n_envs: int = 1, plans=None, weather=None, initial_te
       reset_temp_values=sc.reset_temp_values,
       convection_simulator=(sbx.StochasticConvectionSimulator(*sc.convection)
                             if sc.convection else None), solver=solver)
-  reward = sbx.SetpointEnergyCarbonRegretFunction(
-      300.0, 100.0, 160000, 400000, 0.5, 4.3, sbx.ElectricityEnergyCost(),
-      sbx.NaturalGasEnergyCost(), 0.2, 0.4, 0.4)
+  if sc.reward == "energy_carbon":
+    reward = sbx.SetpointEnergyCarbonRewardFunction(
+        300.0, 0.5, 4.3, sbx.ElectricityEnergyCost(), sbx.NaturalGasEnergyCost(),
+        1.5, 2.0, 0.3, 25.0, 400.0)
+  else:
+    reward = sbx.SetpointEnergyCarbonRegretFunction(
+        300.0, 100.0, 160000, 400000, 0.5, 4.3, sbx.ElectricityEnergyCost(),
+        sbx.NaturalGasEnergyCost(), 0.2, 0.4, 0.4)
   return sbx.Environment(
       building, reward, sbx.StandardScoreObservationNormalizer(NORMALIZATION),
       sbx.ActionConfig({

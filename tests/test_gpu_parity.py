@@ -401,3 +401,32 @@ def test_pipelined_step_equals_single_launch_step_and_timing():
   finally:
     for e in envs:
       e.close()
+
+
+def test_energy_carbon_reward_function_matches_oracle():
+  """SetpointEnergyCarbonRewardFunction (setpoint_energy_carbon_reward.py:127-190, SURVEY
+  section 8f rank 4): productivity - w_e * cost - w_c * carbon cost, shifted and scaled."""
+  sc = S.Scenario(floor_plan=S.small_plan(), reward="energy_carbon", occupancy="step",
+                  start="2023-07-06 07:30:00")
+  cp = sc.compiled()
+  B = 2
+  env = S.make_env(sc, n_envs=B, plans=cp)
+  try:
+    oracles = [S.make_oracle(sc, cp) for _ in range(B)]
+    env.reset()
+    for o in oracles:
+      o.reset()
+    rng = np.random.default_rng(3)
+    seen = set()
+    for step in range(40):
+      a = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+      ts = env.step(a)
+      for b, o in enumerate(oracles):
+        ots = o.step(a[b])
+        np.testing.assert_allclose(ts.reward[b], ots[1], rtol=RTOL, atol=1e-6,
+                                   err_msg=f"reward step {step} env {b}")
+        np.testing.assert_allclose(ts.observation[b], ots[3], rtol=RTOL, atol=2e-5)
+        seen.add(round(float(ots[1]), 3))
+    assert len(seen) > 5          # the reward actually varies over the rollout
+  finally:
+    env.close()

@@ -138,3 +138,42 @@ def test_oracle_tf_jacobi_on_calibrated_plan_matches_reference(calibrated_plan):
   np.testing.assert_array_equal(temp[::31, ::37], r["temp_sample"])
   np.testing.assert_array_equal(temp[[100, 372, 600], :], r["temp_rows"])
   assert float(temp.astype(np.float64).sum()) == float(r["temp_sum"])
+
+
+class _FlatEnergyCost:
+  """TestEnergyCost of setpoint_energy_carbon_reward_test.py:232-254."""
+
+  def __init__(self, usd_per_kwh, kg_per_kwh):
+    self._p = usd_per_kwh / 3600.0 / 1000.0
+    self._c = kg_per_kwh / 3600.0 / 1000.0
+
+  def cost(self, start, end, rate):
+    return self._p * rate * (end - start).total_seconds()
+
+  def carbon(self, start, end, rate):
+    return self._c * rate * (end - start).total_seconds()
+
+
+@pytest.mark.parametrize("temp,occ,blower,ac,gas,pump,want", [
+    # setpoint_energy_carbon_reward_test.py:30-112 (reward, productivity, elec cost, gas cost,
+    # carbon emitted, carbon cost); the reference's info has two of every device
+    (293.0, 10.0, 500.0, 2500.0, 20000.0, 250.0, (0.11660, 5000.0 / 6, 0.102916665, 0.1, 0.63208336, 0.12641667)),
+    (293.0, 0.0, 500.0, 2500.0, 20000.0, 250.0, (-0.050065, 0.0, 0.102916665, 0.1, 0.63208336, 0.12641667)),
+    (292.0, 10.0, 500.0, 2500.0, 20000.0, 250.0, (0.099212, 746.3906, 0.102916665, 0.1, 0.63208336, 0.12641667)),
+    (299.0, 10.0, 500.0, 2500.0, 20000.0, 250.0, (-0.0326773, 86.942687, 0.102916665, 0.1, 0.63208336, 0.12641667)),
+    (293.0, 10.0, 0.0, 0.0, 0.0, 0.0, (0.116666, 5000.0 / 6, 0.0, 0.0, 0.0, 0.0)),
+])
+def test_energy_carbon_reward_reference_known_answers(temp, occ, blower, ac, gas, pump, want):
+  fn = orew.SetpointEnergyCarbonRewardFunction(
+      500.0, 1.5, 4.3, _FlatEnergyCost(0.19, 0.01), _FlatEnergyCost(0.03, 0.188),
+      1.0, 1.0, 0.2, 250.0, 500.0 * 10)
+  f32 = orew.f32
+  zone = orew.ZoneRewardInfo(f32(293.0), f32(297.0), f32(temp), f32(0.013), f32(0.012), f32(occ))
+  info = orew.RewardInfo(
+      pd.Timestamp("2021-05-03 12:13:00-05:00"), pd.Timestamp("2021-05-03 12:18:00-05:00"),
+      [zone, zone], 2 * blower, 2 * ac, 2 * gas, 2 * pump)
+  r = fn.compute_reward(info)
+  got = (r.agent_reward_value, r.productivity_reward, r.electricity_energy_cost,
+         r.natural_gas_energy_cost, r.carbon_emitted, r.carbon_cost)
+  for g, w in zip(got, want):
+    assert abs(g - w) < 0.5e-4, (got, want)     # assertAlmostEqual(..., 4)

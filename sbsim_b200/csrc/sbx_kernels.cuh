@@ -20,6 +20,14 @@ namespace sbx {
 constexpr int kResidentThreads = 512;
 constexpr int kStreamThreads = 256;
 constexpr int kStreamRowsPerWarp = 8;
+#ifndef SBX_SWEEP_MIN_CTAS
+#define SBX_SWEEP_MIN_CTAS 4      // k_sweep: <= 64 registers, 32 warps per SM
+#endif
+#ifndef SBX_SWEEP_UNROLL
+#define SBX_SWEEP_UNROLL 2
+#endif
+#define SBX_STR_(x) #x
+#define SBX_STR(x) SBX_STR_(x)
 
 template <int V>
 struct Vec;
@@ -1116,7 +1124,7 @@ __global__ void k_pack_stream(const Params p) {
 // Every class of CV runs the same instruction stream (cv_update_packed): warps that
 // mix interior / wall / boundary / exterior CVs do not diverge.
 template <int V>
-__global__ void __launch_bounds__(kStreamThreads, 4) k_sweep(const Params p, const int k) {
+__global__ void __launch_bounds__(kStreamThreads, SBX_SWEEP_MIN_CTAS) k_sweep(const Params p, const int k) {
   __shared__ Combo tab[kNumCombos];
   __shared__ float qcv[kMaxZones + 1];
   const StreamTiling tl = stream_tiling(p.H, p.W, V);
@@ -1161,7 +1169,7 @@ __global__ void __launch_bounds__(kStreamThreads, 4) k_sweep(const Params p, con
       if (r0 > 0) load_f<V>(tin + off - W, up);
       load_f<V>(tin + off, c);
     }
-#pragma unroll 2
+_Pragma(SBX_STR(unroll SBX_SWEEP_UNROLL))
     for (int r = r0; r < r1; ++r, off += W) {
       fill<V>(dn, t_inf);
       if (col_ok && r + 1 < H) load_f<V>(tin + off + W, dn);

@@ -206,6 +206,9 @@ def run_sbx(args):
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   if world > 1:
+    # NCCL prints its version banner on stdout when NCCL_DEBUG is set (as on the GPU box);
+    # stdout carries exactly one JSON line, so send NCCL's own output to stderr
+    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
   line = _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu=True)
   # The other single-GPU configurations of BASELINE.json, measured briefly beside the

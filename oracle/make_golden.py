@@ -21,6 +21,8 @@ Fixtures
                        actions, observations, rewards, zone temperatures, final field.
   ref_env_hist.npz     same with the histogram observation reducer (D = 53 layout).
   ref_tf_calibrated.npz  one reset + 2 FD steps of TFSimulator on the calibrated plan.
+  ref_env_ecr.npz      ref_env_tf's scenario with SetpointEnergyCarbonRewardFunction
+                       (reward/setpoint_energy_carbon_reward.py) instead of the regret reward.
 """
 
 from __future__ import annotations
@@ -74,7 +76,7 @@ def _ref_modules():
       bl="simulator.boiler", ss="simulator.setpoint_schedule",
       wc="simulator.weather_controller", sb="simulator.simulator_building",
       occ="simulator.step_function_occupancy", sffp="simulator.simulator_flexible_floor_plan",
-      regret="reward.setpoint_energy_carbon_regret", elec="reward.electricity_energy_cost",
+      regret="reward.setpoint_energy_carbon_regret", ecr="reward.setpoint_energy_carbon_reward", elec="reward.electricity_energy_cost",
       gas="reward.natural_gas_energy_cost", env="environment.environment",
       onorm="utils.observation_normalizer", anorm="utils.bounded_action_normalizer",
       npb="proto.smart_control_normalization_pb2", hist="utils.histogram_reducer")
@@ -82,7 +84,7 @@ def _ref_modules():
           for k, v in names.items()}
 
 
-def build_reference_env(m, plan, solver, histogram=False):
+def build_reference_env(m, plan, solver, histogram=False, reward="regret"):
   """The scenario of tests/scenarios.py:Scenario() built from reference classes."""
   b = m["building"].FloorPlanBasedBuilding(
       cv_size_cm=20.0, floor_height_cm=300.0, initial_temp=292.0,
@@ -108,6 +110,10 @@ def build_reference_env(m, plan, solver, histogram=False):
   rf = m["regret"].SetpointEnergyCarbonRegretFunction(
       300.0, 100.0, 160000, 400000, 0.5, 4.3, m["elec"].ElectricityEnergyCost(),
       m["gas"].NaturalGasEnergyCost(), 0.2, 0.4, 0.4)
+  if reward == "energy_carbon":      # the parameters of tests/scenarios.py
+    rf = m["ecr"].SetpointEnergyCarbonRewardFunction(
+        300.0, 0.5, 4.3, m["elec"].ElectricityEnergyCost(), m["gas"].NaturalGasEnergyCost(),
+        1.5, 2.0, 0.3, 25.0, 400.0)
   norm = {k: m["npb"].ContinuousVariableInfo(id=k, sample_mean=mu, sample_variance=var)
           for k, (mu, var) in NORMALIZATION.items()}
   on = m["onorm"].StandardScoreObservationNormalizer(norm)
@@ -127,9 +133,9 @@ def build_reference_env(m, plan, solver, histogram=False):
   return env, b
 
 
-def make_env_rollout(m, solver, histogram, n_steps, seed):
+def make_env_rollout(m, solver, histogram, n_steps, seed, reward="regret"):
   plan = small_plan()
-  env, b = build_reference_env(m, plan, solver, histogram)
+  env, b = build_reference_env(m, plan, solver, histogram, reward)
   rng = np.random.default_rng(seed)
   ts = env.reset()
   obs, rew, stype, disc, zts, acts, blr, ahu = [ts.observation], [0.0], [0], [1.0], [], [], [], []
@@ -253,6 +259,8 @@ def main():
   np.savez_compressed(os.path.join(OUT, "ref_env_tf.npz"), **make_env_rollout(m, "tf", False, 40, 0))
   np.savez_compressed(os.path.join(OUT, "ref_env_gs.npz"), **make_env_rollout(m, "gs", False, 25, 1))
   np.savez_compressed(os.path.join(OUT, "ref_env_hist.npz"), **make_env_rollout(m, "tf", True, 40, 2))
+  np.savez_compressed(os.path.join(OUT, "ref_env_ecr.npz"),
+                      **make_env_rollout(m, "tf", False, 60, 3, reward="energy_carbon"))
   np.savez_compressed(os.path.join(OUT, "ref_gs_golden.npz"), **make_gs_golden(m))
   sb1, cal = make_sb1(m)
   np.savez_compressed(os.path.join(OUT, "sb1_calibrated.npz"), **sb1)

@@ -23,12 +23,13 @@ def _load(name):
   return np.load(os.path.join(GOLD, name), allow_pickle=False)
 
 
-@pytest.mark.parametrize("name,solver,histogram", [
-    ("ref_env_tf.npz", "tf", False), ("ref_env_hist.npz", "tf", True),
-    ("ref_env_gs.npz", "gs", False)])
-def test_oracle_env_matches_reference_rollout(name, solver, histogram):
+@pytest.mark.parametrize("name,solver,histogram,reward", [
+    ("ref_env_tf.npz", "tf", False, "regret"), ("ref_env_hist.npz", "tf", True, "regret"),
+    ("ref_env_gs.npz", "gs", False, "regret"), ("ref_env_ecr.npz", "tf", False, "energy_carbon")])
+def test_oracle_env_matches_reference_rollout(name, solver, histogram, reward):
   g = _load(name)
-  sc = S.Scenario(floor_plan=g["floor_plan"].astype(np.int64), histogram=histogram)
+  sc = S.Scenario(floor_plan=g["floor_plan"].astype(np.int64), histogram=histogram,
+                  reward=reward)
   o = S.make_oracle(sc, solver=solver)
   ts = o.reset()
   np.testing.assert_allclose(ts[3], g["observations"][0], rtol=1e-6, atol=1e-7)

@@ -17,7 +17,10 @@
 
 namespace sbx {
 
-constexpr int kResidentThreads = 512;
+#ifndef SBX_RESIDENT_THREADS
+#define SBX_RESIDENT_THREADS 512
+#endif
+constexpr int kResidentThreads = SBX_RESIDENT_THREADS;
 constexpr int kStreamThreads = 256;
 constexpr int kStreamRowsPerWarp = 8;
 #ifndef SBX_SWEEP_MIN_CTAS

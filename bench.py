@@ -206,9 +206,6 @@ def run_sbx(args):
   torch.cuda.set_device(local_rank)
   dev = torch.device("cuda", local_rank)
   if world > 1:
-    # NCCL prints its version banner on stdout when NCCL_DEBUG is set (as on the GPU box);
-    # stdout carries exactly one JSON line, so send NCCL's own output to stderr
-    os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")
     dist.init_process_group("nccl", device_id=dev)
   line = _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu=True)
   # The other single-GPU configurations of BASELINE.json, measured briefly beside the
@@ -228,7 +225,7 @@ def run_sbx(args):
                        "error": f"{type(e).__name__}: {e}"})
     line["other_configs"] = others
   if rank == 0:
-    print(json.dumps(line), flush=True)
+    emit(line)
   if world > 1:
     dist.destroy_process_group()
 
@@ -442,8 +439,8 @@ def run_reference(args):
   from oracle import bench_support
   from sbsim_b200 import workloads
   if args.workload != "randomized":
-    print(json.dumps({"impl": "reference", "unavailable":
-                      "reference arm implemented for the randomized workload only"}))
+    emit({"impl": "reference", "unavailable":
+          "reference arm implemented for the randomized workload only"})
     return
   cores = bench_support.host_cores()
   n = args.cpu_sample_envs or min(max(cores * 128, 256), 4096)
@@ -466,11 +463,34 @@ def run_reference(args):
                                  f"{wall:.1f} s wall, {sweeps:.2f} sweeps/step)"},
       "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
   }
-  print(json.dumps(line), flush=True)
+  emit(line)
+
+
+_REAL_STDOUT = None
+
+
+def protect_stdout():
+  """stdout carries exactly ONE JSON line.  Libraries print there too (NCCL's version
+  banner with NCCL_DEBUG=VERSION, as on the GPU box), so file descriptor 1 is pointed at
+  stderr for the whole run and the JSON line goes to the saved descriptor."""
+  global _REAL_STDOUT
+  sys.stdout.flush()
+  _REAL_STDOUT = os.dup(1)
+  os.dup2(2, 1)
+
+
+def emit(line):
+  data = (json.dumps(line) + "\n").encode()
+  if _REAL_STDOUT is None:
+    sys.stdout.write(data.decode())
+    sys.stdout.flush()
+  else:
+    os.write(_REAL_STDOUT, data)
 
 
 def main():
   args = parse_args()
+  protect_stdout()
   if args.impl == "reference":
     run_reference(args)
   else:

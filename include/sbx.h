@@ -45,6 +45,7 @@ extern "C" {
 #define SBX_E_STATE (-3)     /* call not valid in the current episode state */
 #define SBX_E_NOMEM (-4)
 
+#define SBX_PHASE_WORDS 264
 #define SBX_MAX_ACTIONS 3
 #define SBX_MAX_HIST_BINS 32
 #define SBX_N_DEVICE_FIELDS 15 /* 9 AHU + 3 boiler + 3 VAV measurement names */
@@ -226,8 +227,10 @@ enum {
   SBX_F_Q_ZONE = 63,       /* f64 [B,Z]  VAV thermal power per zone computed this step */
   SBX_F_ZONE_SUPPLY_TEMP = 64, /* f64 [B,Z] */
   SBX_F_PRE_ZONE_MEAN = 65,/* f32 [B,Z]  zone means the thermostats saw this step */
-  SBX_F_PHASE_CYCLES = 66  /* u64 [8]    per-phase SM cycles of the resident kernel, summed over CTAs;
-                              only filled by builds with -DSBX_PROFILE_PHASES (profiling aid) */
+  SBX_F_PHASE_CYCLES = 66  /* u64 [SBX_PHASE_WORDS]  [0..7] per-phase SM cycles of the resident kernel, summed over
+                              CTAs; [8..] per-warp barrier-arrival timestamps of ONE probe CTA (warp w, sweep k <= 3:
+                              word 8 + w*8 + 2*(k-1) = cycles from CTA start to the warp reaching the sweep's
+                              barrier, +1 = to leaving it); only filled by builds with -DSBX_PROFILE_PHASES */
 };
 
 enum {

@@ -15,15 +15,26 @@ act = torch.rand(40, B, 2, device=dev) * 2 - 1
 for i in range(5):
   env.step_device(act[i], obs, rew, st, dis)
 torch.cuda.synchronize()
-env.handle.upload("phase_cycles", np.zeros(8, dtype=np.uint64))
+W = 264
+env.handle.upload("phase_cycles", np.zeros(W, dtype=np.uint64))
 K = 20
 for i in range(K):
   env.step_device(act[5 + i], obs, rew, st, dis)
 torch.cuda.synchronize()
-cyc = env.handle.download("phase_cycles", (8,)).astype(np.float64)
+raw = env.handle.download("phase_cycles", (W,)).astype(np.float64)
+cyc = raw[:8]
 names = ["prologue (TMA issued)", "wait TMA load", "sweep 1 (+n3)", "sweeps 2..n", "store issue (+gather)",
          "zone sums (warp 0)", "barrier after sums"]
 tot = cyc[:7].sum()
 for n, c in zip(names, cyc):
   print(f"{n:28s} {c / (B * K):9.0f} cycles/CTA  {100 * c / tot:5.1f}%")
 print(f"total {tot / (B * K):.0f} cycles/CTA = {tot / (B * K) / 1.965e3:.2f} us at 1.965 GHz")
+
+# the probe CTA (building B/2, last step): cycles from CTA start to each warp ARRIVING at the
+# barrier that ends sweep k, and to LEAVING it (= the slowest warp's arrival)
+probe = raw[8:8 + 16 * 8].reshape(16, 8)
+for k in range(3):
+  arr, leave = probe[:, 2 * k], probe[:, 2 * k + 1]
+  if leave.max() == 0:
+    continue
+  print(f"sweep {k + 1}: arrivals " + " ".join(f"{int(a):6d}" for a in arr) + f" | released at {int(leave.max())}")

@@ -654,7 +654,7 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.active, uint8_t, B);
   ALLOC(p.n_active, int32_t, 1);
   ALLOC(p.sweeps_total, unsigned long long, 1);
-  ALLOC(p.phase_cycles, unsigned long long, 8);
+  ALLOC(p.phase_cycles, unsigned long long, SBX_PHASE_WORDS);
   ALLOC(h->carry, CarryStore, B);
   ALLOC(h->fd_ambient, double, B);
   ALLOC(h->fd_convection, double, B);
@@ -794,7 +794,7 @@ static int field_info(sbx_handle h, int field, FieldInfo* fi) {
     F(SBX_F_Q_ZONE, p.q_zone, B * Z, double, false);
     F(SBX_F_ZONE_SUPPLY_TEMP, p.zone_supply, B * Z, double, false);
     F(SBX_F_PRE_ZONE_MEAN, p.pre_zone_mean, B * Z, float, false);
-    F(SBX_F_PHASE_CYCLES, p.phase_cycles, 8, unsigned long long, true);
+    F(SBX_F_PHASE_CYCLES, p.phase_cycles, SBX_PHASE_WORDS, unsigned long long, true);
     default: break;
   }
 #undef F

@@ -21,6 +21,11 @@ namespace sbx {
 #define SBX_RESIDENT_THREADS 512
 #endif
 constexpr int kResidentThreads = SBX_RESIDENT_THREADS;
+// register-resident HEAD vectors per thread (see HeadVec)
+#ifndef SBX_RESIDENT_HEADS
+#define SBX_RESIDENT_HEADS (SBX_RESIDENT_THREADS <= 256 ? 4 : 2)
+#endif
+constexpr int kHeads = SBX_RESIDENT_HEADS;
 constexpr int kStreamThreads = 256;
 constexpr int kStreamRowsPerWarp = 8;
 #ifndef SBX_SWEEP_MIN_CTAS
@@ -515,6 +520,36 @@ __device__ __forceinline__ float fast_vector4(const float* __restrict__ in, floa
   return lmax;
 }
 
+// A thread's HEAD vectors (its first two list entries, FAST by construction when the list
+// holds two rounds of FAST vectors) are the same in every sweep: their own temperatures and
+// thermal-mass terms stay in REGISTERS from sweep to sweep -- no shared-memory load of the
+// centre or of n3, no n3 store -- and only the new temperatures go to shared memory for
+// the neighbours.  The shared-memory pipe is ~70 % busy in this kernel.
+struct HeadVec {
+  float4 c;          // T_est of the vector (this sweep's input)
+  f32x2 n3a, n3b;    // (cm * T_prev) / dt of its two pairs
+  int base;          // CV index of the vector in the planes
+};
+template <bool FIRST>
+__device__ __forceinline__ float fast_head4(const float* __restrict__ in, float* __restrict__ out,
+                                            HeadVec& hv, int W, const FastCoef2& fc2, float kq1) {
+  const int base = hv.base;
+  if constexpr (FIRST) {
+    hv.c = *reinterpret_cast<const float4*>(in + base);
+    hv.n3a = div_rn2(mul2(fc2.cm, pack2(hv.c.x, hv.c.y)), fc2.ndt, fc2.rdt);
+    hv.n3b = div_rn2(mul2(fc2.cm, pack2(hv.c.z, hv.c.w)), fc2.ndt, fc2.rdt);
+  }
+  const float4 up4 = *reinterpret_cast<const float4*>(in + base - W);
+  const float4 dn4 = *reinterpret_cast<const float4*>(in + base + W);
+  const float left = in[base - 1];
+  const float right = in[base + 4];
+  float4 o4;
+  const float lmax = fast_core4(hv.c, up4, dn4, left, right, hv.n3a, hv.n3b, fc2, kq1, 0.f, o4);
+  *reinterpret_cast<float4*>(out + base) = o4;
+  hv.c = o4;         // next sweep's input
+  return lmax;
+}
+
 // Per-material coefficients of an interior-class CV (header, MEDIUM list)
 struct MedCoef {
   float kq, cm, den, rden;
@@ -541,7 +576,8 @@ struct SweepCtx {
 };
 template <int V, bool FIRST>
 __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, float* __restrict__ out,
-                                                float* __restrict__ n3p, const SweepCtx& s, int tid) {
+                                                float* __restrict__ n3p, const SweepCtx& s, int tid,
+                                                HeadVec (&heads)[kHeads]) {
   constexpr int NT = kResidentThreads;
   const int W = s.P, wq = s.wq;      // W: row pitch in CVs
   const float t_inf = s.t_inf;
@@ -551,13 +587,20 @@ __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, fl
     // Every thread's first two vectors are FAST when the list holds two rounds of them:
     // run them as ONE instruction stream (two independent dependency chains), the
     // sweeps being latency-bound at 8 warps per scheduler.
-    if (s.n_fast >= 2 * NT) {
-      const int base0 = ((int)s.qlist[u] & 0x7FFF) * V, base1 = ((int)s.qlist[u + NT] & 0x7FFF) * V;
-      const float l0 = fast_vector4<FIRST>(in, out, n3p, base0, W, s.fc2, s.fc.kq, 0.f);
-      const float l1 = fast_vector4<FIRST>(in, out, n3p, base1, W, s.fc2, s.fc.kq, 0.f);
-      lmax = fmaxf(l0, l1);
-      u += 2 * NT;
+    // as many head rounds as the FAST list fills completely (uniform over the CTA)
+    const int nh = min(kHeads, s.n_fast / NT);
+    float lh[kHeads];
+#pragma unroll
+    for (int j = 0; j < kHeads; ++j) {
+      lh[j] = 0.f;
+      if (j < nh) {
+        if constexpr (FIRST) heads[j].base = ((int)s.qlist[u + j * NT] & 0x7FFF) * V;
+        lh[j] = fast_head4<FIRST>(in, out, heads[j], W, s.fc2, s.fc.kq);
+      }
     }
+#pragma unroll
+    for (int j = 0; j < kHeads; ++j) lmax = fmaxf(lmax, lh[j]);
+    u += nh * NT;
   }
   for (; u < s.n_items; u += NT) {
     const int entry = (int)s.qlist[u];
@@ -684,6 +727,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   extern __shared__ __align__(128) unsigned char smem[];
 #ifdef SBX_PROFILE_PHASES
   long long phase_t0__ = clock64();
+  const long long cta_t0__ = phase_t0__;
 #endif
   const int b = p.b_begin + blockIdx.x;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -799,17 +843,33 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   // ---- stage 2: Jacobi sweeps to convergence (simulator.py:348-364) ---------
   float* in = bufA;
   float* out = bufB;
+  HeadVec heads[kHeads];
+#pragma unroll
+  for (int j = 0; j < kHeads; ++j) {
+    heads[j].c = make_float4(0.f, 0.f, 0.f, 0.f);
+    heads[j].n3a = heads[j].n3b = 0ull;
+    heads[j].base = 0;
+  }
   int k = 0;
   float md = 0.f, last_lmax = 0.f;
   const int limit = p.iteration_limit;
   while (k < limit) {
     ++k;
     float lmax;
-    if (k == 1) lmax = resident_sweep<V, true>(in, out, n3p, sc, tid);
-    else lmax = resident_sweep<V, false>(in, out, n3p, sc, tid);
+    if (k == 1) lmax = resident_sweep<V, true>(in, out, n3p, sc, tid, heads);
+    else lmax = resident_sweep<V, false>(in, out, n3p, sc, tid, heads);
     // max|dT| <= threshold  <=>  no thread saw a delta above it (simulator.py:362);
     // the barrier doubles as the ping-pong hazard fence.
+#ifdef SBX_PROFILE_PHASES
+    const long long t_arrive__ = clock64();
+#endif
     const int above = __syncthreads_or(lmax > p.threshold);
+#ifdef SBX_PROFILE_PHASES
+    if (b == p.B / 2 && lane == 0 && k <= 3 && !p.fd_only) {   // one probe CTA: who waits for whom
+      p.phase_cycles[8 + warp * 8 + 2 * (k - 1)] = (unsigned long long)(t_arrive__ - cta_t0__);
+      p.phase_cycles[8 + warp * 8 + 2 * (k - 1) + 1] = (unsigned long long)(clock64() - cta_t0__);
+    }
+#endif
     last_lmax = lmax;
     float* tmp = in; in = out; out = tmp;
     if (k == 1) SBX_PHASE(2); else SBX_PHASE(3);   // first sweep (computes n3) / later sweeps

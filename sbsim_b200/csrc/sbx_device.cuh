@@ -115,7 +115,7 @@ struct Params {
   const double* price_g;
   const double* time_feat;   // [T,4]
   const double* obs_mean;    // [15]
-  const double* obs_inv_std; // unused slot kept for layout clarity
+  const double* obs_sd;      // [15] sqrt(variance), taken once on the host (IEEE sqrt: the same double)
   const double* obs_var;     // [15]
   const double* hist_bins;   // [3,SBX_MAX_HIST_BINS]
   // state
@@ -607,7 +607,7 @@ struct Carry {
 __device__ inline float normalize(const Params& p, int field, double native) {
   const double v = f32r(native);
   const double var = p.obs_var[field];
-  if (var > 0.0) return (float)((v - p.obs_mean[field]) / sqrt(var));
+  if (var > 0.0) return (float)((v - p.obs_mean[field]) / p.obs_sd[field]);   // / np.sqrt(variance)
   return 0.f;
 }
 

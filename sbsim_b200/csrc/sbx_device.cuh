@@ -266,11 +266,6 @@ __device__ __forceinline__ int combo_index(uint32_t d) {
   return desc_class(d) * kNumMaterials + desc_material(d);
 }
 
-// thermal-mass coefficient cm of a CV (for the n3 term)
-__device__ __forceinline__ float cv_cm(uint32_t d, const Combo* tab) {
-  return tab[combo_index(d)].cm;
-}
-
 // One CV update (tf_simulator.py:719-754, 843, 847-849), branch-free: every
 // class runs the same instruction stream with its own coefficients, so warps that
 // mix interior / wall / boundary / exterior CVs do not diverge.  Two 128-bit
@@ -326,22 +321,6 @@ __device__ __forceinline__ float cv_divide_packed(uint32_t d, float num, float t
   const float2 dr = *reinterpret_cast<const float2*>(&tab[idx].den);
   const float t = div_rn(num, dr.x, dr.y);
   return idx < kNumMaterials ? t_inf : t;
-}
-
-// same update from a raw descriptor (streaming path)
-__device__ __forceinline__ float cv_update(uint32_t d, float t_jp, float t_jm, float t_im,
-                                           float t_ip, float n3, float q, float t_inf,
-                                           const Combo* tab) {
-  const Combo& c = tab[combo_index(d)];
-  float n1 = add(mul(c.k1, t_jp), mul(c.k3, t_jm));
-  n1 = add(n1, c.hh);
-  n1 = mul(c.vz, n1);
-  float n2 = add(mul(c.k2, t_ip), mul(c.k4, t_im));
-  n2 = add(n2, c.hv);
-  n2 = mul(c.uz, n2);
-  const float num = add(add(add(n1, n2), n3), q);
-  const float t = div_rn(num, c.den, c.rden);
-  return desc_class(d) == SBX_CV_EXTERIOR ? t_inf : t;
 }
 
 // Interior CV of the dominant material with no heat input: coefficients are

@@ -223,28 +223,6 @@ __host__ inline ResidentGeom resident_geom(int H, int W, int Z, int V) {
   return g;
 }
 
-// Accumulates V consecutive CVs into per-zone shared bins (fixed point) + grid total.
-// (streaming path: one atomic per run of equal zone ids)
-template <int V>
-__device__ __forceinline__ void zone_accumulate(const float (&t)[V], const uint32_t (&d)[V],
-                                                long long* bins, long long& total) {
-  int z0 = desc_zone(d[0]);
-  long long run = 0;
-#pragma unroll
-  for (int e = 0; e < V; ++e) {
-    const int z = desc_zone(d[e]);
-    const long long v = to_fix(t[e]);
-    total += v;
-    if (z != z0) {
-      if (z0 != SBX_ZONE_NONE) fix_add(&bins[z0], run);
-      z0 = z;
-      run = 0;
-    }
-    run += v;
-  }
-  if (z0 != SBX_ZONE_NONE) fix_add(&bins[z0], run);
-}
-
 // Packed descriptor: combo index (5 bits) | diffuser flag | zone.
 __device__ __forceinline__ uint32_t repack_desc(uint32_t d) {
   const int cls = desc_class(d);
@@ -1329,8 +1307,8 @@ __global__ void __launch_bounds__(256) k_prepare_tiles(const Params p) {
   const uint16_t* raw = p.desc + (size_t)plan * p.H * p.W;
   uint16_t* list = p.tlist + ((size_t)plan * tg.tiles + tile) * kTileEntries;
   __shared__ int s_fast[8], s_other[8];
-  __shared__ int s_base_fast, s_base_other;
-  if (tid == 0) { s_base_fast = 0; s_base_other = 0; }
+  __shared__ int s_base_other;
+  if (tid == 0) s_base_other = 0;
   __syncthreads();
   // two passes of counting + writing per class keep raster order without sorting
   for (int pass = 0; pass < 2; ++pass) {                // 0: count, 1: write

@@ -314,8 +314,22 @@ int run_stream_sweeps(sbx_handle h, cudaStream_t st) {
     if (h->list_sweep) {
       const TileGrid tg = tile_grid(p.H, p.W);
       k_sweep_list<<<(unsigned)((size_t)tg.tiles * p.B), 256, 0, st>>>(p, k);
-    } else if (h->V == 4) k_sweep<4><<<grid, kStreamThreads, 0, st>>>(p, k);
-    else k_sweep<1><<<grid, kStreamThreads, 0, st>>>(p, k);
+    } else {
+#define SBX_SWEEP_CASE(R)                                                          \
+  case R:                                                                          \
+    if (h->V == 4) k_sweep<4, R><<<grid, kStreamThreads, 0, st>>>(p, k);           \
+    else k_sweep<1, R><<<grid, kStreamThreads, 0, st>>>(p, k);                     \
+    break
+      switch (tl.rows_per_warp) {
+        SBX_SWEEP_CASE(8);
+        SBX_SWEEP_CASE(16);
+        SBX_SWEEP_CASE(32);
+        SBX_SWEEP_CASE(48);
+        default:
+          SBX_SWEEP_CASE(64);
+      }
+#undef SBX_SWEEP_CASE
+    }
     if (int rc = launch_check(h, "k_sweep")) return rc;
     if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
     CUDA_TRY(h, cudaMemsetAsync(p.n_active, 0, sizeof(int32_t), st));
@@ -472,7 +486,7 @@ int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_
     CUDA_TRY(h, cudaStreamWaitEvent(st, h->ev_join, 0));
     p.b_begin = 0; p.b_end = p.B; p.build_hdr = 0;
   } else {
-    p.build_hdr = (jacobi_resident || h->list_sweep) ? 1 : 0;
+    p.build_hdr = h->cfg.solver == SBX_SOLVER_TF_JACOBI ? 1 : 0;   // both Jacobi paths read the header
     if (int rc = launch_pre(h, st)) return rc;
     p.build_hdr = 0;
     if (h->path == SBX_PATH_RESIDENT) {
@@ -1003,7 +1017,7 @@ int sbx_fd_step(sbx_handle h, const double* ambient, const double* convection) {
     if (!rc) rc = run_resident(h, h->stream, true);
   } else {
     rc = SBX_OK;
-    if (h->list_sweep) {             // the list-driven sweep reads the per-building solve header
+    {                                // the sweeps read the per-building solve header
       const int wpb = 4;
       k_build_header<<<(unsigned)((p.B + wpb - 1) / wpb), wpb * 32, 0, h->stream>>>(p);
       rc = launch_check(h, "k_build_header");

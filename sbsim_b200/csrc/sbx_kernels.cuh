@@ -27,7 +27,17 @@ constexpr int kResidentThreads = SBX_RESIDENT_THREADS;
 #endif
 constexpr int kHeads = SBX_RESIDENT_HEADS;
 constexpr int kStreamThreads = 256;
-constexpr int kStreamRowsPerWarp = 8;
+// Rows per warp of the streaming kernels: chosen per grid height so that a CTA column of
+// 8 warps covers the height in few, evenly filled tiles (long strips amortise the 2 halo
+// rows and the per-CTA set-up: 74 % of the HBM roofline at 47 rows against 65 % at 8).
+constexpr int kStreamMaxRowsPerWarp = 64;
+__host__ __device__ inline int stream_rows_per_warp(int H) {
+  const int warps = 256 / 32;
+  const int n_tiles = (H + warps * kStreamMaxRowsPerWarp - 1) / (warps * kStreamMaxRowsPerWarp);
+  const int rows = (H + warps * n_tiles - 1) / (warps * n_tiles);
+  // k_sweep is instantiated for these strip lengths (compile-time trip count)
+  return rows <= 8 ? 8 : rows <= 16 ? 16 : rows <= 32 ? 32 : rows <= 48 ? 48 : 64;
+}
 #ifndef SBX_SWEEP_MIN_CTAS
 #define SBX_SWEEP_MIN_CTAS 4      // k_sweep: <= 64 registers, 32 warps per SM
 #endif
@@ -1140,12 +1150,13 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
 // ---------------------------------------------------------------------------
 
 struct StreamTiling {
-  int tiles_x, tiles_y, tiles;
+  int tiles_x, tiles_y, tiles, rows_per_warp;
 };
 __host__ __device__ inline StreamTiling stream_tiling(int H, int W, int V) {
   StreamTiling t;
   const int tile_w = 32 * V;
-  const int tile_h = (kStreamThreads / 32) * kStreamRowsPerWarp;
+  t.rows_per_warp = stream_rows_per_warp(H);
+  const int tile_h = (kStreamThreads / 32) * t.rows_per_warp;
   t.tiles_x = (W + tile_w - 1) / tile_w;
   t.tiles_y = (H + tile_h - 1) / tile_h;
   t.tiles = t.tiles_x * t.tiles_y;
@@ -1170,9 +1181,9 @@ __global__ void k_pack_stream(const Params p) {
 // One Jacobi sweep of every still-active building.  Sweep index k is 1-based.
 // Every class of CV runs the same instruction stream (cv_update_packed): warps that
 // mix interior / wall / boundary / exterior CVs do not diverge.
-template <int V>
+template <int V, int R>
 __global__ void __launch_bounds__(kStreamThreads, SBX_SWEEP_MIN_CTAS) k_sweep(const Params p, const int k) {
-  __shared__ Combo tab[kNumCombos];
+  __shared__ __align__(16) Combo tab[kNumCombos];
   __shared__ float qcv[kMaxZones + 1];
   const StreamTiling tl = stream_tiling(p.H, p.W, V);
   const int b = blockIdx.x / tl.tiles;
@@ -1183,10 +1194,14 @@ __global__ void __launch_bounds__(kStreamThreads, SBX_SWEEP_MIN_CTAS) k_sweep(co
   const int H = p.H, W = p.W, Z = p.Z;
   const size_t n_cv = (size_t)H * W;
   const int plan = p.n_plans == 1 ? 0 : b;
-  const float t_inf = (float)env_ambient(p, b, p.time_index);
-  const float h = (float)env_convection(p, b);
-  build_combo_table(tab, p, plan, b, h, t_inf, tid, kStreamThreads);
-  for (int i = tid; i < Z; i += kStreamThreads) qcv[i] = p.qcv[(size_t)b * Z + i];
+  // coefficient table, heat inputs and T_inf of this building: built once per step by
+  // k_pre / k_build_header (the solve header of the resident kernel), not once per CTA
+  const unsigned char* gH = p.hdr + (size_t)b * header_bytes(Z);
+  for (int i = tid; i < (int)(sizeof(Combo) * kNumCombos / 16); i += kStreamThreads)
+    reinterpret_cast<float4*>(tab)[i] = reinterpret_cast<const float4*>(gH)[i];
+  const float* hq = reinterpret_cast<const float*>(gH + sizeof(Combo) * kNumCombos);
+  for (int i = tid; i < Z; i += kStreamThreads) qcv[i] = hq[i];
+  const float t_inf = hq[header_q_slots(Z)];
   __syncthreads();
   AreaCoef az;
   az.full = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
@@ -1203,11 +1218,11 @@ __global__ void __launch_bounds__(kStreamThreads, SBX_SWEEP_MIN_CTAS) k_sweep(co
   const uint16_t* __restrict__ dsc = p.desc_spk + (size_t)plan * n_cv;
 
   const int c0 = (tx * 32 + lane) * V;
-  const int r0 = (ty * (kStreamThreads / 32) + warp) * kStreamRowsPerWarp;
+  const int r0 = (ty * (kStreamThreads / 32) + warp) * R;      // R == tl.rows_per_warp
   const bool col_ok = c0 < W;
   float lmax = 0.f;
   if (r0 < H) {
-    const int r1 = min(r0 + kStreamRowsPerWarp, H);
+    const int r1 = min(r0 + R, H);
     float up[V], c[V], dn[V];
     fill<V>(up, t_inf);
     fill<V>(c, t_inf);
@@ -1543,12 +1558,12 @@ __global__ void __launch_bounds__(kStreamThreads) k_zone_reduce(const Params p) 
   const float* __restrict__ t = p.tbuf[p.cur[b]] + (size_t)b * n_cv;
   const uint16_t* __restrict__ dsc = p.desc + (size_t)plan * n_cv;
   const int c0 = (tx * 32 + lane) * V;
-  const int r0 = (ty * (kStreamThreads / 32) + warp) * kStreamRowsPerWarp;
+  const int r0 = (ty * (kStreamThreads / 32) + warp) * tl.rows_per_warp;
   long long total = 0;                       // every CV: the grid mean
   long long runL = 0, runR = 0;              // CVs of zone zL / zR seen by this thread
   int zL = SBX_ZONE_NONE, zR = SBX_ZONE_NONE;
   if (c0 < W && r0 < H) {
-    const int nr = min(kStreamRowsPerWarp, H - r0);
+    const int nr = min(tl.rows_per_warp, H - r0);
     const float* tp = t + (size_t)r0 * W + c0;
     const uint16_t* dp = dsc + (size_t)r0 * W + c0;
 #pragma unroll 4

@@ -19,7 +19,8 @@ from sbsim_b200.exogenous import (ConstantOccupancy, ElectricityEnergyCost,
                                   NaturalGasEnergyCost, ReplayWeatherController,
                                   SetpointSchedule, StepFunctionOccupancy, TableOccupancy,
                                   WeatherController)
-from sbsim_b200.floorplan import CompiledPlan, MaterialProperties, compile_plan
+from sbsim_b200.floorplan import (CompiledPlan, MaterialProperties, compile_plan,
+                                  legacy_building, legacy_building_plan)
 
 __all__ = [
     "ActionConfig", "AirHandler", "BatchedWeather", "Boiler", "BoundedActionNormalizer",
@@ -29,5 +30,5 @@ __all__ = [
     "ReplayWeatherController", "SbxLibraryError", "SetpointEnergyCarbonRegretFunction",
     "SetpointEnergyCarbonRewardFunction",
     "SetpointSchedule", "SimulatorBuilding", "StandardScoreObservationNormalizer",
-    "StepFunctionOccupancy", "StochasticConvectionSimulator", "TableOccupancy", "WeatherController", "compile_plan",
+    "StepFunctionOccupancy", "StochasticConvectionSimulator", "TableOccupancy", "WeatherController", "compile_plan", "legacy_building", "legacy_building_plan",
 ]

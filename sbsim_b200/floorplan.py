@@ -165,8 +165,14 @@ def compile_plan(floor_plan: np.ndarray, zone_map: Optional[np.ndarray] = None, 
                  inside_wall: MaterialProperties,
                  building_exterior: MaterialProperties,
                  buffer_from_walls: int = 3,
-                 diffuser_spacing: int = 10) -> CompiledPlan:
-  """FloorPlanBasedBuilding.__init__ (building.py:634-766) + TFSimulator statics."""
+                 diffuser_spacing: int = 10,
+                 diffuser_mask: Optional[np.ndarray] = None) -> CompiledPlan:
+  """FloorPlanBasedBuilding.__init__ (building.py:634-766) + TFSimulator statics.
+
+  `diffuser_mask` (bool [H, W], optional) places the diffusers explicitly instead of the
+  spacing rule -- what the reference's tests do with `building.diffusers = ...`
+  (simulator_flexible_floor_plan_test.py:467-471); every zone's diffusers share its power
+  equally (building.py:349-351)."""
   floor_plan = np.asarray(floor_plan)
   zone_map = floor_plan if zone_map is None else np.asarray(zone_map)
   plan = guarantee_air_padding_in_frame(floor_plan)
@@ -206,10 +212,21 @@ def compile_plan(floor_plan: np.ndarray, zone_map: Optional[np.ndarray] = None, 
   zone_ncv = np.zeros(n_zones, dtype=np.int32)
   zone_ndiff = np.zeros(n_zones, dtype=np.int32)
   iw_for_check = interior_walls.astype(np.int8)            # pre-shrink walls, building.py:751-757
+  dmask = None
+  if diffuser_mask is not None:
+    dmask = np.asarray(diffuser_mask, dtype=bool)
+    if dmask.shape != floor_plan.shape:
+      raise ValueError("diffuser_mask must have the floor plan's shape")
+    pad = (plan.shape[0] - floor_plan.shape[0]) // 2       # ring added by guarantee_air_padding_in_frame
+    if pad:
+      dmask = np.pad(dmask, pad, mode="constant", constant_values=False)
   for zi in range(n_zones):
     rows, cols = np.nonzero(zone_id == zi)
     zone_ncv[zi] = len(rows)
-    inds = _diffusers_for_room(rows, cols, diffuser_spacing, buffer_from_walls, iw_for_check)
+    if diffuser_mask is not None:
+      inds = [(int(r), int(c)) for r, c in zip(rows, cols) if dmask[r, c]]
+    else:
+      inds = _diffusers_for_room(rows, cols, diffuser_spacing, buffer_from_walls, iw_for_check)
     zone_ndiff[zi] = len(inds)
     for r, c in inds:
       diffuser_weight[r, c] = 1.0 / float(len(inds))       # building.py:349-351
@@ -230,6 +247,56 @@ def compile_plan(floor_plan: np.ndarray, zone_map: Optional[np.ndarray] = None, 
       zone_ncv=zone_ncv, zone_ndiff=zone_ndiff, obs_zone_order=obs_order,
       cv_class=cv_class, material_id=material_id, zone_id=zone_id,
       diffuser_weight=diffuser_weight, exterior_space=ext)
+
+
+# ----------------------------------------------------------------------------
+# legacy rectangular Building
+# ----------------------------------------------------------------------------
+
+
+def legacy_building_plan(room_shape: Tuple[int, int], building_shape: Tuple[int, int]):
+  """The reference's deprecated rectangular `Building` (building.py:394-505: rooms of
+  room_shape air CVs in a building_shape grid, one-CV interior walls, a two-CV exterior
+  shell) as (floor_plan, diffuser_mask) for compile_plan.
+
+  The equivalence is the reference's own: its tests rebuild the old building as a floor plan
+  -- the old grid with one more ring of exterior space around it -- and copy the old
+  diffusers over (simulator_flexible_floor_plan_test.py:103-160, 467-471).  The four
+  diffusers per room follow generate_thermal_diffusers (building.py:102-157)."""
+  rs0, rs1 = int(room_shape[0]), int(room_shape[1])
+  nrows = (rs0 + 1) * int(building_shape[0]) + 3           # building.py:463-464
+  ncols = (rs1 + 1) * int(building_shape[1]) + 3
+  old = np.zeros((nrows, ncols), dtype=np.int8)            # 0 air, 1 wall
+  for x in range(rs0 + 2, nrows - 2, rs0 + 1):             # assign_interior_wall_values :94-99
+    old[x, 2:ncols - 2] = 1
+  for y in range(rs1 + 2, ncols - 2, rs1 + 1):
+    old[2:nrows - 2, y] = 1
+  old[:, [0, 1, -2, -1]] = 1                               # assign_building_exterior_values :73-74
+  old[[0, 1, -2, -1], :] = 1
+  diff = np.zeros((nrows, ncols), dtype=bool)              # generate_thermal_diffusers :117-156
+  d1x = (rs0 - 2) // 3
+  d2x = rs0 - d1x - 1
+  d1y = (rs1 - 2) // 3
+  d2y = rs1 - d1y - 1
+  for sx in range(2, nrows - 3, rs0 + 1):
+    for sy in range(2, ncols - 3, rs1 + 1):
+      for dx in (d1x, d2x):
+        for dy in (d1y, d2y):
+          diff[sx + dx, sy + dy] = True
+  plan = np.pad(old, 1, mode="constant", constant_values=2)
+  return plan, np.pad(diff, 1, mode="constant", constant_values=False)
+
+
+def legacy_building(cv_size_cm: float, room_shape: Tuple[int, int], building_shape: Tuple[int, int],
+                    inside_air: MaterialProperties, inside_wall: MaterialProperties,
+                    building_exterior: MaterialProperties) -> CompiledPlan:
+  """`Building(cv_size_cm, floor_height_cm, room_shape, building_shape, initial_temp, ...)`
+  of the reference (building.py:419-505) compiled for libsbx; floor height and initial
+  temperature are arguments of SimulatorBuilding here."""
+  plan, dm = legacy_building_plan(room_shape, building_shape)
+  return compile_plan(plan.astype(np.int64), None, cv_size_cm=cv_size_cm, inside_air=inside_air,
+                      inside_wall=inside_wall, building_exterior=building_exterior,
+                      buffer_from_walls=0, diffuser_mask=dm)
 
 
 # ----------------------------------------------------------------------------

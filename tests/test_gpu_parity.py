@@ -461,3 +461,37 @@ def test_list_sweep_equals_rolling_window_sweep():
   finally:
     for e in envs:
       e.close()
+
+
+def test_gauss_seidel_on_the_legacy_rectangular_building():
+  """The deprecated rectangular `Building` (3 x 3 rooms of 20 x 30 CVs)
+  through legacy_building(): fp64 Gauss-Seidel solve bit-identical to the oracle."""
+  from oracle import gs_solver
+  cp = floorplan.legacy_building(
+      20.0, (20, 30), (3, 3), floorplan.MaterialProperties(50.0, 700.0, 1.0),
+      floorplan.MaterialProperties(5.0, 800.0, 1800.0), floorplan.MaterialProperties(5.0, 800.0, 3000.0))
+  sc = S.Scenario(floor_plan=np.zeros((4, 4), dtype=np.int64), cv_size_cm=20.0)
+  B = 2
+  env = S.make_env(sc, n_envs=B, plans=cp, solver="gauss_seidel")
+  try:
+    env.reset()
+    rng = np.random.default_rng(8)
+    H, W, Z = cp.height, cp.width, env.building.n_zones
+    assert (H, W, Z) == (68, 98, 9)
+    temp = rng.uniform(285, 300, (B, H, W))
+    qcv = rng.uniform(-50, 400, (B, Z))
+    ambient = rng.uniform(270, 300, B)
+    conv = rng.uniform(5, 100, B)
+    env.handle.upload("temp64", temp)
+    env.handle.upload("q_cv64", qcv)
+    env.handle.fd_step(ambient, conv)
+    got = env.handle.download("temp64", (B, H, W))
+    sweeps = env.handle.download("n_sweeps", (B,))
+    gs = gs_solver.GaussSeidel(S.oracle_plan(cp, sc.floor_height_cm), sc.time_step_sec,
+                               sc.convergence_threshold, sc.iteration_limit)
+    for b in range(B):
+      want, n, _, _ = gs.fd_step(temp[b], _dense_q(cp, qcv[b]), ambient[b], conv[b])
+      assert sweeps[b] == n
+      np.testing.assert_array_equal(got[b], want)
+  finally:
+    env.close()

@@ -178,3 +178,56 @@ def test_energy_carbon_reward_reference_known_answers(temp, occ, blower, ac, gas
          r.natural_gas_energy_cost, r.carbon_emitted, r.carbon_cost)
   for g, w in zip(got, want):
     assert abs(g - w) < 0.5e-4, (got, want)     # assertAlmostEqual(..., 4)
+
+
+def _legacy_cp():
+  return floorplan.legacy_building(
+      20.0, (20, 30), (3, 3), floorplan.MaterialProperties(50.0, 700.0, 1.0),
+      floorplan.MaterialProperties(5.0, 800.0, 1800.0), floorplan.MaterialProperties(5.0, 800.0, 3000.0))
+
+
+def test_legacy_rectangular_building_equals_reference_arrays():
+  """the deprecated `Building(room_shape, building_shape)`
+  (building.py:394-505) through legacy_building(): materials, exterior space, rooms and the
+  four diffusers per room equal the arrays of the reference's own buildings (the fixture
+  holds its FloorPlanBasedBuilding twin with the OLD Building's diffusers copied over,
+  simulator_flexible_floor_plan_test.py:467-471)."""
+  g = _load("ref_gs_golden.npz")
+  cp = _legacy_cp()
+  assert (cp.height, cp.width) == g["exterior_space"].shape == (68, 98)
+  np.testing.assert_array_equal(cp.exterior_space, g["exterior_space"])
+  for k, name in enumerate(("conductivity", "heat_capacity", "density")):
+    np.testing.assert_array_equal(cp.dense_material(k), g[name])
+  np.testing.assert_array_equal(cp.diffuser_weight, g["diffusers"].astype(np.float64))
+  assert cp.zone_names == [str(n) for n in g["room_names"]]
+  np.testing.assert_array_equal(cp.zone_ncv, g["room_sizes"])
+  assert list(cp.zone_ndiff) == [4] * 9
+
+
+def test_oracle_gs_golden_through_legacy_building():
+  """The reference's golden return-water temperature 301.895482
+  (simulator_test.py:955-987 on the old Building, simulator_flexible_floor_plan_test.py:1275-1312
+  on its twin) from legacy_building() + the oracle's Gauss-Seidel step."""
+  g = _load("ref_gs_golden.npz")
+  hp, sch = g["hvac_params"], g["schedule"]
+  cfg = oenv.OracleEnvConfig(
+      plan=S.oracle_plan(_legacy_cp(), 300.0), start_timestamp=pd.Timestamp("12-21-2012"),
+      weather=oex.WeatherController(296.0, 296.0),
+      schedule=ohvac.SetpointSchedule(int(sch[0]), int(sch[1]), (sch[2], sch[3]), (sch[4], sch[5])),
+      occupancy=oex.ConstantOccupancy(1.0),
+      reward_function=orew.SetpointEnergyCarbonRegretFunction(
+          300.0, 100.0, 160000, 400000, 0.5, 4.3, oex.ElectricityEnergyCost(),
+          oex.NaturalGasEnergyCost(), 0.2, 0.4, 0.4),
+      solver="gs", time_step_sec=300.0, convergence_threshold=0.1, iteration_limit=100,
+      initial_temp=200.0, ahu_recirculation=hp[0], ahu_heating_setpoint=hp[1],
+      ahu_cooling_setpoint=hp[2], ahu_fan_differential_pressure=hp[3],
+      ahu_fan_efficiency=hp[4], ahu_max_air_flow_rate=hp[5], boiler_setpoint=hp[6],
+      boiler_pump_head=hp[7], boiler_pump_efficiency=hp[8], boiler_heating_rate=0,
+      boiler_cooling_rate=0, vav_max_air_flow_rate=hp[9],
+      vav_reheat_max_water_flow_rate=hp[10])
+  o = oenv.OracleEnvironment(cfg)
+  o._setup_step_sim()
+  o._execute_step_sim()
+  got = o.boiler.return_water_temperature_sensor
+  assert abs(got - 301.895482) < 1e-5
+  np.testing.assert_array_equal(o.temp, g["reference_temp_after_step"])

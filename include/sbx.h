@@ -247,6 +247,9 @@ enum {
   SBX_DIAG_NORM_CARBON = 10,
   SBX_DIAG_TOTAL_OCC = 11,
   SBX_DIAG_PRODUCTIVITY = 12,
+  SBX_DIAG_COOLING_REQUESTS = 13, /* AirHandler cooling_request_count (air_handler.py:254-268) */
+  SBX_DIAG_HEATING_REQUESTS = 14, /* Boiler heating_request_count (boiler.py:219-231) */
+  SBX_DIAG_TANK_TEMP = 15,        /* Boiler supply_water_temperature_sensor as observed this step */
   SBX_DIAG_N = 16
 };
 

@@ -74,6 +74,7 @@ DIAG = {
     "supply_air_temp": 0, "ahu_flow": 1, "boiler_flow": 2, "return_water": 3,
     "blower_w": 4, "ac_w": 5, "gas_w": 6, "pump_w": 7, "regret": 8,
     "norm_cost": 9, "norm_carbon": 10, "total_occ": 11, "productivity": 12,
+    "cooling_requests": 13, "heating_requests": 14, "tank_temp": 15,
 }
 
 

@@ -823,6 +823,9 @@ __device__ inline void hvac_post(const Params& p, int b, int plan, int lane, uns
     dg[SBX_DIAG_NORM_CARBON] = n_carbon;
     dg[SBX_DIAG_TOTAL_OCC] = occ_sum;
     dg[SBX_DIAG_PRODUCTIVITY] = actual;
+    dg[SBX_DIAG_COOLING_REQUESTS] = (double)cy.ahu_count;
+    dg[SBX_DIAG_HEATING_REQUESTS] = (double)cy.boiler_count;
+    dg[SBX_DIAG_TANK_TEMP] = tank;
   }
 }
 

@@ -166,13 +166,15 @@ def compile_plan(floor_plan: np.ndarray, zone_map: Optional[np.ndarray] = None, 
                  building_exterior: MaterialProperties,
                  buffer_from_walls: int = 3,
                  diffuser_spacing: int = 10,
-                 diffuser_mask: Optional[np.ndarray] = None) -> CompiledPlan:
+                 diffuser_mask: Optional[np.ndarray] = None,
+                 material_id: Optional[np.ndarray] = None) -> CompiledPlan:
   """FloorPlanBasedBuilding.__init__ (building.py:634-766) + TFSimulator statics.
 
   `diffuser_mask` (bool [H, W], optional) places the diffusers explicitly instead of the
   spacing rule -- what the reference's tests do with `building.diffusers = ...`
   (simulator_flexible_floor_plan_test.py:467-471); every zone's diffusers share its power
-  equally (building.py:349-351)."""
+  equally (building.py:349-351).  `material_id` (int [H, W] of MAT_AIR / MAT_INTERIOR_WALL /
+  MAT_EXTERIOR_WALL, optional) overrides the wall classification (legacy_building)."""
   floor_plan = np.asarray(floor_plan)
   zone_map = floor_plan if zone_map is None else np.asarray(zone_map)
   plan = guarantee_air_padding_in_frame(floor_plan)
@@ -186,8 +188,16 @@ def compile_plan(floor_plan: np.ndarray, zone_map: Optional[np.ndarray] = None, 
   near_shell = ndimage.binary_dilation(shell, structure=_ENLARGE)
   exterior_walls = shell | (near_shell & interior_walls)
   interior_walls_shrunk = interior_walls & ~exterior_walls
-  material_id = np.where(interior_walls_shrunk, MAT_INTERIOR_WALL,
-                         np.where(exterior_walls, MAT_EXTERIOR_WALL, MAT_AIR)).astype(np.int8)
+  if material_id is None:
+    material_id = np.where(interior_walls_shrunk, MAT_INTERIOR_WALL,
+                           np.where(exterior_walls, MAT_EXTERIOR_WALL, MAT_AIR)).astype(np.int8)
+  else:
+    material_id = np.asarray(material_id, dtype=np.int8)
+    if material_id.shape != floor_plan.shape:
+      raise ValueError("material_id must have the floor plan's shape")
+    pad = (plan.shape[0] - floor_plan.shape[0]) // 2
+    if pad:
+      material_id = np.pad(material_id, pad, mode="constant", constant_values=MAT_AIR)
   # rooms: 4-connected components of the zone map's interior space :254-292, 376-414
   labels, n_rooms = ndimage.label(zmap == 0, structure=_CROSS)
   labels = np.where(zmap == 2, -1, labels)                 # exterior space set negative :294-320
@@ -289,14 +299,26 @@ def legacy_building_plan(room_shape: Tuple[int, int], building_shape: Tuple[int,
 
 def legacy_building(cv_size_cm: float, room_shape: Tuple[int, int], building_shape: Tuple[int, int],
                     inside_air: MaterialProperties, inside_wall: MaterialProperties,
-                    building_exterior: MaterialProperties) -> CompiledPlan:
+                    building_exterior: MaterialProperties, exact_materials: bool = True) -> CompiledPlan:
   """`Building(cv_size_cm, floor_height_cm, room_shape, building_shape, initial_temp, ...)`
   of the reference (building.py:419-505) compiled for libsbx; floor height and initial
-  temperature are arguments of SimulatorBuilding here."""
+  temperature are arguments of SimulatorBuilding here.
+
+  exact_materials=True reproduces the old Building's material arrays exactly (two exterior
+  layers, interior wall lines up to them); False gives the reference's own floor-plan twin
+  (simulator_flexible_floor_plan_test.py:431-472), whose wall classification turns the 2 x
+  (rooms - 1) x 2 interior-wall CVs that touch the shell into exterior wall."""
   plan, dm = legacy_building_plan(room_shape, building_shape)
+  mat = None
+  if exact_materials:
+    old = plan[1:-1, 1:-1]
+    m = np.where(old == 1, MAT_INTERIOR_WALL, MAT_AIR).astype(np.int8)
+    m[:, [0, 1, -2, -1]] = MAT_EXTERIOR_WALL                # assign_building_exterior_values :73-74
+    m[[0, 1, -2, -1], :] = MAT_EXTERIOR_WALL
+    mat = np.pad(m, 1, mode="constant", constant_values=MAT_AIR)
   return compile_plan(plan.astype(np.int64), None, cv_size_cm=cv_size_cm, inside_air=inside_air,
                       inside_wall=inside_wall, building_exterior=building_exterior,
-                      buffer_from_walls=0, diffuser_mask=dm)
+                      buffer_from_walls=0, diffuser_mask=dm, material_id=mat)
 
 
 # ----------------------------------------------------------------------------

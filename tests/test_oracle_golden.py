@@ -180,18 +180,20 @@ def test_energy_carbon_reward_reference_known_answers(temp, occ, blower, ac, gas
     assert abs(g - w) < 0.5e-4, (got, want)     # assertAlmostEqual(..., 4)
 
 
-def _legacy_cp():
+def _legacy_cp(exact_materials=False):
   return floorplan.legacy_building(
       20.0, (20, 30), (3, 3), floorplan.MaterialProperties(50.0, 700.0, 1.0),
-      floorplan.MaterialProperties(5.0, 800.0, 1800.0), floorplan.MaterialProperties(5.0, 800.0, 3000.0))
+      floorplan.MaterialProperties(5.0, 800.0, 1800.0), floorplan.MaterialProperties(5.0, 800.0, 3000.0),
+      exact_materials=exact_materials)
 
 
 def test_legacy_rectangular_building_equals_reference_arrays():
   """the deprecated `Building(room_shape, building_shape)`
-  (building.py:394-505) through legacy_building(): materials, exterior space, rooms and the
-  four diffusers per room equal the arrays of the reference's own buildings (the fixture
-  holds its FloorPlanBasedBuilding twin with the OLD Building's diffusers copied over,
-  simulator_flexible_floor_plan_test.py:467-471)."""
+  (building.py:394-505) through legacy_building(exact_materials=False): materials, exterior
+  space, rooms and the four diffusers per room equal the arrays of the reference's own
+  floor-plan twin of it (the fixture: FloorPlanBasedBuilding with the OLD Building's diffusers
+  copied over, simulator_flexible_floor_plan_test.py:467-471).  The old Building itself is
+  compared live in tests/test_oracle_vs_reference.py."""
   g = _load("ref_gs_golden.npz")
   cp = _legacy_cp()
   assert (cp.height, cp.width) == g["exterior_space"].shape == (68, 98)
@@ -204,14 +206,16 @@ def test_legacy_rectangular_building_equals_reference_arrays():
   assert list(cp.zone_ndiff) == [4] * 9
 
 
-def test_oracle_gs_golden_through_legacy_building():
+@pytest.mark.parametrize("exact_materials", [False, True])
+def test_oracle_gs_golden_through_legacy_building(exact_materials):
   """The reference's golden return-water temperature 301.895482
   (simulator_test.py:955-987 on the old Building, simulator_flexible_floor_plan_test.py:1275-1312
-  on its twin) from legacy_building() + the oracle's Gauss-Seidel step."""
+  on its twin) from legacy_building() + the oracle's Gauss-Seidel step, for the old
+  Building's exact materials and for the twin's."""
   g = _load("ref_gs_golden.npz")
   hp, sch = g["hvac_params"], g["schedule"]
   cfg = oenv.OracleEnvConfig(
-      plan=S.oracle_plan(_legacy_cp(), 300.0), start_timestamp=pd.Timestamp("12-21-2012"),
+      plan=S.oracle_plan(_legacy_cp(exact_materials), 300.0), start_timestamp=pd.Timestamp("12-21-2012"),
       weather=oex.WeatherController(296.0, 296.0),
       schedule=ohvac.SetpointSchedule(int(sch[0]), int(sch[1]), (sch[2], sch[3]), (sch[4], sch[5])),
       occupancy=oex.ConstantOccupancy(1.0),
@@ -230,4 +234,7 @@ def test_oracle_gs_golden_through_legacy_building():
   o._execute_step_sim()
   got = o.boiler.return_water_temperature_sensor
   assert abs(got - 301.895482) < 1e-5
-  np.testing.assert_array_equal(o.temp, g["reference_temp_after_step"])
+  if exact_materials:      # 8 wall CVs at the shell differ in density from the twin's
+    np.testing.assert_allclose(o.temp, g["reference_temp_after_step"], rtol=2e-4)
+  else:
+    np.testing.assert_array_equal(o.temp, g["reference_temp_after_step"])

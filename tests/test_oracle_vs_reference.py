@@ -99,3 +99,34 @@ def test_oracle_env_matches_live_reference_env(ref):
     np.testing.assert_allclose(ots[3], rts.observation, rtol=1e-6, atol=1e-7)
     np.testing.assert_allclose(float(ots[1]), float(rts.reward), rtol=1e-6, atol=1e-9)
     np.testing.assert_array_equal(np.asarray(o.temp), np.asarray(b.temp))
+
+
+@pytest.mark.parametrize("room_shape,building_shape", [((20, 30), (3, 3)), ((5, 7), (2, 4)),
+                                                       ((9, 4), (1, 1)), ((6, 11), (4, 2))])
+def test_legacy_building_plan_matches_reference_building(ref, room_shape, building_shape):
+  """legacy_building() against the reference's deprecated rectangular Building
+  (building.py:394-505) for several shapes: materials and diffusers, one ring of exterior
+  space added around the old grid."""
+  bp = ref["building"]
+  air = (50.0, 700.0, 1.0)
+  wall = (5.0, 800.0, 1800.0)
+  ext = (0.5, 900.0, 3000.0)
+  old = bp.Building(20.0, 300.0, room_shape, building_shape, 292.0, bp.MaterialProperties(*air),
+                    bp.MaterialProperties(*wall), bp.MaterialProperties(*ext))
+  cp = floorplan.legacy_building(20.0, room_shape, building_shape, floorplan.MaterialProperties(*air),
+                                 floorplan.MaterialProperties(*wall), floorplan.MaterialProperties(*ext))
+  assert (cp.height, cp.width) == (old.temp.shape[0] + 2, old.temp.shape[1] + 2)
+  for k, arr in enumerate((old.conductivity, old.heat_capacity, old.density)):
+    np.testing.assert_array_equal(cp.dense_material(k)[1:-1, 1:-1], arr)
+  np.testing.assert_array_equal(cp.diffuser_weight[1:-1, 1:-1] > 0, old.diffusers > 0)
+  np.testing.assert_allclose(cp.diffuser_weight[1:-1, 1:-1], old.diffusers.astype(np.float64))
+  assert cp.n_zones == building_shape[0] * building_shape[1]
+  # zones in the old building's (zone_x, zone_y) row-major order, air CVs only
+  zi = 0
+  for zx in range(building_shape[0]):
+    for zy in range(building_shape[1]):
+      x0 = zx * (room_shape[0] + 1) + 2
+      y0 = zy * (room_shape[1] + 1) + 2
+      block = cp.zone_id[1:-1, 1:-1][x0:x0 + room_shape[0], y0:y0 + room_shape[1]]
+      assert np.all(block == zi), (zx, zy)
+      zi += 1

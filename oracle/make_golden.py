@@ -23,6 +23,8 @@ Fixtures
   ref_tf_calibrated.npz  one reset + 2 FD steps of TFSimulator on the calibrated plan.
   ref_env_ecr.npz      ref_env_tf's scenario with SetpointEnergyCarbonRewardFunction
                        (reward/setpoint_energy_carbon_reward.py) instead of the regret reward.
+  ref_env_conv.npz     ref_env_tf's scenario with the shipped StochasticConvectionSimulator
+                       (p = 1, distance = 5, seed = 5; sim_config.gin:37-39) in the building.
 """
 
 from __future__ import annotations
@@ -76,6 +78,7 @@ def _ref_modules():
       bl="simulator.boiler", ss="simulator.setpoint_schedule",
       wc="simulator.weather_controller", sb="simulator.simulator_building",
       occ="simulator.step_function_occupancy", sffp="simulator.simulator_flexible_floor_plan",
+      conv="simulator.stochastic_convection_simulator",
       regret="reward.setpoint_energy_carbon_regret", ecr="reward.setpoint_energy_carbon_reward", elec="reward.electricity_energy_cost",
       gas="reward.natural_gas_energy_cost", env="environment.environment",
       onorm="utils.observation_normalizer", anorm="utils.bounded_action_normalizer",
@@ -84,14 +87,16 @@ def _ref_modules():
           for k, v in names.items()}
 
 
-def build_reference_env(m, plan, solver, histogram=False, reward="regret"):
+def build_reference_env(m, plan, solver, histogram=False, reward="regret", convection=None):
   """The scenario of tests/scenarios.py:Scenario() built from reference classes."""
   b = m["building"].FloorPlanBasedBuilding(
       cv_size_cm=20.0, floor_height_cm=300.0, initial_temp=292.0,
       inside_air_properties=m["building"].MaterialProperties(50.0, 700.0, 1.0),
       inside_wall_properties=m["building"].MaterialProperties(2.0, 1000.0, 1800.0),
       building_exterior_properties=m["building"].MaterialProperties(0.05, 1000.0, 3000.0),
-      floor_plan=plan, zone_map=plan.copy(), buffer_from_walls=2)
+      floor_plan=plan, zone_map=plan.copy(), buffer_from_walls=2,
+      convection_simulator=(m["conv"].StochasticConvectionSimulator(*convection)
+                            if convection else None))
   sched = m["ss"].SetpointSchedule(6, 19, (294, 297), (289, 298))
   weather = m["wc"].WeatherController(275.0, 290.0, convection_coefficient=60.0)
   boiler = m["bl"].Boiler(360.0, 6.0, 0.98, heating_rate=0.5, cooling_rate=0.1,
@@ -133,9 +138,9 @@ def build_reference_env(m, plan, solver, histogram=False, reward="regret"):
   return env, b
 
 
-def make_env_rollout(m, solver, histogram, n_steps, seed, reward="regret"):
+def make_env_rollout(m, solver, histogram, n_steps, seed, reward="regret", convection=None):
   plan = small_plan()
-  env, b = build_reference_env(m, plan, solver, histogram, reward)
+  env, b = build_reference_env(m, plan, solver, histogram, reward, convection)
   rng = np.random.default_rng(seed)
   ts = env.reset()
   obs, rew, stype, disc, zts, acts, blr, ahu = [ts.observation], [0.0], [0], [1.0], [], [], [], []
@@ -261,6 +266,8 @@ def main():
   np.savez_compressed(os.path.join(OUT, "ref_env_hist.npz"), **make_env_rollout(m, "tf", True, 40, 2))
   np.savez_compressed(os.path.join(OUT, "ref_env_ecr.npz"),
                       **make_env_rollout(m, "tf", False, 60, 3, reward="energy_carbon"))
+  np.savez_compressed(os.path.join(OUT, "ref_env_conv.npz"),
+                      **make_env_rollout(m, "tf", False, 30, 4, convection=(1.0, 5, 5)))
   np.savez_compressed(os.path.join(OUT, "ref_gs_golden.npz"), **make_gs_golden(m))
   sb1, cal = make_sb1(m)
   np.savez_compressed(os.path.join(OUT, "sb1_calibrated.npz"), **sb1)

@@ -25,11 +25,12 @@ def _load(name):
 
 @pytest.mark.parametrize("name,solver,histogram,reward", [
     ("ref_env_tf.npz", "tf", False, "regret"), ("ref_env_hist.npz", "tf", True, "regret"),
-    ("ref_env_gs.npz", "gs", False, "regret"), ("ref_env_ecr.npz", "tf", False, "energy_carbon")])
+    ("ref_env_gs.npz", "gs", False, "regret"), ("ref_env_ecr.npz", "tf", False, "energy_carbon"),
+    ("ref_env_conv.npz", "tf", False, "regret")])
 def test_oracle_env_matches_reference_rollout(name, solver, histogram, reward):
   g = _load(name)
   sc = S.Scenario(floor_plan=g["floor_plan"].astype(np.int64), histogram=histogram,
-                  reward=reward)
+                  reward=reward, convection=(1.0, 5, 5) if "conv" in name else None)
   o = S.make_oracle(sc, solver=solver)
   ts = o.reset()
   np.testing.assert_allclose(ts[3], g["observations"][0], rtol=1e-6, atol=1e-7)

@@ -7,7 +7,10 @@
 Metric: building-env-steps/s (BASELINE.json).  Workload (config.workload):
 "randomized" = BASELINE.json configs[3] sharded per GPU (32768 randomised 64x96
 buildings per GPU; N=8 is exactly configs[3], N=1 with --envs-per-gpu 65536 is
-configs[2]); "office" = configs[1]'s size class (copies of one 744x1004 plan).
+configs[2]); "office" = configs[1]: copies of the calibrated sb1 building
+(744x1004 CVs, 126 zones, reset_temps.npy, Moffett Field replay weather, the shipped
+randomized occupancy; sim_config.gin:160-196) from the committed fixture
+tests/golden/sb1_calibrated.npz; with --envs-per-gpu 1 it is configs[0].
 
 One JSON line is printed by rank 0.  Keys follow the driver's contract:
 value = whole-job steps/s with inputs resident in HBM (actions already on the
@@ -34,6 +37,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+CALIBRATED_FIXTURE = os.path.join(ROOT, "tests", "golden", "sb1_calibrated.npz")
 METRIC = "building_env_steps_per_sec"
 UNIT = "env-steps/s"
 
@@ -178,17 +182,16 @@ def build_env(args, rank, local_rank):
             "plans": "per-env descriptor, materials, weather, T0, actions"}
     return env, wl, desc
   n = args.envs_per_gpu or 4096
-  plan = workloads.synthetic_office_plan()
-  cp = floorplan.compile_plan(plan, None, cv_size_cm=10.0,
-                              inside_air=floorplan.MaterialProperties(50.0, 700.0, 1.0),
-                              inside_wall=floorplan.MaterialProperties(50.0, 1.0, 700.0),
-                              building_exterior=floorplan.MaterialProperties(0.05, 700.0, 1.0))
-  env = workloads.make_shared_plan_env(cp, n, episode_steps=episode,
-                                       histogram=bool(args.histogram), device=local_rank,
-                                       kernel_path=path)
-  desc = {"workload": "office-744x1004 x copies (BASELINE.json configs[1] size class)",
+  cal = workloads.load_calibrated(CALIBRATED_FIXTURE)
+  cp = cal.plan
+  env = workloads.make_calibrated_env(cal, n, episode_steps=episode,
+                                      histogram=bool(args.histogram), device=local_rank,
+                                      kernel_path=path)
+  desc = {"workload": "calibrated sb1 building 744x1004 x copies (BASELINE.json configs[1]; "
+                      "sim_config.gin:160-196: TF-Jacobi, reset_temps.npy, Moffett replay weather, "
+                      "US/Pacific schedule, RandomizedArrivalDepartureOccupancy seed 17321)",
           "envs_per_gpu": n, "grid": [cp.height, cp.width], "zones": cp.n_zones,
-          "plans": "one shared descriptor"}
+          "plans": "one shared descriptor", "stochastic_convection": "off"}
   return env, None, desc
 
 
@@ -217,9 +220,10 @@ def run_sbx(args):
       a2 = copy.copy(args)
       a2.workload, a2.envs_per_gpu, a2.steps, a2.warmup = wl_name, envs, steps, 3
       try:
-        l2 = _measure(a2, torch, dist, rank, local_rank, world, dev, with_cpu=False)
+        l2 = _measure(a2, torch, dist, rank, local_rank, world, dev, with_cpu=wl_name == "office")
         others.append({k: l2[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step",
-                                          "config", "gpu_launches", "roofline", "e2e") if k in l2})
+                                          "config", "gpu_launches", "roofline", "e2e",
+                                          "cpu_baseline") if k in l2})
       except Exception as e:  # pylint: disable=broad-except
         others.append({"config": {"workload": wl_name, "envs_per_gpu": envs},
                        "error": f"{type(e).__name__}: {e}"})
@@ -378,8 +382,11 @@ def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
 
   # ---- CPU baseline beside it (rank 0, N=1 only) ----
   cpu = None
-  if with_cpu and rank == 0 and world == 1 and not args.no_cpu_baseline and args.workload == "randomized":
-    cpu = cpu_baseline(args, wl, K=args.cpu_sample_steps)
+  if with_cpu and rank == 0 and world == 1 and not args.no_cpu_baseline:
+    if args.workload == "randomized":
+      cpu = cpu_baseline(args, wl, K=args.cpu_sample_steps)
+    else:
+      cpu = cpu_baseline_calibrated(min(args.cpu_sample_steps, 12))
 
   line = {
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
@@ -429,6 +436,22 @@ def cpu_baseline(args, wl, K):
                     "oracle/ NumPy-fp32 restatement, one process per core"}
 
 
+def cpu_baseline_calibrated(K, warmup=2):
+  """The oracle on the calibrated building (BASELINE.json configs[0]): one building per
+  host core, K timed steps each after `warmup` untimed ones (the first step after
+  reset_temps.npy takes 7 sweeps, the steady state about 2)."""
+  from oracle import bench_support
+  from sbsim_b200 import workloads
+  cores = bench_support.host_cores()
+  rate, total, wall, sweeps = bench_support.time_calibrated_oracle(
+      CALIBRATED_FIXTURE, workloads.NORMALIZATION, workloads.HISTOGRAM, K, warmup, cores)
+  return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+          "sample": f"{cores} copies of the calibrated sb1 building (one per core) x {K} steps "
+                    f"after {warmup} warm-up steps ({total} env-steps, {wall:.1f} s wall, "
+                    f"{sweeps:.2f} sweeps/step), oracle/ NumPy-fp32 restatement of "
+                    "TFSimulator + Environment"}
+
+
 def run_reference(args):
   """--impl reference: the CPU restatement of the reference's own path (oracle
   port; the reference is Python with TensorFlow, which this image lacks) on all
@@ -439,8 +462,20 @@ def run_reference(args):
   from oracle import bench_support
   from sbsim_b200 import workloads
   if args.workload != "randomized":
-    emit({"impl": "reference", "unavailable":
-          "reference arm implemented for the randomized workload only"})
+    # calibrated building: ~7 env-steps/s/core -> bound the run to ~12 timed steps
+    K_eff = max(1, min(args.steps, 12))
+    cpu = cpu_baseline_calibrated(K_eff, warmup=min(max(args.warmup, 0), 3))
+    n = cpu["cores"]
+    emit({
+        "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT,
+        "n_gpus": args.gpus, "steps": K_eff, "warmup": min(max(args.warmup, 0), 3),
+        "ms_per_step": 1e3 * n / cpu["value"], "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "calibrated sb1 building 744x1004 (BASELINE.json configs[0/1])",
+                   "sample_envs": n, "grid": [744, 1004]},
+        "cpu_baseline": cpu,
+        "e2e": {"value": cpu["value"], "unit": UNIT, "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0}})
     return
   cores = bench_support.host_cores()
   n = args.cpu_sample_envs or min(max(cores * 128, 256), 4096)

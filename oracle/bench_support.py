@@ -58,6 +58,65 @@ def make_oracle_env(cp, low: float, high: float, convection: float, initial_temp
   return oenv.OracleEnvironment(cfg)
 
 
+def make_calibrated_oracle_env(fixture_path: str, normalization, histogram, episode_steps: int,
+                               occupancy: str = "randomized") -> oenv.OracleEnvironment:
+  """BASELINE.json configs[0]: the calibrated sb1 building (sim_config.gin:160-196) --
+  TF-Jacobi solver, reset_temps.npy, Moffett replay weather, US/Pacific schedule, the
+  shipped randomized occupancy -- from the committed fixture of its resource files."""
+  from sbsim_b200 import workloads      # plan compiler + the gin constants (host-side data only)
+  cal = workloads.load_calibrated(fixture_path)
+  occ = (oex.RandomizedArrivalDepartureOccupancy(1, 7, 12, 13, 18, 300, seed=17321,
+                                                 time_zone=workloads.CALIBRATED_TZ)
+         if occupancy == "randomized" else oex.ConstantOccupancy(0.7))
+  cfg = oenv.OracleEnvConfig(
+      plan=oracle_plan(cal.plan), start_timestamp=pd.Timestamp(workloads.CALIBRATED_START),
+      weather=oex.ReplayWeatherController(cal.weather_time_sec, cal.weather_temp_f, 100.0),
+      schedule=ohvac.SetpointSchedule(6, 19, (294, 297), (289, 298),
+                                      time_zone=workloads.CALIBRATED_TZ),
+      occupancy=occ,
+      reward_function=orew.SetpointEnergyCarbonRegretFunction(
+          300.0, 100.0, 160000, 400000, 0.5, 4.3, oex.ElectricityEnergyCost(),
+          oex.NaturalGasEnergyCost(), 0.2, 0.4, 0.4),
+      solver="tf", initial_temp=294.0, reset_temp_values=cal.reset_temps,
+      normalization={k: (f32(m), f32(v)) for k, (m, v) in normalization.items()},
+      histogram=histogram, discount_factor=0.9, num_timesteps_in_episode=episode_steps,
+      occupancy_normalization_constant=125.0)
+  return oenv.OracleEnvironment(cfg)
+
+
+def _calibrated_worker(args) -> Tuple[int, float, int]:
+  fixture, normalization, histogram, steps, warmup, seed = args
+  env = make_calibrated_oracle_env(fixture, normalization, histogram, steps + warmup + 8)
+  rng = np.random.default_rng(seed)
+  env.reset()
+  for _ in range(warmup):
+    env.step(rng.uniform(-1, 1, 2).astype(np.float32))
+  sweeps = 0
+  t0 = time.perf_counter()
+  for _ in range(steps):
+    env.step(rng.uniform(-1, 1, 2).astype(np.float32))
+    sweeps += env.info["n_sweeps"]
+  return steps, time.perf_counter() - t0, sweeps
+
+
+def time_calibrated_oracle(fixture: str, normalization, histogram, steps: int, warmup: int,
+                           n_procs: int):
+  """One calibrated building per host core, env b driven by default_rng(1000 + b)
+  (SURVEY 8d config 2's action streams).  Returns like time_oracle."""
+  jobs = [(fixture, normalization, histogram, steps, warmup, 1000 + i) for i in range(n_procs)]
+  t0 = time.perf_counter()
+  if n_procs == 1:
+    res = [_calibrated_worker(jobs[0])]
+  else:
+    ctx = mp.get_context("fork")
+    with ctx.Pool(n_procs) as pool:
+      res = pool.map(_calibrated_worker, jobs)
+  wall = time.perf_counter() - t0
+  total = sum(r[0] for r in res)
+  busy = max(r[1] for r in res)
+  return total / busy, total, wall, sum(r[2] for r in res) / max(total, 1)
+
+
 _WORKER_ENVS: List[oenv.OracleEnvironment] = []
 
 

@@ -199,6 +199,53 @@ class StepFunctionOccupancy:
     return before, during, after
 
 
+class RandomizedArrivalDepartureOccupancy:
+  """randomized_arrival_departure_occupancy.py:36-238, occupant by occupant (the
+  product's generator, sbsim_b200/exogenous.py, batches the draws of one call)."""
+
+  def __init__(self, zone_assignment, earliest_expected_arrival_hour,
+               latest_expected_arrival_hour, earliest_expected_departure_hour,
+               latest_expected_departure_hour, time_step_sec, seed=17321, time_zone="UTC"):
+    self._n = zone_assignment
+    self._arr = (earliest_expected_arrival_hour, latest_expected_arrival_hour)
+    self._dep = (earliest_expected_departure_hour, latest_expected_departure_hour)
+    step = pd.Timedelta(time_step_sec, unit="second")
+    self._p_arr = 1.0 / (pd.Timedelta(self._arr[1] - self._arr[0], unit="hour") / step / 2.0)   # :93-104
+    self._p_dep = 1.0 / (pd.Timedelta(self._dep[1] - self._dep[0], unit="hour") / step / 2.0)
+    self._rs = np.random.RandomState(seed)
+    self._tz = time_zone
+    self._work = {}              # zone_id -> list of bool (occupant is at WORK)
+
+  def _local(self, ts):                                        # :86-91
+    if ts.tz is None:
+      return ts
+    import zoneinfo
+    tz = {"US/Pacific": "America/Los_Angeles"}.get(self._tz, self._tz)
+    return ts.tz_convert(zoneinfo.ZoneInfo(tz) if isinstance(tz, str) and tz != "UTC" else tz)
+
+  def average_zone_occupancy(self, zone_id, start_time, end_time) -> float:  # :198-238
+    if zone_id not in self._work:
+      self._work[zone_id] = [False] * self._n
+    states = self._work[zone_id]
+    local = self._local(start_time)
+    day = pd.Timestamp(year=local.year, month=local.month, day=local.day)
+    count = 0.0
+    for i in range(self._n):                                   # ZoneOccupant.peek :127-147
+      if not is_work_day(day):
+        states[i] = False
+      elif not states[i]:
+        if not (local.hour < self._arr[0] or local.hour > self._arr[1]):     # :106-117
+          if self._rs.rand() < self._p_arr:
+            states[i] = True
+      else:
+        if not local.hour < self._dep[0]:                      # :119-125
+          if self._rs.rand() < self._p_dep:
+            states[i] = False
+      if states[i]:
+        count += 1.0
+    return count
+
+
 class ConstantOccupancy:
   """Trivial occupancy used by tz-aware scenarios (a BaseOccupancy, models/base_occupancy.py:27-46)."""
 

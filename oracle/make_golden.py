@@ -87,7 +87,8 @@ def _ref_modules():
           for k, v in names.items()}
 
 
-def build_reference_env(m, plan, solver, histogram=False, reward="regret", convection=None):
+def build_reference_env(m, plan, solver, histogram=False, reward="regret", convection=None,
+                        occupancy=None):
   """The scenario of tests/scenarios.py:Scenario() built from reference classes."""
   b = m["building"].FloorPlanBasedBuilding(
       cv_size_cm=20.0, floor_height_cm=300.0, initial_temp=292.0,
@@ -111,7 +112,7 @@ def build_reference_env(m, plan, solver, histogram=False, reward="regret", conve
   sim = cls(b, hv, weather, 300.0, 0.1, 100, 30, start)
   occ = m["occ"].StepFunctionOccupancy(pd.Timedelta(9, unit="h"), pd.Timedelta(17, unit="h"),
                                        1.0, 0.1)
-  sb = m["sb"].SimulatorBuilding(sim, occ)
+  sb = m["sb"].SimulatorBuilding(sim, occupancy or occ)
   rf = m["regret"].SetpointEnergyCarbonRegretFunction(
       300.0, 100.0, 160000, 400000, 0.5, 4.3, m["elec"].ElectricityEnergyCost(),
       m["gas"].NaturalGasEnergyCost(), 0.2, 0.4, 0.4)
@@ -165,6 +166,43 @@ def make_env_rollout(m, solver, histogram, n_steps, seed, reward="regret", conve
               zone_temps=np.array(zts), boiler_rates=np.array(blr), ahu_rates=np.array(ahu),
               final_temp=np.asarray(b.temp, dtype=np.float64),
               field_names=np.array(env._field_names))
+
+
+def make_occupancy_golden(m, n_steps=200):
+  """The shipped RandomizedArrivalDepartureOccupancy (sim_config.gin:185-196, two
+  occupants per zone here) under the unmodified reference Environment: every
+  average_zone_occupancy call the Environment makes is logged in order, so the
+  host generator of sbsim_b200.exogenous can be checked call for call."""
+  import importlib
+  rado = importlib.import_module(
+      "smart_buildings.smart_control.simulator.randomized_arrival_departure_occupancy")
+  occ = rado.RandomizedArrivalDepartureOccupancy(2, 7, 12, 13, 18, 300, seed=17321)
+  log = []
+  inner = occ.average_zone_occupancy
+
+  def logged(zone_id, start, end):
+    v = inner(zone_id, start, end)
+    log.append((zone_id, start, end, v))
+    return v
+
+  occ.average_zone_occupancy = logged
+  env, b = build_reference_env(m, small_plan(), "tf", occupancy=occ)
+  rng = np.random.default_rng(7)
+  ts = env.reset()
+  n_occ = [float(ts.observation[-1])]
+  rewards = [0.0]
+  for _ in range(n_steps):
+    ts = env.step(rng.uniform(-1, 1, 2).astype(np.float32))
+    n_occ.append(float(ts.observation[-1]))
+    rewards.append(float(ts.reward))
+  epoch = pd.Timestamp("1970-01-01")
+  zones = sorted({z for z, _, _, _ in log})
+  return dict(call_zone=np.array([zones.index(z) for z, _, _, _ in log]),
+              call_start_sec=np.array([(s - epoch).total_seconds() for _, s, _, _ in log]),
+              call_end_sec=np.array([(e - epoch).total_seconds() for _, _, e, _ in log]),
+              call_value=np.array([v for _, _, _, v in log]), zone_ids=np.array(zones),
+              num_occupants_feature=np.array(n_occ), rewards=np.array(rewards),
+              start="2023-07-06 05:00:00", n_steps=n_steps)
 
 
 def make_gs_golden(m):
@@ -268,6 +306,7 @@ def main():
                       **make_env_rollout(m, "tf", False, 60, 3, reward="energy_carbon"))
   np.savez_compressed(os.path.join(OUT, "ref_env_conv.npz"),
                       **make_env_rollout(m, "tf", False, 30, 4, convection=(1.0, 5, 5)))
+  np.savez_compressed(os.path.join(OUT, "ref_occupancy.npz"), **make_occupancy_golden(m))
   np.savez_compressed(os.path.join(OUT, "ref_gs_golden.npz"), **make_gs_golden(m))
   sb1, cal = make_sb1(m)
   np.savez_compressed(os.path.join(OUT, "sb1_calibrated.npz"), **sb1)

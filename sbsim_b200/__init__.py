@@ -16,7 +16,8 @@ from sbsim_b200.config import (ActionConfig, AirHandler, Boiler, BoundedActionNo
 from sbsim_b200.convection import StochasticConvectionSimulator
 from sbsim_b200.environment import BatchedWeather, Environment, SimulatorBuilding
 from sbsim_b200.exogenous import (ConstantOccupancy, ElectricityEnergyCost,
-                                  NaturalGasEnergyCost, ReplayWeatherController,
+                                  NaturalGasEnergyCost, RandomizedArrivalDepartureOccupancy,
+                                  ReplayWeatherController,
                                   SetpointSchedule, StepFunctionOccupancy, TableOccupancy,
                                   WeatherController)
 from sbsim_b200.floorplan import (CompiledPlan, MaterialProperties, compile_plan,
@@ -27,6 +28,7 @@ __all__ = [
     "CompiledPlan", "ConstantOccupancy", "ElectricityEnergyCost", "Environment",
     "FloorPlanBasedHvac", "HistogramReducer", "LIB_PATH", "MaterialProperties",
     "NaturalGasEnergyCost", "PATH_AUTO", "PATH_RESIDENT", "PATH_STREAMING",
+    "RandomizedArrivalDepartureOccupancy",
     "ReplayWeatherController", "SbxLibraryError", "SetpointEnergyCarbonRegretFunction",
     "SetpointEnergyCarbonRewardFunction",
     "SetpointSchedule", "SimulatorBuilding", "StandardScoreObservationNormalizer",

@@ -225,7 +225,9 @@ class Environment:
         and b.occupancy.reward_table.shape[1] > 1)
     cfg.n_occ_zones = b.n_zones if per_zone_occ else 1
     cfg.episode_steps = self._num_timesteps_in_episode
-    cfg.n_table_steps = self._num_timesteps_in_episode + 3
+    # rows 0 .. N+1: an episode is N+1 steps (the terminal one included), and the
+    # reference never evaluates weather / occupancy beyond t_{N+1} either
+    cfg.n_table_steps = self._num_timesteps_in_episode + 2
     cfg.kernel_path = int(kernel_path)
     cfg.solver = (_lib.SOLVER_GAUSS_SEIDEL if b.solver == "gauss_seidel"
                   else _lib.SOLVER_TF_JACOBI)
@@ -367,8 +369,23 @@ class Environment:
     h.upload("comfort", sched.table(ts))
     soon = pd.Timedelta(60, unit="minute")
     h.upload("comfort_soon", sched.table([t + soon for t in ts]))
+    self._upload_occupancy()
+    pe, ce, pg = exogenous.energy_tables(self.reward_function.electricity_energy_cost,
+                                         self.reward_function.natural_gas_energy_cost, ts)
+    h.upload("price_elec", pe)
+    h.upload("carbon_elec", ce)
+    h.upload("price_gas", pg)
+    h.upload("time_features", exogenous.time_feature_table(ts))
+
+  def _upload_occupancy(self):
+    """Occupancy tables of ONE episode.  A stateful model (the shipped
+    RandomizedArrivalDepartureOccupancy) keeps drawing from its generator, so the
+    tables are rebuilt at every reset after the first, continuing the stream like
+    the reference does over consecutive (complete) episodes."""
+    b, h = self.building, self._handle
+    T = self._cfg.n_table_steps
     occ_r, occ_o, occ_z = exogenous.occupancy_tables(
-        b.occupancy, b.zone_ids or ["zone_id_0"], ts, b.time_step_sec,
+        b.occupancy, b.zone_ids or ["zone_id_0"], self._timestamps, b.time_step_sec,
         per_zone=self._cfg.n_occ_zones > 1)
     if occ_r.shape[0] < T or occ_o.shape[0] < T:
       raise ValueError("occupancy tables shorter than the episode")
@@ -376,12 +393,11 @@ class Environment:
     h.upload("occ_obs", occ_o[:T])
     if occ_z is not None:      # per-building count of the zones each plan really has
       h.upload("occ_obs_zone", occ_z[:T])
-    pe, ce, pg = exogenous.energy_tables(self.reward_function.electricity_energy_cost,
-                                         self.reward_function.natural_gas_energy_cost, ts)
-    h.upload("price_elec", pe)
-    h.upload("carbon_elec", ce)
-    h.upload("price_gas", pg)
-    h.upload("time_features", exogenous.time_feature_table(ts))
+    self._occupancy_episodes = getattr(self, "_occupancy_episodes", 0) + 1
+
+  def _before_reset(self):
+    if getattr(self.building.occupancy, "stateful", False) and self._current_time_step is not None:
+      self._upload_occupancy()
 
   # ---- PyEnvironment surface ----------------------------------------------
 
@@ -461,6 +477,7 @@ class Environment:
 
   def reset(self) -> specs.TimeStep:
     """Environment._reset (environment.py:1165-1212) for every env."""
+    self._before_reset()
     self._handle.reset_host(self._obs, self._reward, self._step_type, self._discount)
     self._episode_ended = False
     self._step_count = 0
@@ -520,6 +537,7 @@ class Environment:
 
   def reset_device(self, obs, reward, step_type, discount, stream: int = 0):
     """Like reset() but writes into caller-owned CUDA tensors (asynchronous)."""
+    self._before_reset()
     self._handle.reset_device(obs.data_ptr(), reward.data_ptr(), step_type.data_ptr(),
                               discount.data_ptr(), stream)
     self._episode_ended = False

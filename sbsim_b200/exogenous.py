@@ -282,6 +282,70 @@ class ConstantOccupancy:
     return self.value
 
 
+class RandomizedArrivalDepartureOccupancy:
+  """The shipped occupancy model (randomized_arrival_departure_occupancy.py:36-238;
+  sim_config.gin:185-196): `zone_assignment` occupants per zone arrive between
+  the earliest and latest arrival hour and leave after the earliest departure
+  hour, one Bernoulli draw per occupant per call from ONE shared
+  numpy RandomState(seed).
+
+  The model is stateful and advances its generator on every call, so the
+  per-step tables must be produced in the reference's call order (see
+  `occupancy_tables`): the observation's `num_occupants` at reset, then per step
+  the reward's occupancy of every zone followed by the observation's.  The
+  draws of all occupants of one (zone, time) call are taken with one
+  `rand(k)`, which yields the same stream as k successive `rand()` calls.
+  """
+
+  stateful = True
+  per_zone = True
+
+  def __init__(self, zone_assignment: int, earliest_expected_arrival_hour: int,
+               latest_expected_arrival_hour: int, earliest_expected_departure_hour: int,
+               latest_expected_departure_hour: int, time_step_sec: int,
+               seed: Optional[int] = 17321, time_zone="UTC"):
+    assert (earliest_expected_arrival_hour < latest_expected_arrival_hour
+            < earliest_expected_departure_hour < latest_expected_departure_hour)
+    self._zone_assignment = int(zone_assignment)
+    self._arrival = (earliest_expected_arrival_hour, latest_expected_arrival_hour)
+    self._departure = (earliest_expected_departure_hour, latest_expected_departure_hour)
+    step = pd.Timedelta(time_step_sec, unit="second")
+    # ZoneOccupant._get_event_probability :93-104: p = 1 / (window / step / 2)
+    self._p_arrival = 1.0 / (pd.Timedelta(self._arrival[1] - self._arrival[0], unit="hour")
+                             / step / 2.0)
+    self._p_departure = 1.0 / (pd.Timedelta(self._departure[1] - self._departure[0],
+                                            unit="hour") / step / 2.0)
+    self._random_state = np.random.RandomState(seed)
+    self._time_zone = resolve_timezone(time_zone)
+    self._at_work = {}           # zone_id -> bool[zone_assignment]
+
+  def average_zone_occupancy(self, zone_id: str, start_time: pd.Timestamp,
+                             end_time: pd.Timestamp) -> float:
+    """:198-238 with ZoneOccupant.peek :127-147 inlined over the zone's occupants."""
+    state = self._at_work.get(zone_id)
+    if state is None:
+      state = self._at_work[zone_id] = np.zeros(self._zone_assignment, dtype=bool)
+    local = start_time if start_time.tz is None else start_time.tz_convert(self._time_zone)
+    day = pd.Timestamp(year=local.year, month=local.month, day=local.day)
+    hour = local.hour
+    if not is_work_day(day):
+      state[:] = False
+      return 0.0
+    # AWAY occupants draw only inside [earliest, latest] arrival hours (:106-117);
+    # WORK occupants draw once the earliest departure hour is reached (:119-125)
+    arrive = (~state) if self._arrival[0] <= hour <= self._arrival[1] else np.zeros_like(state)
+    depart = state if hour >= self._departure[0] else np.zeros_like(state)
+    draws = arrive | depart
+    k = int(draws.sum())
+    if k:
+      r = self._random_state.rand(k)
+      p = np.where(arrive[draws], self._p_arrival, self._p_departure)
+      flip = np.zeros_like(state)
+      flip[draws] = r < p
+      state ^= flip
+    return float(state.sum())
+
+
 class TableOccupancy:
   """Replays a host-generated [T, Z] table (e.g. produced by the reference's
   RandomizedArrivalDepartureOccupancy)."""
@@ -310,6 +374,26 @@ def occupancy_tables(occupancy, zone_ids: Sequence[str], timestamps, time_step_s
   rew = np.zeros((len(timestamps), zo), dtype=np.float64)
   obs = np.zeros(len(timestamps), dtype=np.int32)
   obs_zone = np.zeros((len(timestamps), zo), dtype=np.float64)
+  if getattr(occupancy, "stateful", False):
+    # Call order of the reference for a model that advances a generator on every
+    # call: _reset -> _get_observation -> num_occupants(t_0)
+    # (environment.py:1165-1212, simulator_building.py:305-315); then each _step
+    # (environment.py:1298-1306): _get_observation -> num_occupants(t_s) for every
+    # zone, then _get_reward -> reward_info -> occupancy(z, t_s, t_s + dt) for every
+    # zone (simulator_flexible_floor_plan.py:192-230).  Row 0 of the reward table
+    # is never read, so it draws nothing.
+    if not per_zone:
+      raise ValueError("a stateful occupancy model needs per-zone tables")
+    for s, ts in enumerate(timestamps):
+      n = 0.0
+      for z, zid in enumerate(zone_ids):
+        obs_zone[s, z] = occupancy.average_zone_occupancy(zid, ts - five, ts)
+        n += obs_zone[s, z]
+      obs[s] = int(n)
+      if s > 0:
+        for z, zid in enumerate(zone_ids):
+          rew[s, z] = occupancy.average_zone_occupancy(zid, ts, ts + dt)
+    return rew, obs, obs_zone
   for s, ts in enumerate(timestamps):
     if per_zone:
       for z, zid in enumerate(zone_ids):

@@ -4,11 +4,14 @@
                     floor plans, wall/exterior materials, CV size, initial
                     temperature, sinusoid weather and convection coefficient
                     ("Config 3").
-  calibrated(...)   configs 1/2: B copies of one large plan.  The calibrated
-                    744x1004 sb1 plan lives in the reference tree, which is not
-                    present on the GPU box; `synthetic_office_plan` generates a
-                    plan of the same size class (same grid, ~126 zones) so that
-                    config 2's memory footprint and kernel path are exercised.
+  make_calibrated_env(...)
+                    configs 1/2: B copies of the calibrated sb1 building
+                    (744x1004 CVs, 126 zones; sim_config.gin:160-196): floor plan,
+                    reset temperatures and the Moffett Field weather rows come from
+                    a committed fixture of the reference's resource files
+                    (tests/golden/sb1_calibrated.npz, written by
+                    oracle/make_golden.py), the devices, schedule, occupancy model,
+                    reward and normalisation constants from the gin file.
 """
 
 from __future__ import annotations
@@ -142,6 +145,69 @@ def make_randomized_env(n_envs: int, seed: int = 2024, episode_steps: int = 288,
       observation_histogram_reducer=sbx.HistogramReducer(HISTOGRAM) if histogram else None,
       device=device, kernel_path=kernel_path)
   return env, wl
+
+
+CALIBRATED_START = "2023-07-06 07:00:00+00:00"   # sim_config.gin:164
+CALIBRATED_TZ = "US/Pacific"                       # sim_config.gin:20
+CALIBRATED_CONVECTION = (1.0, 5, 5)                # StochasticConvectionSimulator p, distance, seed (:37-39)
+
+
+@dataclasses.dataclass
+class CalibratedBuilding:
+  plan: floorplan.CompiledPlan
+  reset_temps: np.ndarray          # fp64 [744, 1004], reset_temps.npy
+  weather_time_sec: np.ndarray     # Moffett Field CSV rows covering the episode
+  weather_temp_f: np.ndarray
+
+
+def load_calibrated(fixture_path: str) -> CalibratedBuilding:
+  """The calibrated building of sim_config.gin:42-99 from the committed fixture."""
+  g = np.load(fixture_path)
+  cp = floorplan.compile_plan(
+      g["floor_plan"].astype(np.int64), None, cv_size_cm=10.0,
+      inside_air=floorplan.MaterialProperties(50.0, 700.0, 1.0),
+      inside_wall=floorplan.MaterialProperties(50.0, 1.0, 700.0),
+      building_exterior=floorplan.MaterialProperties(0.05, 700.0, 1.0),
+      buffer_from_walls=3)
+  return CalibratedBuilding(cp, np.asarray(g["reset_temps"], dtype=np.float64),
+                            np.asarray(g["weather_time_sec"], dtype=np.float64),
+                            np.asarray(g["weather_temp_f"], dtype=np.float64))
+
+
+def calibrated_occupancy(kind: str = "randomized"):
+  """sim_config.gin:179-196 ("randomized", the shipped model) or a constant 0.7
+  occupants per zone ("const", the deterministic stand-in of the parity tests: the
+  reference's StepFunctionOccupancy raises on the tz-aware start timestamp)."""
+  if kind == "randomized":
+    return exogenous.RandomizedArrivalDepartureOccupancy(
+        1, 7, 12, 13, 18, time_step_sec=300, seed=17321, time_zone=CALIBRATED_TZ)
+  if kind == "const":
+    return exogenous.ConstantOccupancy(0.7)
+  raise ValueError(kind)
+
+
+def make_calibrated_env(cal: CalibratedBuilding, n_envs: int, episode_steps: int = 288,
+                        histogram: bool = True, device: int = 0,
+                        kernel_path: int = sbx.PATH_AUTO, occupancy: str = "randomized",
+                        convection=None) -> sbx.Environment:
+  """Configs 1/2: n_envs copies of the calibrated building (one shared descriptor),
+  Moffett replay weather, reset_temps.npy, schedule in US/Pacific."""
+  weather = sbx.ReplayWeatherController(times_utc_sec=cal.weather_time_sec,
+                                        temps_f=cal.weather_temp_f,
+                                        convection_coefficient=100.0)
+  building = sbx.SimulatorBuilding(
+      cal.plan, calibrated_hvac(CALIBRATED_TZ), weather, calibrated_occupancy(occupancy),
+      n_envs=n_envs, time_step_sec=300.0, convergence_threshold=0.1, iteration_limit=100,
+      start_timestamp=pd.Timestamp(CALIBRATED_START), floor_height_cm=300.0,
+      initial_temp=294.0, reset_temp_values=cal.reset_temps.astype(np.float32),
+      convection_simulator=convection)
+  return sbx.Environment(
+      building, calibrated_reward(), sbx.StandardScoreObservationNormalizer(NORMALIZATION),
+      calibrated_action_config(), discount_factor=0.9,
+      num_days_in_episode=(episode_steps + 0.5) * 300.0 / 86400.0,
+      occupancy_normalization_constant=125.0,
+      observation_histogram_reducer=sbx.HistogramReducer(HISTOGRAM) if histogram else None,
+      time_zone=CALIBRATED_TZ, device=device, kernel_path=kernel_path)
 
 
 def synthetic_office_plan(height: int = 744, width: int = 1004, rooms_y: int = 9,

@@ -168,3 +168,56 @@ def test_environment_rejects_bad_discount_before_touching_the_gpu():
   sc = S.Scenario(floor_plan=S.small_plan(), discount=1.5)
   with pytest.raises(ValueError, match=r"Discount factor must be in \(0,1\]"):
     S.make_env(sc)
+
+
+def test_randomized_occupancy_matches_reference_call_log():
+  """RandomizedArrivalDepartureOccupancy (randomized_arrival_departure_occupancy.py:36-238):
+  the host generator reproduces, call for call, what the unmodified reference
+  Environment drew from the shipped model (fixture ref_occupancy.npz, written by
+  oracle/make_golden.py:make_occupancy_golden)."""
+  import os
+  from sbsim_b200 import exogenous
+  g = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                           "ref_occupancy.npz"))
+  zone_ids = [str(z) for z in g["zone_ids"]]
+  n = int(g["n_steps"])
+  occ = exogenous.RandomizedArrivalDepartureOccupancy(2, 7, 12, 13, 18, 300, seed=17321)
+  ts = exogenous.step_timestamps(pd.Timestamp(str(g["start"])), 300.0, n + 1)
+  rew, obs, obs_zone = exogenous.occupancy_tables(occ, zone_ids, ts, 300.0, per_zone=True)
+  # replay the reference's call order from the tables
+  Z = len(zone_ids)
+  values, starts = [], []
+  epoch = pd.Timestamp("1970-01-01")
+  for s in range(n + 1):
+    values += [obs_zone[s, z] for z in range(Z)]
+    starts += [(ts[s] - pd.Timedelta(5, unit="minute") - epoch).total_seconds()] * Z
+    if s > 0:
+      values += [rew[s, z] for z in range(Z)]
+      starts += [(ts[s] - epoch).total_seconds()] * Z
+  np.testing.assert_array_equal(np.array(starts), g["call_start_sec"])
+  np.testing.assert_array_equal(np.array(values), g["call_value"])
+  # and the observation feature the Environment derived from it (environment.py:952-956)
+  np.testing.assert_allclose((obs - 3.0) / 4.0, g["num_occupants_feature"], rtol=1e-6)
+  assert 0 < g["call_value"].sum() < 2 * len(g["call_value"])
+
+
+def test_randomized_occupancy_tz_aware_matches_oracle_restatement():
+  """Same model on the calibrated config's tz-aware clock (sim_config.gin:164, :20): the
+  batched host generator against the occupant-by-occupant restatement in oracle/."""
+  from sbsim_b200 import exogenous
+  from oracle import exogenous as oex
+  zone_ids = [f"zone_id_{i}" for i in range(5)]
+  ts = exogenous.step_timestamps(pd.Timestamp("2023-07-06 07:00:00+00:00"), 300.0, 400)
+  a = exogenous.RandomizedArrivalDepartureOccupancy(3, 7, 12, 13, 18, 300, seed=17321,
+                                                    time_zone="US/Pacific")
+  b = oex.RandomizedArrivalDepartureOccupancy(3, 7, 12, 13, 18, 300, seed=17321,
+                                              time_zone="US/Pacific")
+  rew, obs, obs_zone = exogenous.occupancy_tables(a, zone_ids, ts, 300.0, per_zone=True)
+  five, dt = pd.Timedelta(5, unit="minute"), pd.Timedelta(300, unit="s")
+  for s, t in enumerate(ts):
+    for z, zid in enumerate(zone_ids):
+      assert obs_zone[s, z] == b.average_zone_occupancy(zid, t - five, t)
+    if s > 0:
+      for z, zid in enumerate(zone_ids):
+        assert rew[s, z] == b.average_zone_occupancy(zid, t, t + dt)
+  assert obs.max() > 5 and obs.min() == 0

@@ -32,7 +32,11 @@ class StochasticConvectionSimulator:
     self._p = p
     self._distance = distance
     self._seed = seed
-    self._cache: Dict[int, Dict[Tuple[int, int], List[Tuple[int, int]]]] = {}
+    # swap candidates per (room list, max distance, CV).  The reference keeps one simulator
+    # -- and so one cache -- per building (stochastic_convection_simulator.py:120-134); a
+    # batch with one plan per env must not reuse env 0's candidates for another plan's room
+    # at the same coordinates, so the cache is keyed by the identity of the room list.
+    self._cache: Dict[Tuple[int, int], Dict[Tuple[int, int], List[Tuple[int, int]]]] = {}
 
   def make_stream(self) -> _random.Random:
     return _random.Random(self._seed) if self._seed is not None else _random.Random()
@@ -53,7 +57,7 @@ class StochasticConvectionSimulator:
       if distance == -1 and p == 1:
         self._shuffle_no_max_dist(v, idx, rng)
       else:
-        self._shuffle_max_dist(p, v, distance, idx, rng)
+        self._shuffle_max_dist(p, v, distance, idx, rng, cache_key=id(v))
     return idx.ravel().astype(np.int32)
 
   @staticmethod
@@ -65,11 +69,11 @@ class StochasticConvectionSimulator:
     for i, cv in enumerate(shuffled):
       arr[cv[0], cv[1]] = vals[v[i]]
 
-  def _shuffle_max_dist(self, p, v, max_dist, arr, rng):
+  def _shuffle_max_dist(self, p, v, max_dist, arr, rng, cache_key=0):
     if max_dist == -1:
       max_dist = 1000
     members = set(v)
-    cache = self._cache.setdefault(max_dist, {})
+    cache = self._cache.setdefault((cache_key, max_dist), {})
     swaps = []
     for val in v:
       if rng.uniform(0, 1) > p:

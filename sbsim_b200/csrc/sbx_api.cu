@@ -25,6 +25,7 @@
 
 #include "../../include/sbx.h"
 #include "sbx_kernels.cuh"
+#include "sbx_resident2.cuh"
 
 using namespace sbx;
 
@@ -52,6 +53,10 @@ struct sbx_env {
   size_t resident_smem = 0;
   CUtensorMap tmap_t;            // [B, H, W] temperature field, box [1, H, P] (k_resident_step)
   size_t gs_smem = 0;
+  // k_resident_step2 (persistent, record-driven) when the grid allows it and no plan
+  // overflows its list capacities; otherwise k_resident_step
+  int v2_capable = 0, use_v2 = 0, v1_allocated = 0;
+  int resident2_ctas_per_sm = 0;
   Params P;
   // host-level episode state
   int step_count = 0, time_index = 0, episode_ended = 0, reset_called = 0;
@@ -269,7 +274,27 @@ int timing_record(sbx_handle h, std::vector<cudaEvent_t>& pool, size_t& used, cu
   return SBX_OK;
 }
 
+// CTAs of a k_resident_step2 launch over buildings [b_begin, b_end): one per resident slot
+unsigned v2_grid(const sbx_handle h) {
+  const unsigned nb = (unsigned)(h->P.b_end - h->P.b_begin);
+#if SBX_R2_PERSISTENT
+  const unsigned slots = (unsigned)(h->n_sms * (h->resident2_ctas_per_sm > 0 ? h->resident2_ctas_per_sm : 1));
+  return nb < slots ? nb : slots;
+#else
+  return nb;                              // one building per CTA
+#endif
+}
+// building whose list sizes ride in building b's header: the one the same SM slot takes next
+int v2_next_distance(const sbx_handle h) {
+#if SBX_R2_PERSISTENT
+  return (int)v2_grid(h);
+#else
+  return h->P.prefetch_dist;
+#endif
+}
+
 int launch_pre(sbx_handle h, cudaStream_t st) {
+  h->P.v2_stride = v2_next_distance(h);  // build_header stores the next building's list sizes
   const Params& p = h->P;
   const int G = hvac_group(h), bpc = 128 / G;          // buildings per CTA
   const unsigned grid = (unsigned)((p.b_end - p.b_begin + bpc - 1) / bpc);
@@ -367,18 +392,51 @@ int make_plane_tensor_map(sbx_handle h, float* base, int B, int H, int W, int P)
   return SBX_OK;
 }
 
+// v1 structures (packed descriptor plane, vector list, zone-sum list) exist only when
+// k_resident_step is the kernel in use
+int ensure_v1_buffers(sbx_handle h) {
+  if (h->v1_allocated) return SBX_OK;
+  Params& p = h->P;
+  const sbx_config& c = h->cfg;
+  uint16_t* dp = nullptr; uint16_t* ql = nullptr; int32_t* nf = nullptr; uint32_t* rl = nullptr; int32_t* rc = nullptr;
+  if (int rc_ = dev_alloc<uint16_t>(h, &dp, (size_t)c.n_plans * p.geom.desc_stride)) return rc_;
+  if (int rc_ = dev_alloc<uint16_t>(h, &ql, (size_t)c.n_plans * p.geom.list_stride)) return rc_;
+  if (int rc_ = dev_alloc<int32_t>(h, &nf, (size_t)c.n_plans * 4)) return rc_;
+  if (int rc_ = dev_alloc<uint32_t>(h, &rl, (size_t)c.n_plans * p.geom.rl_cap)) return rc_;
+  if (int rc_ = dev_alloc<int32_t>(h, &rc, (size_t)c.n_plans)) return rc_;
+  p.desc_packed = dp; p.qlist = ql; p.n_fast = nf; p.rlist = rl; p.rl_chunks = rc;
+  h->v1_allocated = 1;
+  return SBX_OK;
+}
+
 int prepare_plans(sbx_handle h, cudaStream_t st) {
   if (!h->plans_dirty) return SBX_OK;
-  const Params& p = h->P;
-  const size_t smem = (sizeof(uint32_t) + sizeof(uint16_t)) * (size_t)(p.H * p.W / h->V);
+  Params& p = h->P;
   cudaError_t e;
-  if (h->V == 4) e = cudaFuncSetAttribute(k_prepare_plan<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  else e = cudaFuncSetAttribute(k_prepare_plan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-  if (h->V == 4) k_prepare_plan<4><<<p.n_plans, kPrepThreads, smem, st>>>(p);
-  else k_prepare_plan<1><<<p.n_plans, kPrepThreads, smem, st>>>(p);
-  if (int rc = launch_check(h, "k_prepare_plan")) return rc;
-  {
+  h->use_v2 = 0;
+  if (h->v2_capable) {
+    const size_t sm = prepare2_smem(p.H * (p.W / 4), p.Z);
+    e = cudaFuncSetAttribute(k_prepare_plan2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    k_prepare_plan2<<<p.n_plans, kPrepThreads, sm, st>>>(p);
+    if (int rc = launch_check(h, "k_prepare_plan2")) return rc;
+    // any plan whose lists do not fit sends the handle back to k_resident_step
+    std::vector<int32_t> counts((size_t)p.n_plans * 8);
+    CUDA_TRY(h, cudaMemcpyAsync(counts.data(), p.counts2, counts.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+    CUDA_TRY(h, cudaStreamSynchronize(st));
+    h->use_v2 = 1;
+    for (int i = 0; i < p.n_plans; ++i)
+      if (counts[(size_t)i * 8 + 7] < 0) { h->use_v2 = 0; break; }
+  }
+  if (!h->use_v2) {
+    if (int rc = ensure_v1_buffers(h)) return rc;
+    const size_t smem = (sizeof(uint32_t) + sizeof(uint16_t)) * (size_t)(p.H * p.W / h->V);
+    if (h->V == 4) e = cudaFuncSetAttribute(k_prepare_plan<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    else e = cudaFuncSetAttribute(k_prepare_plan<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+    if (h->V == 4) k_prepare_plan<4><<<p.n_plans, kPrepThreads, smem, st>>>(p);
+    else k_prepare_plan<1><<<p.n_plans, kPrepThreads, smem, st>>>(p);
+    if (int rc = launch_check(h, "k_prepare_plan")) return rc;
     const size_t n_items = (size_t)(p.H * p.W / h->V);
     const size_t sm2 = sizeof(uint2) * n_items + sizeof(int) * 2 * (size_t)(p.Z + 1);
     if (h->V == 4) e = cudaFuncSetAttribute(k_prepare_reduce<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm2);
@@ -395,6 +453,7 @@ int prepare_plans(sbx_handle h, cudaStream_t st) {
 // The solve of buildings [p.b_begin, p.b_end).  `with_header`: the per-building solve
 // header has not been built by k_pre (sbx_fd_step, which has no HVAC prologue).
 int run_resident(sbx_handle h, cudaStream_t st, bool with_header) {
+  h->P.v2_stride = v2_next_distance(h);
   const Params& p = h->P;
   if (h->cfg.solver == SBX_SOLVER_GAUSS_SEIDEL) {
     if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
@@ -409,6 +468,12 @@ int run_resident(sbx_handle h, cudaStream_t st, bool with_header) {
   }
   const unsigned grid = (unsigned)(p.b_end - p.b_begin);
   if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
+  if (h->use_v2) {
+    // persistent CTAs: one per resident slot, each walks buildings b, b + grid, ...
+    k_resident_step2<<<v2_grid(h), kR2Threads, p.g2.total, st>>>(p, h->tmap_t);
+    if (int rc = launch_check(h, "k_resident_step2")) return rc;
+    return timing_record(h, h->t_solve, h->t_solve_used, st);
+  }
   if (h->V == 4) k_resident_step<4><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
   else k_resident_step<1><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
   if (int rc = launch_check(h, "k_resident_step")) return rc;
@@ -615,8 +680,29 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.zone_ncv, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.zone_ndiff, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.obs_zone_order, int32_t, (size_t)c.n_plans * Z);
-  ALLOC(p.desc_packed, uint16_t, (size_t)c.n_plans * p.geom.desc_stride);
   ALLOC(p.desc_spk, uint16_t, h->path == SBX_PATH_STREAMING ? (size_t)c.n_plans * N : 1);
+  h->v2_capable = 0;
+  if (h->path == SBX_PATH_RESIDENT && c.solver == SBX_SOLVER_TF_JACOBI && h->V == 4 && L.use_tmap &&
+      !getenv("SBX_RESIDENT_V1")) {
+    p.g2 = resident2_geom(L, c.height, c.width, (int)Z);
+    if (p.g2.total <= max_optin) {
+      cudaError_t e2 = cudaFuncSetAttribute(k_resident_step2, cudaFuncAttributeMaxDynamicSharedMemorySize, p.g2.total);
+      int nb2 = 0;
+      if (e2 == cudaSuccess) e2 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb2, k_resident_step2, kR2Threads, p.g2.total);
+      if (e2 != cudaSuccess) { fail(h, SBX_E_CUDA, "k_resident_step2 set-up failed: %s", cudaGetErrorString(e2)); return bail(SBX_E_CUDA); }
+      if (nb2 > 0) {
+        h->v2_capable = 1;
+        h->resident2_ctas_per_sm = nb2;
+        ALLOC(p.flist2, uint16_t, (size_t)c.n_plans * L.list_stride);
+        ALLOC(p.rec2, uint4, (size_t)c.n_plans * p.g2.rec_cap);
+        ALLOC(p.sched2, uint32_t, (size_t)c.n_plans * r2_sched_cap(c.height * (c.width / 4)));
+        ALLOC(p.counts2, int32_t, (size_t)c.n_plans * 8);
+        ALLOC(p.zfull, uint16_t, (size_t)c.n_plans * p.g2.zfull_cap);
+        ALLOC(p.zpart, uint32_t, (size_t)c.n_plans * p.g2.zpart_cap);
+        ALLOC(p.zchunk, uint8_t, (size_t)c.n_plans * p.g2.zchunk_cap);
+      }
+    }
+  }
   // Measured on B200 (4096 x 744x1004): 10.1 ms per sweep against 9.3 ms for the
   // rolling-window k_sweep, so the list-driven sweep is off unless SBX_OPT_LIST_SWEEP asks.
   h->list_sweep = 0;
@@ -626,11 +712,7 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
     ALLOC(p.tlist, uint16_t, list_capable ? (size_t)c.n_plans * tg.tiles * kTileEntries : 1);
     ALLOC(p.tcount, int32_t, list_capable ? (size_t)c.n_plans * tg.tiles * 2 : 2);
   }
-  ALLOC(p.qlist, uint16_t, (size_t)c.n_plans * p.geom.list_stride);
-  ALLOC(p.n_fast, int32_t, (size_t)c.n_plans * 4);
   ALLOC(p.hdr, unsigned char, B * header_bytes((int)Z));
-  ALLOC(p.rlist, uint32_t, (size_t)c.n_plans * p.geom.rl_cap);
-  ALLOC(p.rl_chunks, int32_t, (size_t)c.n_plans);
   ALLOC(p.reset_temps, float, (size_t)c.n_reset * N);
   ALLOC(p.initial_temp, float, B);
   ALLOC(p.ambient, double, (size_t)c.n_weather * T);
@@ -725,8 +807,10 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   // than the monolithic step -- the cross-stream event hand-offs cost more than the
   // exposed HVAC kernels they hide.  The option stays for callers with other shapes.
   h->n_chunks = 1;
-  if (h->path == SBX_PATH_RESIDENT && c.solver == SBX_SOLVER_TF_JACOBI)
-    h->P.prefetch_dist = h->n_sms * (h->resident_ctas_per_sm > 0 ? h->resident_ctas_per_sm : 1);
+  if (h->path == SBX_PATH_RESIDENT && c.solver == SBX_SOLVER_TF_JACOBI) {
+    const int per_sm = h->v2_capable ? h->resident2_ctas_per_sm : h->resident_ctas_per_sm;
+    h->P.prefetch_dist = h->n_sms * (per_sm > 0 ? per_sm : 1);
+  }
   h->h_comfort = new (std::nothrow) uint8_t[T]();
   if (!h->h_comfort) { fail(h, SBX_E_NOMEM, "out of host memory"); return bail(SBX_E_NOMEM); }
   *out = h;

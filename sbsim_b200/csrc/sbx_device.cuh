@@ -58,9 +58,20 @@ struct ResidentGeom {
   int off_a, off_b, off_n3, off_desc, off_list, off_rlist, off_hdr, off_bins, off_wmax, off_bar, total;
 };
 
+// Shared-memory layout and per-plan list capacities of k_resident_step2 (sbx_resident2.cuh)
+struct Resident2Geom {
+  int rec_cap;       // 16-byte records (non-FAST, non-EXT vectors) per plan
+  int zfull_cap;     // u16 entries of the zone-sum list's single-zone section
+  int zpart_cap;     // u32 entries of its masked section
+  int zchunk_cap;    // u8 zone slot per 32-entry chunk
+  int off_p0, off_p1, off_p2, off_flist, off_sched, off_rec, off_zfull, off_zpart, off_zchunk, off_hdr,
+      off_bins, off_misc, off_bar, total;
+};
+
 // Everything a kernel needs; passed by value.
 struct Params {
   ResidentGeom geom;
+  Resident2Geom g2;
   // sizes
   int B, H, W, Z, n_plans, n_weather, n_reset, n_occ_zones, T_rows;
   int obs_mode, D, n_actions;
@@ -99,6 +110,14 @@ struct Params {
   uint32_t* rlist;           // [P, rl_cap] zone-sum list (k_prepare_reduce)
   int32_t* rl_chunks;        // [P] warps' worth of entries in it, -1 = does not fit
   unsigned char* hdr;        // [B, header_bytes(Z)] per-building solve header (k_build_header)
+  // k_resident_step2 (k_prepare_plan2): per-plan lists
+  uint16_t* flist2;          // [P, list_stride] FAST slots then EXT slots
+  uint32_t* sched2;          // [P, r2_sched_cap] per-warp work schedule of the sweeps
+  uint4* rec2;               // [P, rec_cap] MEDIUM (no heat / heat) then SLOW (no heat / heat) records
+  int32_t* counts2;          // [P, 8] n_fast, n_ext, n_heads, sched words, -, n_rec, n_full_chunks, n_part_chunks (-1: a list overflowed)
+  uint16_t* zfull;           // [P, zfull_cap]
+  uint32_t* zpart;           // [P, zpart_cap]
+  uint8_t* zchunk;           // [P, zchunk_cap]
   const float* reset_temps;  // [n_reset,H,W]
   const float* initial_temp; // [B]
   // tables
@@ -156,6 +175,7 @@ struct Params {
   // per call
   int b_begin, b_end;        // buildings [b_begin, b_end) are this launch's share of the batch
   int build_hdr;             // k_pre also builds the resident solve header of its buildings
+  int v2_stride;             // k_resident_step2: CTAs of the launch (building b's CTA takes b + v2_stride next)
   int prefetch_dist;         // resident solve: CTA b prefetches building b + prefetch_dist into L2 (0 = off)
   int time_index;            // s: this step simulates [t_s, t_s + dt)
   int step_count;

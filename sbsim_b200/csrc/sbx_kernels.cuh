@@ -186,8 +186,16 @@ __device__ __forceinline__ void tma_store_wait() {
 __host__ __device__ inline size_t header_q_slots(int Z) { return (size_t)((Z + 1 + 3) / 4) * 4; }
 // + 8 scalars {T_inf, h, n_fast, n_fast+n_med, n_fast+n_med+n_ext, n_reduce_chunks, 0, 0}
 // + 3 x {k/dx, cm, den, 1/den}: interior-class coefficients per material (MEDIUM list)
-__host__ __device__ inline size_t header_bytes(int Z) {
+// + 9 x {kq_a, kq_b, -den_a, -den_b | 1/den_a, 1/den_b, cm_a, cm_b}: the same coefficients for
+//   every ordered PAIR of materials (packed arithmetic of k_resident_step2's MEDIUM vectors)
+// + 16 ints: the plan's list sizes (Params::counts2) and those of the plan of building
+//   b + v2_stride, the one the same persistent CTA of k_resident_step2 loads next
+constexpr int kPairTabBytes = 9 * 32;
+__host__ __device__ inline size_t header_pair_offset(int Z) {
   return sizeof(Combo) * kNumCombos + header_q_slots(Z) * 4 + 32 + 48;
+}
+__host__ __device__ inline size_t header_bytes(int Z) {
+  return header_pair_offset(Z) + kPairTabBytes + 64;
 }
 
 // Shared-memory geometry of k_resident_step, computed once on the host and passed
@@ -262,19 +270,35 @@ __device__ __forceinline__ void build_header(const Params& p, int b, int lane, u
   for (int zi = lane; zi < (int)header_q_slots(Z); zi += G)
     qcv[zi] = zi < Z ? p.qcv[(size_t)b * Z + zi] : 0.f;
   if (lane == 0) {
-    const int n_f = p.n_fast[plan * 4 + 0], n_m = p.n_fast[plan * 4 + 1], n_e = p.n_fast[plan * 4 + 2];
+    // vector-list sizes of k_resident_step (absent on the streaming path and under k_resident_step2)
+    const bool v1 = p.n_fast != nullptr;
+    const int n_f = v1 ? p.n_fast[plan * 4 + 0] : 0, n_m = v1 ? p.n_fast[plan * 4 + 1] : 0,
+              n_e = v1 ? p.n_fast[plan * 4 + 2] : 0;
     scal[0] = t_inf;
     scal[1] = h;
     scal[2] = __int_as_float(n_f);
     scal[3] = __int_as_float(n_f + n_m);
     scal[4] = __int_as_float(n_f + n_m + n_e);
-    scal[5] = __int_as_float(p.rl_chunks[plan]);
+    scal[5] = __int_as_float(v1 ? p.rl_chunks[plan] : 0);
     scal[6] = scal[7] = 0.f;
   }
   __syncwarp(amask);
   if (lane < kNumMaterials) {
     const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + lane];
     reinterpret_cast<float4*>(scal + 8)[lane] = make_float4(c.k1, c.cm, c.den, c.rden);
+  }
+  float4* pair = reinterpret_cast<float4*>(h8 + header_pair_offset(Z));
+  for (int i = lane; i < kNumMaterials * kNumMaterials; i += G) {
+    const Combo& a = tab[SBX_CV_INTERIOR * kNumMaterials + i / kNumMaterials];
+    const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + i % kNumMaterials];
+    pair[2 * i] = make_float4(a.k1, c.k1, -a.den, -c.den);
+    pair[2 * i + 1] = make_float4(a.rden, c.rden, a.cm, c.cm);
+  }
+  if (p.counts2 != nullptr && lane < 4) {
+    const int bn = b + p.v2_stride;
+    const int pl = lane < 2 ? plan : (p.n_plans == 1 ? 0 : (bn < p.B ? bn : plan));
+    reinterpret_cast<int4*>(h8 + header_pair_offset(Z) + kPairTabBytes)[lane] =
+        reinterpret_cast<const int4*>(p.counts2 + (size_t)pl * 8)[lane & 1];
   }
 }
 __global__ void __launch_bounds__(128) k_build_header(const Params p) {
@@ -1113,6 +1137,16 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
     const int above = __syncthreads_or(lmax > p.threshold64);
     md_block = lmax;
     if (!above) break;
+  }
+  // building.apply_convection() (simulator_flexible_floor_plan.py:156; the legacy config runs
+  // Gauss-Seidel WITH StochasticConvectionSimulator, sim_config_legacy.gin:39-41,101): the
+  // host-composed gather map, through the previous-temperature plane that is no longer needed
+  if (p.conv_perm != nullptr && !p.fd_only) {
+    const int32_t* perm = p.conv_perm + (size_t)b * n_cv;
+    for (int i = tid; i < n_cv; i += kGsThreads) Tp[i] = T[perm[i]];
+    __syncthreads();
+    for (int i = tid; i < n_cv; i += kGsThreads) T[i] = Tp[i];
+    __syncthreads();
   }
   // write back (fp64 state + fp32 mirror), zone sums for k_post
   float* g32 = p.tbuf[0] + (size_t)b * n_cv;

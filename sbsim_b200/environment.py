@@ -170,6 +170,7 @@ class Environment:
 
     # ---- action spec (environment.py:591-653) ----
     self._action_names: List[str] = []
+    self._action_fields: List[tuple] = []      # (device, bare setpoint name) per action dimension
     self._action_normalizers = {}
     targets, lo, hi = [], [], []
     for dev, setpoint, target in _ACTION_SETPOINTS:
@@ -178,6 +179,7 @@ class Environment:
         continue
       field_id = f"{dev}_{setpoint}"
       self._action_names.append(field_id)
+      self._action_fields.append((dev, setpoint))
       self._action_normalizers[field_id] = norm
       targets.append(target)
       lo.append(norm.setpoint_min)

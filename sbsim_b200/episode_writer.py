@@ -268,11 +268,13 @@ class EpisodeWriter:
         resp["agent_reward_value"] = reward[b]
       w.write(REWARD_RESPONSE_PREFIX, ts, encode_reward_response(ts, ts + dt, **resp))
       w.write(OBSERVATION_RESPONSE_FILE_PREFIX, ts, encode_observation_response(ts, obs))
+      # ActionResponse (environment.py:834-871): one SingleActionRequest per action field,
+      # device id + BARE setpoint name + native value (kelvin), as the reference logs it
+      native = {"supply_water_setpoint": boiler_sp[b],
+                "supply_air_heating_temperature_setpoint": heat_sp[b],
+                "supply_air_cooling_temperature_setpoint": cool_sp[b]}
       acts = []
-      for i, aname in enumerate(env._action_names):
-        dev = self.boiler_id if "water" in aname else self.air_handler_id
-        native = {"supply_water_setpoint": boiler_sp[b],
-                  "supply_air_heating_temperature_setpoint": heat_sp[b],
-                  "supply_air_cooling_temperature_setpoint": cool_sp[b]}.get(aname, float(action[b, i]))
-        acts.append((dev, aname, native))
+      for device, setpoint in env._action_fields:
+        dev = self.boiler_id if device == "boiler" else self.air_handler_id
+        acts.append((dev, setpoint, float(native[setpoint])))
       w.write(ACTION_RESPONSE_FILE_PREFIX, ts - dt, encode_action_response(ts - dt, acts))

@@ -163,5 +163,20 @@ def test_episode_writer_on_the_cuda_environment(tmp_path):
     zones = [_decode(v) for f, wt, v in _decode(infos[-1]) if f == 5]
     temps = [[x for ff, _, x in _decode(z[1][2]) if ff == 3][0] for z in zones]
     np.testing.assert_array_equal(np.float32(temps), zmeans[-1][:len(temps)])
+    # ActionResponse: bare setpoint names and NATIVE values (kelvin), device order boiler, AHU
+    # (environment.py:834-871); the last action was `a`
+    acts = [r for f in files if f.startswith("action_response") for r in ew.read_shard(os.path.join(d, f))]
+    assert len(acts) == 4
+    singles = [_decode(v) for f, wt, v in _decode(acts[-1]) if f == 3]
+    got_acts = []
+    for sresp in singles:
+      req = _decode([v for f, wt, v in sresp if f == 1][0])
+      got_acts.append(([v for f, _, v in req if f == 1][0].decode(), [v for f, _, v in req if f == 2][0].decode(),
+                       float([v for f, wt, v in req if f == 3 and wt == 5][0])))
+    assert [g[1] for g in got_acts] == ["supply_water_setpoint", "supply_air_heating_temperature_setpoint"]
+    assert got_acts[0][0].startswith("boiler") and got_acts[1][0].startswith("air_handler")
+    want = [np.float32(np.float32((a[2, 0] + 1) / 2) * np.float32(45.0) + np.float32(310.0)),
+            np.float32(np.float32((a[2, 1] + 1) / 2) * np.float32(15.0) + np.float32(285.0))]
+    np.testing.assert_allclose([g[2] for g in got_acts], want, rtol=1e-6)
   finally:
     env.close()

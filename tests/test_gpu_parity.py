@@ -312,6 +312,36 @@ def test_stochastic_convection_replay_matches_oracle(path):
     env.close()
 
 
+def test_gauss_seidel_with_stochastic_convection_matches_oracle():
+  """The legacy config runs the fp64 Gauss-Seidel solver WITH StochasticConvectionSimulator
+  (sim_config_legacy.gin:39-41, 101, 182): the gather map is applied after the solve, before
+  the write-back and the zone sums."""
+  sc = S.Scenario(floor_plan=S.small_plan(), convection=(1.0, 5, 5))
+  cp = sc.compiled()
+  B = 2
+  env = S.make_env(sc, n_envs=B, plans=cp, solver="gauss_seidel")
+  try:
+    oracles = [S.make_oracle(sc, cp, solver="gs") for _ in range(B)]
+    ts = env.reset()
+    for o in oracles:
+      o.reset()
+    rng = np.random.default_rng(4)
+    for step in range(8):
+      a = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+      ts = env.step(a)
+      t64 = env.handle.download("temp64", (B, cp.height, cp.width))
+      for b, o in enumerate(oracles):
+        ots = o.step(a[b])
+        np.testing.assert_allclose(ts.observation[b], ots[3], rtol=RTOL, atol=2e-5)
+        np.testing.assert_allclose(ts.reward[b], ots[1], rtol=RTOL, atol=1e-6)
+        np.testing.assert_allclose(t64[b], o.temp, rtol=1e-9)
+        if step == 0:
+          np.testing.assert_array_equal(t64[b], o.temp)     # permutation included, bit for bit
+    assert np.abs(np.diff(t64[0][5:10, 5:15], axis=1)).max() > 0
+  finally:
+    env.close()
+
+
 @pytest.mark.parametrize("plan_name", ["tf_test_10x9", "small_24x34", "odd_23x31", "rand_64x96"])
 def test_gauss_seidel_fd_step_bit_exact_fp64(plan_name):
   """the legacy fp64 in-place raster Gauss-Seidel sweep

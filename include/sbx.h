@@ -303,7 +303,7 @@ int sbx_host_free(void* p);
 /* Tuning knobs (new, no reference counterpart). */
 #define SBX_OPT_PIPELINE_CHUNKS 1 /* resident Jacobi path: shares of the batch a step is pipelined over (1 = one launch per kernel) */
 #define SBX_OPT_L2_PREFETCH_DISTANCE 2 /* resident Jacobi path: the CTA of building b prefetches building b + value into L2 (0 = off; default = CTAs in flight) */
-#define SBX_OPT_LIST_SWEEP 3 /* streaming path, width % 4 == 0: 1 = list-driven sweep (per-tile FAST / OTHER vector lists), 0 = rolling-window sweep (default: measured faster) */
+#define SBX_OPT_HOST_SHARES 3 /* sbx_step_host, resident path: shares of the batch stepped one after the other so that a share's device->host copy overlaps the next shares' kernels (0 = the library's choice: 4 for >= 2 MB of outputs, else 1) */
 int sbx_set_option(sbx_handle h, int option, int64_t value);
 
 /* In-library timing with CUDA events on the streams the kernels are launched on:

@@ -103,8 +103,6 @@ struct Params {
   const int32_t* obs_zone_order;  // [P,Z]
   uint16_t* desc_packed;     // [P,H,W] combo index | diffuser | zone (k_prepare_plan)
   uint16_t* desc_spk;        // [P,H,W] the same packing at the natural pitch W (streaming path)
-  uint16_t* tlist;           // [P,tiles,1024] per-tile vector lists of k_sweep_list (FAST first)
-  int32_t* tcount;           // [P,tiles,2] {n_fast, n_all}
   uint16_t* qlist;           // [P,H*W/V] fast vectors from the front, slow from the back
   int32_t* n_fast;           // [P,4] sizes of the FAST / MEDIUM / EXT / SLOW vector lists
   uint32_t* rlist;           // [P, rl_cap] zone-sum list (k_prepare_reduce)
@@ -166,6 +164,8 @@ struct Params {
   uint8_t* active;           // [B]
   int32_t* n_active;         // [1]
   unsigned long long* sweeps_total;  // [1]
+  int32_t* sweep_k;          // [1] sweep index of the device-driven streaming loop (1-based)
+  unsigned long long* sweep_launches;  // [1] k_sweep launches made by that loop since create
   unsigned long long* phase_cycles;  // [8] only with -DSBX_PROFILE_PHASES
   const int32_t* conv_perm;  // [B,H*W] or null: convection gather map for this step
   // sbx_fd_step: solve only, ambient / convection given per env

@@ -1220,9 +1220,10 @@ __global__ void k_pack_stream(const Params p) {
 // Every class of CV runs the same instruction stream (cv_update_packed): warps that
 // mix interior / wall / boundary / exterior CVs do not diverge.
 template <int V, int R>
-__global__ void __launch_bounds__(kStreamThreads, SBX_SWEEP_MIN_CTAS) k_sweep(const Params p, const int k) {
+__global__ void __launch_bounds__(kStreamThreads, SBX_SWEEP_MIN_CTAS) k_sweep(const Params p, const int k_arg) {
   __shared__ __align__(16) Combo tab[kNumCombos];
   __shared__ float qcv[kMaxZones + 1];
+  const int k = k_arg > 0 ? k_arg : *p.sweep_k;        // device-driven loop: the sweep index lives on the device
   const StreamTiling tl = stream_tiling(p.H, p.W, V);
   const int b = blockIdx.x / tl.tiles;
   if (!p.active[b]) return;
@@ -1328,211 +1329,6 @@ _Pragma(SBX_STR(unroll SBX_SWEEP_UNROLL))
   if (lane == 0 && lmax > 0.f) atomicMax(&p.max_delta_bits[b], __float_as_uint(lmax));
 }
 
-// ---------------------------------------------------------------------------
-// List-driven streaming sweep (V == 4).  The rolling-window k_sweep above runs every CV
-// through the table-driven generic update (~75 instructions per CV: it is issue-bound at
-// 60 % of the HBM roofline).  Here each CTA owns a tile of 32 rows x 128 columns whose
-// vectors were sorted ONCE per plan into FAST (4 interior air CVs, no diffuser: >90 % of a
-// real floor plan) and OTHER: FAST warps run the packed uniform-coefficient arithmetic of
-// the resident kernel without descriptor or table loads, OTHER warps the generic update.
-// Operands come straight from global memory: a tile's rows are each other's vertical
-// neighbours, so the 3x re-reads hit L1 and DRAM still sees every temperature once.
-// Measured (B200, 4096 x 744x1004): 25 % fewer instructions than k_sweep but 10.1 ms per
-// sweep against 9.3 ms -- the dependent list -> address -> operand loads leave it latency
-// bound (long-scoreboard stalls), so it is opt-in (SBX_OPT_LIST_SWEEP); the next step is
-// staging the tile with TMA instead of gathering it.
-// ---------------------------------------------------------------------------
-constexpr int kTileRows = 32, kTileVecs = 32;           // 32 rows x 32 vectors (128 columns)
-constexpr int kTileEntries = kTileRows * kTileVecs;
-
-struct TileGrid {
-  int tiles_x, tiles_y, tiles;
-};
-__host__ __device__ inline TileGrid tile_grid(int H, int W) {
-  TileGrid t;
-  t.tiles_x = (W / 4 + kTileVecs - 1) / kTileVecs;
-  t.tiles_y = (H + kTileRows - 1) / kTileRows;
-  t.tiles = t.tiles_x * t.tiles_y;
-  return t;
-}
-
-// Once per uploaded plan: per tile, FAST vectors first, then the others, each class in
-// raster order (consecutive entries are mostly consecutive vectors: coalesced).
-// Entry = row in tile (5 bits) << 5 | vector in row (5 bits); tcount = {n_fast, n_all}.
-__global__ void __launch_bounds__(256) k_prepare_tiles(const Params p) {
-  const TileGrid tg = tile_grid(p.H, p.W);
-  const int plan = blockIdx.x / tg.tiles, tile = blockIdx.x - plan * tg.tiles;
-  const int ty = tile / tg.tiles_x, tx = tile - ty * tg.tiles_x;
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  const int wq = p.W / 4;
-  const uint16_t* raw = p.desc + (size_t)plan * p.H * p.W;
-  uint16_t* list = p.tlist + ((size_t)plan * tg.tiles + tile) * kTileEntries;
-  __shared__ int s_fast[8], s_other[8];
-  __shared__ int s_base_other;
-  if (tid == 0) s_base_other = 0;
-  __syncthreads();
-  // two passes of counting + writing per class keep raster order without sorting
-  for (int pass = 0; pass < 2; ++pass) {                // 0: count, 1: write
-    int run_fast = 0, run_other = 0;                    // entries of earlier chunks
-    for (int chunk = 0; chunk < kTileEntries / 256; ++chunk) {
-      const int e = chunk * 256 + tid;                  // raster index inside the tile
-      const int lr = e / kTileVecs, lc = e % kTileVecs;
-      const int r = ty * kTileRows + lr, q = tx * kTileVecs + lc;
-      const bool valid = r < p.H && q < wq;
-      bool fast = valid;
-      if (valid)
-        for (int k = 0; k < 4; ++k) fast = fast && ((raw[(size_t)r * p.W + q * 4 + k] & 0x007Fu) == kFastDesc);
-      const unsigned mf = __ballot_sync(0xffffffffu, fast);
-      const unsigned mo = __ballot_sync(0xffffffffu, valid && !fast);
-      if (lane == 0) { s_fast[warp] = __popc(mf); s_other[warp] = __popc(mo); }
-      __syncthreads();
-      int wf = 0, wo = 0, tf = 0, to = 0;
-      for (int w = 0; w < 8; ++w) {
-        if (w < warp) { wf += s_fast[w]; wo += s_other[w]; }
-        tf += s_fast[w]; to += s_other[w];
-      }
-      if (pass == 1 && valid) {
-        const unsigned below = (1u << lane) - 1u;
-        const int pos = fast ? run_fast + wf + __popc(mf & below)
-                             : s_base_other + run_other + wo + __popc(mo & below);
-        list[pos] = (uint16_t)((lr << 5) | lc);
-      }
-      run_fast += tf;
-      run_other += to;
-      __syncthreads();
-    }
-    if (pass == 0) {
-      if (tid == 0) {
-        s_base_other = run_fast;                        // OTHER entries start after all FAST ones
-        p.tcount[((size_t)plan * tg.tiles + tile) * 2 + 0] = run_fast;
-        p.tcount[((size_t)plan * tg.tiles + tile) * 2 + 1] = run_fast + run_other;
-      }
-      __syncthreads();
-    }
-  }
-}
-
-__global__ void __launch_bounds__(256, 4) k_sweep_list(const Params p, const int k) {
-  __shared__ __align__(16) Combo tab[kNumCombos];
-  __shared__ float qcv[kMaxZones + 1];
-  const TileGrid tg = tile_grid(p.H, p.W);
-  const int b = blockIdx.x / tg.tiles;
-  if (!p.active[b]) return;
-  const int tile = blockIdx.x - b * tg.tiles;
-  const int ty = tile / tg.tiles_x, tx = tile - ty * tg.tiles_x;
-  const int tid = threadIdx.x, lane = tid & 31;
-  const int H = p.H, W = p.W, Z = p.Z;
-  const size_t n_cv = (size_t)H * W;
-  const int plan = p.n_plans == 1 ? 0 : b;
-  // coefficient table, heat inputs and T_inf of this building: built once per step by
-  // k_pre / k_build_header (the solve header of the resident kernel), not once per CTA
-  const unsigned char* gH = p.hdr + (size_t)b * header_bytes(Z);
-  for (int i = tid; i < (int)(sizeof(Combo) * kNumCombos / 16); i += 256)
-    reinterpret_cast<float4*>(tab)[i] = reinterpret_cast<const float4*>(gH)[i];
-  const float* hq = reinterpret_cast<const float*>(gH + sizeof(Combo) * kNumCombos);
-  for (int i = tid; i < Z; i += 256) qcv[i] = hq[i];
-  const float t_inf = hq[header_q_slots(Z)];
-  __syncthreads();
-  AreaCoef az;
-  az.full = tab[SBX_CV_INTERIOR * kNumMaterials].vz;
-  az.half = tab[SBX_CV_CORNER_TL * kNumMaterials].vz;
-  const float dt = p.dt, rdt = __frcp_rn(p.dt);
-  FastCoef2 fc2;
-  float kq1;
-  {
-    const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + 0];      // interior, air
-    kq1 = c.k1;
-    fc2.kq = pack2(c.k1, c.k1); fc2.vz = pack2(c.vz, c.vz);
-    fc2.nden = pack2(-c.den, -c.den); fc2.rden = pack2(c.rden, c.rden);
-    fc2.cm = pack2(c.cm, c.cm); fc2.ndt = pack2(-dt, -dt); fc2.rdt = pack2(rdt, rdt);
-  }
-  const int cur = p.cur[b];
-  int bi, bo;
-  sweep_buffers(cur, k, bi, bo);
-  const bool first = k == 1;            // T_est is T_prev itself
-  const float* __restrict__ tin = p.tbuf[bi] + (size_t)b * n_cv;
-  const float* __restrict__ tprev = p.tbuf[cur] + (size_t)b * n_cv;
-  float* __restrict__ tout = p.tbuf[bo] + (size_t)b * n_cv;
-  const uint16_t* __restrict__ dsc = p.desc_spk + (size_t)plan * n_cv;
-  const uint16_t* __restrict__ list = p.tlist + ((size_t)plan * tg.tiles + tile) * kTileEntries;
-  const int n_fast = p.tcount[((size_t)plan * tg.tiles + tile) * 2 + 0];
-  const int n_all = p.tcount[((size_t)plan * tg.tiles + tile) * 2 + 1];
-  const int r_base = ty * kTileRows, c_base = tx * kTileVecs * 4;
-  float lmax = 0.f;
-
-  auto offset_of = [&](int i, int& r, int& c0) {
-    const int e = (int)list[i];
-    r = r_base + (e >> 5);
-    c0 = c_base + (e & 31) * 4;
-    return r * W + c0;
-  };
-  // FAST vector: interior class, all four neighbours exist
-  auto fast_one = [&](int off, float4& o4) {
-    const float4 c4 = *reinterpret_cast<const float4*>(tin + off);
-    const float4 up4 = *reinterpret_cast<const float4*>(tin + off - W);
-    const float4 dn4 = *reinterpret_cast<const float4*>(tin + off + W);
-    const float left = tin[off - 1], right = tin[off + 4];
-    float4 tp4 = c4;
-    if (!first) tp4 = *reinterpret_cast<const float4*>(tprev + off);
-    const f32x2 n3a = div_rn2(mul2(fc2.cm, pack2(tp4.x, tp4.y)), fc2.ndt, fc2.rdt);   // :743-749
-    const f32x2 n3b = div_rn2(mul2(fc2.cm, pack2(tp4.z, tp4.w)), fc2.ndt, fc2.rdt);
-    lmax = fast_core4(c4, up4, dn4, left, right, n3a, n3b, fc2, kq1, lmax, o4);
-  };
-  auto other_one = [&](int off, int r, int c0, float4& o4) {
-    const float4 c4 = *reinterpret_cast<const float4*>(tin + off);
-    float c[4] = {c4.x, c4.y, c4.z, c4.w}, up[4], dn[4], tp[4], o[4];
-    uint32_t d[4];
-    fill<4>(up, t_inf);
-    fill<4>(dn, t_inf);
-    if (r > 0) load_f<4>(tin + off - W, up);                                    // :642-644
-    if (r + 1 < H) load_f<4>(tin + off + W, dn);                                // :646
-    const float left = c0 > 0 ? tin[off - 1] : t_inf;                           // :638-640
-    const float right = c0 + 4 < W ? tin[off + 4] : t_inf;                      // :636
-    load_d<4>(dsc + off, d);
-    if (first) {
-#pragma unroll
-      for (int q = 0; q < 4; ++q) tp[q] = c[q];
-    } else {
-      load_f<4>(tprev + off, tp);
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const float t_jm = q == 0 ? left : c[q - 1];
-      const float t_jp = q == 3 ? right : c[q + 1];
-      const float n3 = div_rn(mul(tab[d[q] & kPackIdxMask].cm, tp[q]), dt, rdt);
-      float num = cv_numerator_packed(d[q], t_jp, t_jm, up[q], dn[q], n3, az, tab);
-      if (d[q] & SBX_DESC_DIFFUSER) num = add(num, qcv[d[q] >> SBX_DESC_ZONE_SHIFT]);   // :754
-      o[q] = cv_divide_packed(d[q], num, t_inf, tab);
-      lmax = fmaxf(lmax, fabsf(__fsub_rn(o[q], c[q])));
-    }
-    o4 = make_float4(o[0], o[1], o[2], o[3]);
-  };
-
-  for (int i0 = tid; i0 < n_all; i0 += 512) {
-    const int i1 = i0 + 256;
-    int r0, c00, r1 = 0, c01 = 0;
-    const int off0 = offset_of(i0, r0, c00);
-    const int off1 = i1 < n_all ? offset_of(i1, r1, c01) : off0;
-    float4 oa, ob;
-    if (i1 < n_fast) {
-      // two FAST vectors as one instruction stream: twice the loads in flight
-      fast_one(off0, oa);
-      fast_one(off1, ob);
-      *reinterpret_cast<float4*>(tout + off0) = oa;
-      *reinterpret_cast<float4*>(tout + off1) = ob;
-    } else {
-      if (i0 < n_fast) fast_one(off0, oa); else other_one(off0, r0, c00, oa);
-      *reinterpret_cast<float4*>(tout + off0) = oa;
-      if (i1 < n_all) {
-        other_one(off1, r1, c01, ob);          // i1 >= n_fast here
-        *reinterpret_cast<float4*>(tout + off1) = ob;
-      }
-    }
-  }
-  lmax = warp_max(lmax);
-  if (lane == 0 && lmax > 0.f) atomicMax(&p.max_delta_bits[b], __float_as_uint(lmax));
-}
-
 // Convergence bookkeeping after sweep k (simulator.py:348-369).
 __global__ void k_check(const Params p, const int k) {
   const int b = blockIdx.x * blockDim.x + threadIdx.x;
@@ -1554,6 +1350,46 @@ __global__ void k_check(const Params p, const int k) {
   }
   const unsigned m = __ballot_sync(0xffffffffu, still);
   if ((threadIdx.x & 31) == 0 && m) atomicAdd(p.n_active, __popc(m));
+}
+
+// Device-driven sweep loop (CUDA graph WHILE node, see build_sweep_graph in sbx_api.cu): ONE
+// block walks every building after a sweep, does the bookkeeping of k_check and tells the
+// graph whether another sweep is needed.  No host round trip between sweeps.
+__global__ void __launch_bounds__(1024) k_check_loop(const Params p, const cudaGraphConditionalHandle handle) {
+  const int k = *p.sweep_k;
+  int still = 0;
+  for (int b = threadIdx.x; b < p.B; b += blockDim.x) {
+    if (!p.active[b]) continue;
+    const float md = __uint_as_float(p.max_delta_bits[b]);
+    p.max_delta_bits[b] = 0u;
+    p.max_delta[b] = md;
+    p.n_sweeps[b] = k;
+    if (md <= p.threshold || k >= p.iteration_limit) {
+      int bi, bo;
+      sweep_buffers(p.cur[b], k, bi, bo);
+      p.cur[b] = (uint8_t)bo;
+      p.active[b] = 0;
+      if (!p.fd_only) atomicAdd(p.sweeps_total, (unsigned long long)k);
+    } else {
+      still = 1;
+    }
+  }
+  const int n_still = __syncthreads_count(still);
+  if (threadIdx.x == 0) {
+    *p.sweep_k = k + 1;
+    atomicAdd(p.sweep_launches, 1ull);
+    cudaGraphSetConditional(handle, n_still > 0 ? 1u : 0u);
+  }
+}
+
+__global__ void k_loop_begin(const Params p) {
+  const int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b == 0) *p.sweep_k = 1;
+  if (b < p.B) {
+    p.active[b] = 1;
+    p.max_delta_bits[b] = 0u;
+    p.n_sweeps[b] = 0;
+  }
 }
 
 __global__ void k_activate(const Params p) {

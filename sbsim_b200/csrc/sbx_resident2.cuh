@@ -814,7 +814,6 @@ k_resident_step2(const Params p, const __grid_constant__ CUtensorMap tmap_t) {
   }
 
   // =========================== compute warps ===========================
-  const f32x2 scale2 = pack2(kFixScaleF, kFixScaleF);
   const int limit = p.iteration_limit;
   const float thr = p.threshold;
   int i_in = 0, i_out = 1, i_n3 = 2;
@@ -905,8 +904,9 @@ k_resident_step2(const Params p, const __grid_constant__ CUtensorMap tmap_t) {
       const uint16_t* zfull = reinterpret_cast<const uint16_t*>(smem + G.off_zfull);
       const uint32_t* zpart = reinterpret_cast<const uint32_t*>(smem + G.off_zpart);
       const uint8_t* zchunk = reinterpret_cast<const uint8_t*>(smem + G.off_zchunk);
-      const float nref = -__fmul_rn(t_inf, kFixScaleF);
-      const f32x2 nref2 = pack2(nref, nref);
+      const f32x2 scale2 = pack2(kFixScaleF, kFixScaleF);
+    const float nref = -__fmul_rn(t_inf, kFixScaleF);
+    const f32x2 nref2 = pack2(nref, nref);
       const int per = (n_chunks + NW - 1) / NW;
       const int c_lo = min(n_chunks, warp * per), c_hi = min(n_chunks, c_lo + per);
       long long* wbins = bins + warp * (Z + 1);            // this warp's private row
@@ -1110,11 +1110,11 @@ k_resident_step2(const Params p, const __grid_constant__ CUtensorMap tmap_t) {
   }
   // ---- zone / grid sums of the final field ----
   if (sums) {
-    const f32x2 scale2 = pack2(kFixScaleF, kFixScaleF);
     // (the zone-sum list came with the second TMA batch, which sweep 1 waited for)
     const uint16_t* zfull = reinterpret_cast<const uint16_t*>(smem + G.off_zfull);
     const uint32_t* zpart = reinterpret_cast<const uint32_t*>(smem + G.off_zpart);
     const uint8_t* zchunk = reinterpret_cast<const uint8_t*>(smem + G.off_zchunk);
+    const f32x2 scale2 = pack2(kFixScaleF, kFixScaleF);
     const float nref = -__fmul_rn(t_inf, kFixScaleF);
     const f32x2 nref2 = pack2(nref, nref);
     const int per = (n_chunks + NW - 1) / NW;

@@ -493,7 +493,8 @@ class Environment:
     if a.shape != want:
       raise ValueError(f"action shape {a.shape} != {want}")
     tol = config_lib.ACTION_TOLERANCE
-    if a.size and (np.any(a < -1.0 - tol) or np.any(a > 1.0 + tol) or np.any(np.isnan(a))):
+    # one pass over the batch on the fast path (NaN fails the comparison too)
+    if a.size and not (np.abs(a).max() <= 1.0 + tol):
       bad = a[(a < -1.0 - tol) | (a > 1.0 + tol) | np.isnan(a)][0]
       raise ValueError(f"agent_action: {bad} not within bounds [-1.0, 1.0]")  # bounded_action_normalizer.py:84-90
     return a

@@ -462,37 +462,6 @@ def test_energy_carbon_reward_function_matches_oracle():
     env.close()
 
 
-def test_list_sweep_equals_rolling_window_sweep():
-  """Streaming path: the list-driven sweep (SBX_OPT_LIST_SWEEP, opt-in for widths that are
-  a multiple of 4) and the rolling-window sweep give the same bits, fields and sweep counts,
-  on a grid with partial tiles in both directions (70 x 132)."""
-  rng = np.random.default_rng(11)
-  spec = floorplan.RandomPlanSpec(height=70, width=132, rooms_y=(2,), rooms_x=(3,), min_room=8)
-  plan = floorplan.random_floor_plan(rng, spec).astype(np.int64)
-  sc = S.Scenario(floor_plan=plan, cv_size_cm=10.0, buffer_from_walls=3)
-  cp = sc.compiled()
-  B = 3
-  envs = []
-  try:
-    for flag in (1, 0):
-      env = S.make_env(sc, n_envs=B, plans=cp, kernel_path=sbx.PATH_STREAMING)
-      env.handle.set_option(_lib.OPT_LIST_SWEEP, flag)
-      envs.append(env)
-    ts = [e.reset() for e in envs]
-    for step in range(12):
-      a = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
-      ts = [e.step(a) for e in envs]
-      np.testing.assert_array_equal(ts[0].observation, ts[1].observation)
-      np.testing.assert_array_equal(ts[0].reward, ts[1].reward)
-      np.testing.assert_array_equal(envs[0].handle.download("n_sweeps", (B,)),
-                                    envs[1].handle.download("n_sweeps", (B,)))
-    np.testing.assert_array_equal(envs[0].handle.download("temp", (B, 70, 132)),
-                                  envs[1].handle.download("temp", (B, 70, 132)))
-  finally:
-    for e in envs:
-      e.close()
-
-
 def test_gauss_seidel_on_the_legacy_rectangular_building():
   """The deprecated rectangular `Building` (3 x 3 rooms of 20 x 30 CVs)
   through legacy_building(): fp64 Gauss-Seidel solve bit-identical to the oracle."""

@@ -66,6 +66,12 @@ def parse_args():
   ap.add_argument("--iteration-limit", type=int, default=100)
   ap.add_argument("--prefetch", type=int, default=-1,
                   help="SBX_OPT_L2_PREFETCH_DISTANCE override (-1 = the library's choice)")
+  ap.add_argument("--convection", choices=["default", "off", "device"], default="default",
+                  help="stochastic convection: the office workload runs the shipped model "
+                       "(p=1, distance=5, seed=5; sim_config.gin:37-39) in device-RNG mode by "
+                       "default, the randomized workload has it off (SURVEY 8d config 3)")
+  ap.add_argument("--host-shares", type=int, default=0,
+                  help="SBX_OPT_HOST_SHARES override (0 = the library's choice)")
   ap.add_argument("--chunks", type=int, default=0,
                   help="SBX_OPT_PIPELINE_CHUNKS override (0 = the library's choice)")
   return ap.parse_args()
@@ -177,21 +183,29 @@ def build_env(args, rank, local_rank):
         n, seed=2024 + rank, episode_steps=episode, n_layouts=args.layouts,
         histogram=bool(args.histogram), device=local_rank, kernel_path=path,
         convergence_threshold=args.convergence_threshold, iteration_limit=args.iteration_limit)
+    if args.convection == "device":
+      env.handle.set_device_convection(*workloads.CALIBRATED_CONVECTION)
     desc = {"workload": "randomized-64x96 (BASELINE.json configs[3] per-GPU shard)",
             "envs_per_gpu": n, "grid": [64, 96], "layouts": wl.n_layouts,
-            "plans": "per-env descriptor, materials, weather, T0, actions"}
+            "plans": "per-env descriptor, materials, weather, T0, actions",
+            "stochastic_convection": "device-rng mode" if args.convection == "device" else "off"}
     return env, wl, desc
   n = args.envs_per_gpu or 4096
   cal = workloads.load_calibrated(CALIBRATED_FIXTURE)
   cp = cal.plan
+  conv_on = args.convection in ("default", "device")
+  conv = (sbx.StochasticConvectionSimulator(*workloads.CALIBRATED_CONVECTION, mode="device")
+          if conv_on else None)
   env = workloads.make_calibrated_env(cal, n, episode_steps=episode,
                                       histogram=bool(args.histogram), device=local_rank,
-                                      kernel_path=path)
+                                      kernel_path=path, convection=conv)
   desc = {"workload": "calibrated sb1 building 744x1004 x copies (BASELINE.json configs[1]; "
                       "sim_config.gin:160-196: TF-Jacobi, reset_temps.npy, Moffett replay weather, "
                       "US/Pacific schedule, RandomizedArrivalDepartureOccupancy seed 17321)",
           "envs_per_gpu": n, "grid": [cp.height, cp.width], "zones": cp.n_zones,
-          "plans": "one shared descriptor", "stochastic_convection": "off"}
+          "plans": "one shared descriptor",
+          "stochastic_convection": ("device-rng mode, p=1 distance=5 seed=5 (sim_config.gin:37-39): "
+                                    "k_convect_reduce fuses it with the zone reduction") if conv_on else "off"}
   return env, None, desc
 
 
@@ -241,6 +255,8 @@ def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
     env.handle.set_option(_lib.OPT_PIPELINE_CHUNKS, args.chunks)
   if args.prefetch >= 0:
     env.handle.set_option(_lib.OPT_L2_PREFETCH_DISTANCE, args.prefetch)
+  if args.host_shares > 0:
+    env.handle.set_option(_lib.OPT_HOST_SHARES, args.host_shares)
   B = env.batch_size
   D = env.observation_spec().shape[0]
   A = env.action_spec().shape[0]
@@ -386,7 +402,7 @@ def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
     if args.workload == "randomized":
       cpu = cpu_baseline(args, wl, K=args.cpu_sample_steps)
     else:
-      cpu = cpu_baseline_calibrated(min(args.cpu_sample_steps, 12))
+      cpu = cpu_baseline_calibrated(min(args.cpu_sample_steps, 8), convection=args.convection != "off")
 
   line = {
       "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K,
@@ -436,20 +452,24 @@ def cpu_baseline(args, wl, K):
                     "oracle/ NumPy-fp32 restatement, one process per core"}
 
 
-def cpu_baseline_calibrated(K, warmup=2):
+def cpu_baseline_calibrated(K, warmup=2, convection=True):
   """The oracle on the calibrated building (BASELINE.json configs[0]): one building per
   host core, K timed steps each after `warmup` untimed ones (the first step after
   reset_temps.npy takes 7 sweeps, the steady state about 2)."""
   from oracle import bench_support
   from sbsim_b200 import workloads
   cores = bench_support.host_cores()
+  warmup = max(warmup, 1)       # the first convection call builds the reference's candidate cache (~25 s)
   rate, total, wall, sweeps = bench_support.time_calibrated_oracle(
-      CALIBRATED_FIXTURE, workloads.NORMALIZATION, workloads.HISTOGRAM, K, warmup, cores)
+      CALIBRATED_FIXTURE, workloads.NORMALIZATION, workloads.HISTOGRAM, K, warmup, cores,
+      convection=workloads.CALIBRATED_CONVECTION if convection else None)
   return {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
           "sample": f"{cores} copies of the calibrated sb1 building (one per core) x {K} steps "
                     f"after {warmup} warm-up steps ({total} env-steps, {wall:.1f} s wall, "
                     f"{sweeps:.2f} sweeps/step), oracle/ NumPy-fp32 restatement of "
-                    "TFSimulator + Environment"}
+                    "TFSimulator + Environment, stochastic convection "
+                    + ("as shipped (p=1, distance=5: the reference's per-CV Python loop)"
+                       if convection else "off")}
 
 
 def run_reference(args):
@@ -463,8 +483,8 @@ def run_reference(args):
   from sbsim_b200 import workloads
   if args.workload != "randomized":
     # calibrated building: ~7 env-steps/s/core -> bound the run to ~12 timed steps
-    K_eff = max(1, min(args.steps, 12))
-    cpu = cpu_baseline_calibrated(K_eff, warmup=min(max(args.warmup, 0), 3))
+    K_eff = max(1, min(args.steps, 8))
+    cpu = cpu_baseline_calibrated(K_eff, warmup=min(max(args.warmup, 1), 2), convection=args.convection != "off")
     n = cpu["cores"]
     emit({
         "impl": "reference", "metric": METRIC, "value": cpu["value"], "unit": UNIT,

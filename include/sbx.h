@@ -37,7 +37,7 @@
 extern "C" {
 #endif
 
-#define SBX_ABI_VERSION 4
+#define SBX_ABI_VERSION 5
 
 #define SBX_OK 0
 #define SBX_E_INVALID (-1)   /* bad argument / config                      */
@@ -303,8 +303,17 @@ int sbx_host_free(void* p);
 /* Tuning knobs (new, no reference counterpart). */
 #define SBX_OPT_PIPELINE_CHUNKS 1 /* resident Jacobi path: shares of the batch a step is pipelined over (1 = one launch per kernel) */
 #define SBX_OPT_L2_PREFETCH_DISTANCE 2 /* resident Jacobi path: the CTA of building b prefetches building b + value into L2 (0 = off; default = CTAs in flight) */
-#define SBX_OPT_HOST_SHARES 3 /* sbx_step_host, resident path: shares of the batch stepped one after the other so that a share's device->host copy overlaps the next shares' kernels (0 = the library's choice: 4 for >= 2 MB of outputs, else 1) */
+#define SBX_OPT_HOST_SHARES 3 /* sbx_step_host, resident path: shares of the batch stepped one after the other so that a share's device->host copy overlaps the next shares' kernels (0 = the library's choice: 2 for >= 2 MB of outputs, else 1) */
 int sbx_set_option(sbx_handle h, int option, int64_t value);
+
+/* Stochastic convection (stochastic_convection_simulator.py:62-145), device-RNG mode: applied
+ * by every following sbx_step after the diffusion solve, from a counter-based generator keyed
+ * by (seed, building, step); p = 0 turns it off.  It keeps the reference model's invariants
+ * (in-room moves of squared length <= distance, participation probability p, zone and grid
+ * sums unchanged) but is NOT the reference's Mersenne-Twister swap sequence: parity runs use
+ * the exact replay through SBX_F_CONVECTION_PERM instead, which takes precedence for the step
+ * it is uploaded for. */
+int sbx_set_device_convection(sbx_handle h, double p, int32_t distance, uint64_t seed);
 
 /* In-library timing with CUDA events on the streams the kernels are launched on:
  * between sbx_timing_begin and sbx_timing_end every sbx_step records an event pair

@@ -15,6 +15,9 @@ from typing import List, Tuple
 import numpy as np
 import pandas as pd
 
+import random
+
+from oracle import convection as oconv
 from oracle import env as oenv
 from oracle import exogenous as oex
 from oracle import hvac as ohvac
@@ -59,7 +62,8 @@ def make_oracle_env(cp, low: float, high: float, convection: float, initial_temp
 
 
 def make_calibrated_oracle_env(fixture_path: str, normalization, histogram, episode_steps: int,
-                               occupancy: str = "randomized") -> oenv.OracleEnvironment:
+                               occupancy: str = "randomized", convection=None
+                               ) -> oenv.OracleEnvironment:
   """BASELINE.json configs[0]: the calibrated sb1 building (sim_config.gin:160-196) --
   TF-Jacobi solver, reset_temps.npy, Moffett replay weather, US/Pacific schedule, the
   shipped randomized occupancy -- from the committed fixture of its resource files."""
@@ -78,6 +82,9 @@ def make_calibrated_oracle_env(fixture_path: str, normalization, histogram, epis
           300.0, 100.0, 160000, 400000, 0.5, 4.3, oex.ElectricityEnergyCost(),
           oex.NaturalGasEnergyCost(), 0.2, 0.4, 0.4),
       solver="tf", initial_temp=294.0, reset_temp_values=cal.reset_temps,
+      convection=(oconv.StochasticConvectionSimulator(convection[0], convection[1], convection[2],
+                                                      rng=random.Random(convection[2]))
+                  if convection else None),
       normalization={k: (f32(m), f32(v)) for k, (m, v) in normalization.items()},
       histogram=histogram, discount_factor=0.9, num_timesteps_in_episode=episode_steps,
       occupancy_normalization_constant=125.0)
@@ -85,8 +92,9 @@ def make_calibrated_oracle_env(fixture_path: str, normalization, histogram, epis
 
 
 def _calibrated_worker(args) -> Tuple[int, float, int]:
-  fixture, normalization, histogram, steps, warmup, seed = args
-  env = make_calibrated_oracle_env(fixture, normalization, histogram, steps + warmup + 8)
+  fixture, normalization, histogram, steps, warmup, seed, convection = args
+  env = make_calibrated_oracle_env(fixture, normalization, histogram, steps + warmup + 8,
+                                   convection=convection)
   rng = np.random.default_rng(seed)
   env.reset()
   for _ in range(warmup):
@@ -100,10 +108,10 @@ def _calibrated_worker(args) -> Tuple[int, float, int]:
 
 
 def time_calibrated_oracle(fixture: str, normalization, histogram, steps: int, warmup: int,
-                           n_procs: int):
+                           n_procs: int, convection=None):
   """One calibrated building per host core, env b driven by default_rng(1000 + b)
   (SURVEY 8d config 2's action streams).  Returns like time_oracle."""
-  jobs = [(fixture, normalization, histogram, steps, warmup, 1000 + i) for i in range(n_procs)]
+  jobs = [(fixture, normalization, histogram, steps, warmup, 1000 + i, convection) for i in range(n_procs)]
   t0 = time.perf_counter()
   if n_procs == 1:
     res = [_calibrated_worker(jobs[0])]

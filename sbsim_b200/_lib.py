@@ -16,7 +16,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 # SBX_LIB: developer override used to A/B kernel variants (profiles/); same ABI, same checks
 LIB_PATH = os.environ.get("SBX_LIB") or os.path.join(_HERE, "lib", "libsbx.so")
 
-ABI_VERSION = 4
+ABI_VERSION = 5
 REWARD_REGRET, REWARD_ENERGY_CARBON = 0, 1
 OPT_PIPELINE_CHUNKS = 1
 OPT_L2_PREFETCH_DISTANCE = 2
@@ -149,7 +149,7 @@ EXPORTS = (
     "sbx_create", "sbx_destroy", "sbx_last_error", "sbx_get_info", "sbx_upload",
     "sbx_download", "sbx_reset", "sbx_step", "sbx_reset_host", "sbx_step_host",
     "sbx_fd_step", "sbx_sync", "sbx_abi_info", "sbx_host_alloc", "sbx_host_free",
-    "sbx_set_option", "sbx_timing_begin", "sbx_timing_end",
+    "sbx_set_option", "sbx_timing_begin", "sbx_timing_end", "sbx_set_device_convection",
 )
 
 _lib: Optional[C.CDLL] = None
@@ -186,6 +186,7 @@ def load() -> C.CDLL:
   lib.sbx_host_alloc.argtypes = [sz, C.POINTER(vp)]
   lib.sbx_host_free.argtypes = [vp]
   lib.sbx_set_option.argtypes = [vp, C.c_int, C.c_int64]
+  lib.sbx_set_device_convection.argtypes = [vp, C.c_double, C.c_int32, C.c_uint64]
   lib.sbx_timing_begin.argtypes = [vp]
   lib.sbx_timing_end.argtypes = [vp, C.POINTER(SbxTiming)]
   for name in EXPORTS:
@@ -315,6 +316,11 @@ class Handle:
   def set_option(self, option: int, value: int):
     self._check(self._lib.sbx_set_option(self._h, int(option), C.c_int64(int(value))),
                 "sbx_set_option")
+
+  def set_device_convection(self, p: float, distance: int, seed: int):
+    self._check(self._lib.sbx_set_device_convection(
+        self._h, C.c_double(float(p)), C.c_int32(int(distance)), C.c_uint64(int(seed) & (2**64 - 1))),
+        "sbx_set_device_convection")
 
   def timing_begin(self):
     self._check(self._lib.sbx_timing_begin(self._h), "sbx_timing_begin")

@@ -10,8 +10,11 @@ diffusion solve and the zone reductions (libsbx field SBX_F_CONVECTION_PERM).
 
 This is the exact-replay mode.  It costs a Python loop
 over every room CV per building per step, so it is meant for parity and small
-batches; large throughput batches run with convection_simulator=None (allowed by
-building.py:647-649).
+batches.  Large throughput batches use `mode="device"`: the same (p, distance, seed)
+drive a counter-based generator on the GPU and a swap pattern that needs no
+sequential pass (libsbx `sbx_set_device_convection`, kernel k_convect_reduce): in-room
+moves of squared length <= distance, participation probability p, zone and grid sums
+unchanged -- the reference model's invariants, not its Mersenne-Twister sequence.
 """
 
 from __future__ import annotations
@@ -28,10 +31,13 @@ class StochasticConvectionSimulator:
   Every environment of a batch gets its own `random.Random(seed)` stream -- what
   B separate reference processes built from the same config would have."""
 
-  def __init__(self, p: float, distance: int, seed: Optional[int]):
+  def __init__(self, p: float, distance: int, seed: Optional[int], mode: str = "replay"):
+    if mode not in ("replay", "device"):
+      raise ValueError("mode must be 'replay' (exact host replay) or 'device' (device RNG)")
     self._p = p
     self._distance = distance
     self._seed = seed
+    self.mode = mode
     # swap candidates per (room list, max distance, CV).  The reference keeps one simulator
     # -- and so one cache -- per building (stochastic_convection_simulator.py:120-134); a
     # batch with one plan per env must not reuse env 0's candidates for another plan's room

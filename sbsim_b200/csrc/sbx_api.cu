@@ -671,7 +671,20 @@ int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_
         k_rotate_cur<<<(unsigned)((p.B + 255) / 256), 256, 0, st>>>(p);
         if (int rc = launch_check(h, "k_rotate_cur")) return rc;
       }
-      if (int rc = launch_zone_reduce(h, st)) return rc;
+      if (p.conv_p > 0.0 && !p.conv_perm) {
+        // device-RNG convection fused with the zone reduction: one read of the field, the
+        // sums, and the permuted field into the next buffer of the rotation
+        CUDA_TRY(h, cudaMemsetAsync(p.zone_sum, 0, sizeof(long long) * (size_t)p.B * (p.Z + 1), st));
+        const StreamTiling tl = stream_tiling(p.H, p.W, h->V);
+        const unsigned grid = (unsigned)((size_t)tl.tiles * p.B);
+        if (h->V == 4) k_convect_reduce<4><<<grid, kStreamThreads, 0, st>>>(p);
+        else k_convect_reduce<1><<<grid, kStreamThreads, 0, st>>>(p);
+        if (int rc = launch_check(h, "k_convect_reduce")) return rc;
+        k_rotate_cur<<<(unsigned)((p.B + 255) / 256), 256, 0, st>>>(p);
+        if (int rc = launch_check(h, "k_rotate_cur")) return rc;
+      } else {
+        if (int rc = launch_zone_reduce(h, st)) return rc;
+      }
     }
     if (int rc = launch_post(h, st, 0)) return rc;
     if (after_share) if (int rc = after_share(0, p.B)) return rc;
@@ -1199,13 +1212,16 @@ int sbx_step_host(sbx_handle h, const float* action, float* obs, float* reward, 
     }
     CUDA_TRY(h, cudaMemcpyAsync(h->d_action, src, sizeof(float) * B * A, cudaMemcpyHostToDevice, h->stream));
   }
-  // Large resident batches are stepped in shares so that the device->host copy of a share
-  // overlaps the kernels of the next ones (the copy of 32768 x 56 floats is 0.15 ms of a
-  // 1.07 ms step when it runs after the last kernel).
+  // Large resident batches are stepped in two shares so that the device->host copy of the
+  // first overlaps the kernels of the second (the copy of 32768 x 56 floats is 0.15 ms of a
+  // 1.06 ms step when it runs after the last kernel).  Measured on B200, 32768 x 64x96,
+  // end-to-end ms per step with 1 / 2 / 4 / 8 shares: 1.277 / 1.244 / 1.352 / 1.579 -- every
+  // further share costs ~75 us (three more launches, their ramp and tail, cold L2 at the
+  // share boundary) and hides less than that.
   const bool pinned[4] = {obs && is_pinned(obs), reward && is_pinned(reward),
                           step_type && is_pinned(step_type), discount && is_pinned(discount)};
   int shares = h->host_shares;
-  if (shares <= 0) shares = (h->path == SBX_PATH_RESIDENT && B * (size_t)(h->D + 3) * 4 >= ((size_t)2 << 20)) ? 4 : 1;
+  if (shares <= 0) shares = (h->path == SBX_PATH_RESIDENT && B * (size_t)(h->D + 3) * 4 >= ((size_t)2 << 20)) ? 2 : 1;
   auto after_share = [&](int b0, int b1) -> int {
     cudaEvent_t ev = h->ev_share[h->share_seq++ % SBX_MAX_CHUNKS];
     CUDA_TRY(h, cudaEventRecord(ev, h->stream));
@@ -1262,6 +1278,16 @@ int sbx_host_alloc(size_t bytes, void** out) {
 
 int sbx_host_free(void* p) {
   if (p) cudaFreeHost(p);
+  return SBX_OK;
+}
+
+int sbx_set_device_convection(sbx_handle h, double p, int32_t distance, uint64_t seed) {
+  if (!h) return fail(h, SBX_E_INVALID, "null handle");
+  if (!(p >= 0.0) || p > 1.0) return fail(h, SBX_E_INVALID, "convection probability must be in [0, 1]");
+  if (p > 0.0 && distance < 1) return fail(h, SBX_E_INVALID, "device-RNG convection needs distance >= 1 (the unbounded shuffle, distance = -1, is replay-only)");
+  h->P.conv_p = distance == 0 ? 0.0 : p;       // p == 0 or distance == 0: no convection (stochastic_convection_simulator.py:70-72)
+  h->P.conv_distance = distance;
+  h->P.conv_seed = seed;
   return SBX_OK;
 }
 

@@ -168,6 +168,10 @@ struct Params {
   unsigned long long* sweep_launches;  // [1] k_sweep launches made by that loop since create
   unsigned long long* phase_cycles;  // [8] only with -DSBX_PROFILE_PHASES
   const int32_t* conv_perm;  // [B,H*W] or null: convection gather map for this step
+  // device-RNG convection (sbx_set_device_convection): p == 0 -> off
+  double conv_p;
+  int conv_distance;
+  unsigned long long conv_seed;
   // sbx_fd_step: solve only, ambient / convection given per env
   int fd_only;
   const double* fd_ambient;     // [B]

@@ -176,6 +176,59 @@ __device__ __forceinline__ void tma_store_wait() {
 }
 
 // ---------------------------------------------------------------------------
+// device-RNG stochastic convection: pattern of one (building, step); see k_convect_reduce
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ uint2 philox2x32_10(uint2 ctr, uint32_t key) {
+#pragma unroll
+  for (int i = 0; i < 10; ++i) {
+    const uint32_t hi = __umulhi(0xD256D193u, ctr.x), lo = 0xD256D193u * ctr.x;
+    ctr = make_uint2(hi ^ key ^ ctr.y, lo);
+    key += 0x9E3779B9u;
+  }
+  return ctr;
+}
+__device__ __forceinline__ uint32_t mix32(uint32_t x) {     // per-pair draw: 2 multiply-xorshift rounds
+  x ^= x >> 16; x *= 0x7FEB352Du; x ^= x >> 15; x *= 0x846CA68Bu; x ^= x >> 16;
+  return x;
+}
+struct ConvectPattern {
+  int vertical, m, phi;       // pair (s, s + m) along rows / columns when ((s - phi) mod 2m) < m
+  uint32_t pair_key;          // seed of the per-pair Bernoulli draws
+};
+__device__ __forceinline__ ConvectPattern convect_pattern(const Params& p, int b) {
+  const uint2 r = philox2x32_10(make_uint2((uint32_t)b, (uint32_t)p.time_index),
+                                (uint32_t)p.conv_seed ^ (uint32_t)(p.conv_seed >> 32));
+  ConvectPattern c;
+  const int n_off = p.conv_distance >= 4 ? 4 : 2;          // offsets of squared length 1 (and 4)
+  const int o = (int)(r.x % (uint32_t)n_off);
+  c.vertical = o & 1;
+  c.m = o < 2 ? 1 : 2;
+  c.phi = (int)((r.x >> 8) % (uint32_t)(2 * c.m));
+  c.pair_key = r.y;
+  return c;
+}
+
+// Source CV of (r, c) under the pattern: its partner when the pair swaps, else itself.
+// `dsc` is the plan's RAW descriptor plane in global memory (zone byte per CV).
+__device__ __forceinline__ int convect_source(const Params& p, const ConvectPattern& cp,
+                                              const uint16_t* __restrict__ dsc, int r, int c) {
+  const int self = r * p.W + c;
+  const int z = desc_zone(dsc[self]);
+  if (z == SBX_ZONE_NONE) return self;                     // only room CVs move
+  const int sc = cp.vertical ? r : c;
+  const int tmod = (sc + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
+  const int sp = tmod < cp.m ? sc + cp.m : sc - cp.m;
+  if (sp < 0 || sp >= (cp.vertical ? p.H : p.W)) return self;
+  const int other = cp.vertical ? sp * p.W + c : r * p.W + sp;
+  if (desc_zone(dsc[other]) != z) return self;             // partner in another room / a wall
+  if (p.conv_p < 1.0) {
+    const uint32_t thr = (uint32_t)(p.conv_p * 4294967296.0);
+    if (mix32((uint32_t)(self < other ? self : other) ^ cp.pair_key) >= thr) return self;
+  }
+  return other;
+}
+
+// ---------------------------------------------------------------------------
 // resident path
 // ---------------------------------------------------------------------------
 
@@ -906,6 +959,19 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     float* tmp = in; in = out; out = tmp;
   }
 
+  if (p.conv_p > 0.0 && p.conv_perm == nullptr && !p.fd_only) {     // device-RNG mode
+    const ConvectPattern cp = convect_pattern(p, b);
+    const uint16_t* raw = p.desc + (size_t)plan * n_cv;
+    for (int i = tid; i < n_cv; i += NT) {
+      const int r = i / W, c = i - r * W;
+      const int src = convect_source(p, cp, raw, r, c);
+      const int rs = src / W;
+      out[r * P + c] = in[rs * P + (src - rs * W)];
+    }
+    __syncthreads();
+    float* tmp = in; in = out; out = tmp;
+  }
+
   // ---- stage 3: write back + zone / grid sums ---------------------------------
   if constexpr (use_tma) {
     if (warp == 0) {
@@ -1144,6 +1210,13 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
   if (p.conv_perm != nullptr && !p.fd_only) {
     const int32_t* perm = p.conv_perm + (size_t)b * n_cv;
     for (int i = tid; i < n_cv; i += kGsThreads) Tp[i] = T[perm[i]];
+    __syncthreads();
+    for (int i = tid; i < n_cv; i += kGsThreads) T[i] = Tp[i];
+    __syncthreads();
+  }
+  if (p.conv_p > 0.0 && p.conv_perm == nullptr && !p.fd_only) {     // device-RNG mode
+    const ConvectPattern cp = convect_pattern(p, b);
+    for (int i = tid; i < n_cv; i += kGsThreads) Tp[i] = T[convect_source(p, cp, gD, i / W, i % W)];
     __syncthreads();
     for (int i = tid; i < n_cv; i += kGsThreads) T[i] = Tp[i];
     __syncthreads();
@@ -1491,6 +1564,191 @@ __global__ void __launch_bounds__(kStreamThreads, SBX_ZR_MIN_CTAS) k_zone_reduce
     }
   }
   // a slot whose zone is still NONE only ever collected CVs outside every zone
+  warp_merge_zone_sums(zL, runL, bins, lane);
+  warp_merge_zone_sums(zR, runR, bins, lane);
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) total += __shfl_xor_sync(0xffffffffu, total, o);
+  if (lane == 0) fix_add(&bins[Z], total);
+  __syncthreads();
+  long long* zs = p.zone_sum + (size_t)b * (Z + 1);
+  if (tile == 0 && tid == 0) p.zone_ref[b] = 0.f;
+  for (int i = tid; i <= Z; i += kStreamThreads)
+    if (bins[i] != 0) fix_add(&zs[i], bins[i]);
+}
+
+// ---------------------------------------------------------------------------
+// Stochastic convection, DEVICE-RNG mode (streaming path), fused with the zone reduction.
+//
+// The reference model (stochastic_convection_simulator.py:62-145) draws, per room CV and with
+// probability p, a partner within squared distance `distance`, shuffles the swap list and
+// applies the swaps one after the other: inherently sequential, and driven by Python's
+// Mersenne Twister.  The exact replay (sbsim_b200/convection.py, SBX_F_CONVECTION_PERM) keeps
+// parity; it is a host loop over every room CV.  This mode keeps the model's invariants --
+// temperatures only move inside a room, every move is within the same squared distance, a
+// CV takes part in a swap with probability p, the grid's and every zone's sums are unchanged
+// -- with a counter-based generator and a swap pattern that needs no sequential pass: per
+// (building, step) one axis-aligned offset (0,1) / (1,0) / (0,2) / (2,0) (those with squared
+// length <= distance) and a phase are drawn (Philox-2x32-10); CVs are paired along that
+// offset in disjoint pairs, and a pair swaps when both CVs belong to the same room and its
+// own Bernoulli(p) draw says so.  Over steps the offsets alternate at random, so heat mixes
+// in both directions like it does under the reference's random partner choice.
+//
+// One pass reads the field once, takes the zone / grid sums (unchanged by an in-room swap)
+// and writes the permuted field into the next buffer of the rotation: the traffic of
+// k_zone_reduce plus one write of the field.
+// ---------------------------------------------------------------------------
+template <int V>
+__global__ void __launch_bounds__(kStreamThreads, 4) k_convect_reduce(const Params p) {
+  __shared__ long long bins[kMaxZones + 1];
+  const StreamTiling tl = stream_tiling(p.H, p.W, V);
+  const int b = blockIdx.x / tl.tiles;
+  const int tile = blockIdx.x - b * tl.tiles;
+  const int ty = tile / tl.tiles_x, tx = tile - ty * tl.tiles_x;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const int H = p.H, W = p.W, Z = p.Z;
+  const size_t n_cv = (size_t)H * W;
+  const int plan = p.n_plans == 1 ? 0 : b;
+  for (int i = tid; i <= Z; i += kStreamThreads) bins[i] = 0;
+  __syncthreads();
+  const int cur = p.cur[b];
+  const float* __restrict__ t = p.tbuf[cur] + (size_t)b * n_cv;
+  float* __restrict__ tout = p.tbuf[(cur + 1) % 3] + (size_t)b * n_cv;
+  const uint16_t* __restrict__ dsc = p.desc + (size_t)plan * n_cv;
+  const ConvectPattern cp = convect_pattern(p, b);
+  const uint32_t thr = p.conv_p >= 1.0 ? 0xFFFFFFFFu : (uint32_t)(p.conv_p * 4294967296.0);
+  const bool always = p.conv_p >= 1.0;
+  const int c0 = (tx * 32 + lane) * V;
+  const int r0 = (ty * (kStreamThreads / 32) + warp) * tl.rows_per_warp;
+  long long total = 0, runL = 0, runR = 0;
+  int zL = SBX_ZONE_NONE, zR = SBX_ZONE_NONE;
+  const bool col_ok = c0 < W;           // lanes right of the grid still take part in the shuffles
+  if (r0 < H) {                         // warp-uniform
+    const int nr = min(tl.rows_per_warp, H - r0);
+    for (int i = 0; i < nr; ++i) {
+      const int r = r0 + i;
+      const size_t off = (size_t)r * W + c0;
+      float tv[V], o[V];
+      uint32_t d[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) { tv[e] = 0.f; d[e] = (uint32_t)SBX_ZONE_NONE << SBX_DESC_ZONE_SHIFT; }
+      if (col_ok) {
+        load_f<V>(t + off, tv);
+        load_d<V>(dsc + off, d);
+        if (i + SBX_ZR_PREFETCH < nr) asm volatile("prefetch.global.L2 [%0];" ::"l"(t + off + (size_t)SBX_ZR_PREFETCH * W));
+      }
+      // ---- zone / grid sums of the INPUT field (== those of the output) ----
+      const int z_first = desc_zone(d[0]), z_last = desc_zone(d[V - 1]);
+      if (z_first != zL && z_first != SBX_ZONE_NONE) {
+        if (zL != SBX_ZONE_NONE && runL != 0) fix_add(&bins[zL], runL);
+        zL = z_first;
+        runL = 0;
+      }
+      if (z_last != zR && z_last != SBX_ZONE_NONE && z_last != zL) {
+        if (zR != SBX_ZONE_NONE && runR != 0) fix_add(&bins[zR], runR);
+        zR = z_last;
+        runR = 0;
+      }
+      int sl = 0, sr = 0, sa = 0;
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        const int z = desc_zone(d[e]);
+        const int v = __float2int_rn(__fmul_rn(tv[e], kFixScaleF));
+        sa += v;
+        if (z == zL) sl += v;
+        else if (z == zR) sr += v;
+        else if (z != SBX_ZONE_NONE) fix_add(&bins[z], (long long)v);
+      }
+      total += sa;
+      runL += sl;
+      runR += sr;
+      // ---- the swap pattern ----
+      // candidate partner values / zones of the V CVs: the same columns of row r +- m
+      // (vertical pattern: one more vector load of T and of the descriptor), or the columns
+      // c +- m of this row (horizontal: this thread's vector and its lane neighbours' by
+      // shuffle; the two lanes at the warp's ends read the adjacent tile from memory)
+      float pt[V];
+      int pz[V];
+#pragma unroll
+      for (int e = 0; e < V; ++e) { pt[e] = tv[e]; pz[e] = -1; }
+      if (cp.vertical) {
+        const int tmod = (r + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
+        const int rp = tmod < cp.m ? r + cp.m : r - cp.m;
+        if (rp >= 0 && rp < H && col_ok) {
+          uint32_t dp[V];
+          load_f<V>(t + (size_t)rp * W + c0, pt);
+          load_d<V>(dsc + (size_t)rp * W + c0, dp);
+#pragma unroll
+          for (int e = 0; e < V; ++e) pz[e] = desc_zone(dp[e]);
+        }
+      } else {
+        // window of V + 4 columns around the vector: [c0 - 2, c0 + V + 2)
+        float wt[V + 4];
+        int wz[V + 4];
+#pragma unroll
+        for (int e = 0; e < V; ++e) { wt[2 + e] = tv[e]; wz[2 + e] = desc_zone(d[e]); }
+        if constexpr (V == 4) {
+          wt[0] = __shfl_up_sync(0xffffffffu, tv[2], 1); wt[1] = __shfl_up_sync(0xffffffffu, tv[3], 1);
+          wt[6] = __shfl_down_sync(0xffffffffu, tv[0], 1); wt[7] = __shfl_down_sync(0xffffffffu, tv[1], 1);
+          const int zlo = wz[4] | (wz[5] << 8), zhi = wz[2] | (wz[3] << 8);
+          const int zl = __shfl_up_sync(0xffffffffu, zlo, 1), zr = __shfl_down_sync(0xffffffffu, zhi, 1);
+          wz[0] = zl & 0xFF; wz[1] = zl >> 8; wz[6] = zr & 0xFF; wz[7] = zr >> 8;
+          if (col_ok && (lane == 0 || lane == 31 || c0 + V >= W)) {     // the window leaves the warp's columns
+#pragma unroll
+            for (int k = 0; k < 2; ++k) {
+              const int cl = c0 - 2 + k, cr = c0 + V + k;
+              if (lane == 0) {
+                wz[k] = cl >= 0 ? desc_zone(dsc[(size_t)r * W + cl]) : -1;
+                wt[k] = cl >= 0 ? t[(size_t)r * W + cl] : 0.f;
+              }
+              if (lane == 31 || c0 + V >= W) {
+                wz[6 + k] = cr < W ? desc_zone(dsc[(size_t)r * W + cr]) : -1;
+                wt[6 + k] = cr < W ? t[(size_t)r * W + cr] : 0.f;
+              }
+            }
+          }
+        } else if (col_ok) {
+#pragma unroll
+          for (int k = 0; k < 2; ++k) {                     // V == 1: plain loads
+            const int cl = c0 - 2 + k, cr = c0 + V + k;
+            wz[k] = cl >= 0 ? desc_zone(dsc[(size_t)r * W + cl]) : -1;
+            wt[k] = cl >= 0 ? t[(size_t)r * W + cl] : 0.f;
+            wz[V + 2 + k] = cr < W ? desc_zone(dsc[(size_t)r * W + cr]) : -1;
+            wt[V + 2 + k] = cr < W ? t[(size_t)r * W + cr] : 0.f;
+          }
+        }
+#pragma unroll
+        for (int e = 0; e < V; ++e) {
+          const int tmod = (c0 + e + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
+          const int sh = tmod < cp.m ? cp.m : -cp.m;       // +-1 or +-2
+          // select from the window without dynamic indexing
+          const float a1 = sh > 0 ? wt[2 + e + 1] : wt[2 + e - 1];
+          const float a2 = sh > 0 ? wt[2 + e + 2] : wt[2 + e - 2];
+          const int b1 = sh > 0 ? wz[2 + e + 1] : wz[2 + e - 1];
+          const int b2 = sh > 0 ? wz[2 + e + 2] : wz[2 + e - 2];
+          pt[e] = cp.m == 1 ? a1 : a2;
+          pz[e] = cp.m == 1 ? b1 : b2;
+        }
+      }
+#pragma unroll
+      for (int e = 0; e < V; ++e) {
+        o[e] = tv[e];
+        const int z = desc_zone(d[e]);
+        if (z == SBX_ZONE_NONE || pz[e] != z) continue;      // only room CVs move, inside their room
+        if (!always) {
+          const int c = c0 + e;
+          const int sc = cp.vertical ? r : c;
+          const int tmod = (sc + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
+          const int sp = tmod < cp.m ? sc + cp.m : sc - cp.m;
+          const size_t self = (size_t)r * W + c;
+          const size_t poff = cp.vertical ? (size_t)sp * W + c : (size_t)r * W + sp;
+          const uint32_t key = (uint32_t)(self < poff ? self : poff);
+          if (mix32(key ^ cp.pair_key) >= thr) continue;
+        }
+        o[e] = pt[e];
+      }
+      if (col_ok) store_f<V>(tout + off, o);
+    }
+  }
   warp_merge_zone_sums(zL, runL, bins, lane);
   warp_merge_zone_sums(zR, runR, bins, lane);
 #pragma unroll

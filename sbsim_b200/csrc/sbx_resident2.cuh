@@ -885,6 +885,20 @@ k_resident_step2(const Params p, const __grid_constant__ CUtensorMap tmap_t) {
       { float* tmp = in; in = out; out = tmp; }
       { const int t = i_in; i_in = i_out; i_out = t; }
     }
+    if (p.conv_p > 0.0 && p.conv_perm == nullptr && sums) {   // device-RNG convection (k_convect_reduce)
+      const ConvectPattern cp = convect_pattern(p, b);
+      const uint16_t* raw = p.desc + (size_t)(shared_plan ? 0 : b) * n_cv;
+      const int W = p.W, P = L.P;
+      for (int i = tid; i < n_cv; i += NT) {
+        const int r = i / W, c = i - r * W;
+        const int src = convect_source(p, cp, raw, r, c);
+        const int rs = src / W;
+        out[r * P + c] = in[rs * P + (src - rs * W)];
+      }
+      compute_barrier();
+      { float* tmp = in; in = out; out = tmp; }
+      { const int t = i_in; i_in = i_out; i_out = t; }
+    }
     {
       const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(last_lmax));
       if (lane == 0) atomicMax(&misc[kMiscMax + ph], wm);
@@ -1095,6 +1109,19 @@ k_resident_step2(const Params p, const __grid_constant__ CUtensorMap tmap_t) {
       const int src = perm[i];
       const int r = i / W, rs = src / W;
       out[r * P + (i - r * W)] = in[rs * P + (src - rs * W)];
+    }
+    __syncthreads();
+    float* tmp = in; in = out; out = tmp;
+  }
+  if (p.conv_p > 0.0 && p.conv_perm == nullptr && sums) {     // device-RNG convection (k_convect_reduce)
+    const ConvectPattern cp = convect_pattern(p, b);
+    const uint16_t* raw = p.desc + (size_t)plan * n_cv;
+    const int W = p.W, P = L.P;
+    for (int i = tid; i < n_cv; i += NT) {
+      const int r = i / W, c = i - r * W;
+      const int src = convect_source(p, cp, raw, r, c);
+      const int rs = src / W;
+      out[r * P + c] = in[rs * P + (src - rs * W)];
     }
     __syncthreads();
     float* tmp = in; in = out; out = tmp;

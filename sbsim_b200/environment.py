@@ -323,6 +323,11 @@ class Environment:
     self._bind_outputs()
     # stochastic convection: exact host replay, one generator stream per env
     self._conv = b.convection_simulator
+    if self._conv is not None and getattr(self._conv, "mode", "replay") == "device":
+      # device-RNG mode: nothing is drawn on the host (see sbsim_b200/convection.py)
+      seed = self._conv._seed if self._conv._seed is not None else int.from_bytes(__import__("os").urandom(8), "little")
+      self._handle.set_device_convection(self._conv._p, self._conv._distance, seed)
+      self._conv = None
     if self._conv is not None:
       self._conv_streams = [self._conv.make_stream() for _ in range(B)]
       self._conv_rooms = []

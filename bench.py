@@ -48,7 +48,7 @@ def parse_args():
   ap.add_argument("--steps", type=int, default=200)
   ap.add_argument("--warmup", type=int, default=5)
   ap.add_argument("--impl", choices=["sbx", "reference"], default="sbx")
-  ap.add_argument("--workload", choices=["randomized", "office"], default="randomized")
+  ap.add_argument("--workload", choices=["randomized", "office", "sac_rollout"], default="randomized")
   ap.add_argument("--envs-per-gpu", type=int, default=None)
   ap.add_argument("--layouts", type=int, default=1024)
   ap.add_argument("--histogram", type=int, default=1)
@@ -176,16 +176,21 @@ def build_env(args, rank, local_rank):
   from sbsim_b200 import floorplan, workloads
   path = {"auto": sbx.PATH_AUTO, "streaming": sbx.PATH_STREAMING,
           "resident": sbx.PATH_RESIDENT}[args.path]
-  episode = args.warmup + args.steps + 16
-  if args.workload == "randomized":
-    n = args.envs_per_gpu or 32768
+  episode = args.warmup + args.steps + 16 + (24 if dist_env()[2] > 1 else 0)
+  if args.workload in ("randomized", "sac_rollout"):
+    n = args.envs_per_gpu or (1024 if args.workload == "sac_rollout" else 32768)
+    if args.workload == "sac_rollout":
+      episode = max(episode, 288)
     env, wl = workloads.make_randomized_env(
         n, seed=2024 + rank, episode_steps=episode, n_layouts=args.layouts,
         histogram=bool(args.histogram), device=local_rank, kernel_path=path,
         convergence_threshold=args.convergence_threshold, iteration_limit=args.iteration_limit)
     if args.convection == "device":
       env.handle.set_device_convection(*workloads.CALIBRATED_CONVECTION)
-    desc = {"workload": "randomized-64x96 (BASELINE.json configs[3] per-GPU shard)",
+    desc = {"workload": ("SAC rollout: randomized-64x96 buildings, one-day (288-step) episode, actions from a "
+                         "fixed-seed tanh-Gaussian policy stub drawn on the device (BASELINE.json configs[4] per-GPU shard)"
+                         if args.workload == "sac_rollout" else
+                         "randomized-64x96 (BASELINE.json configs[3] per-GPU shard)"),
             "envs_per_gpu": n, "grid": [64, 96], "layouts": wl.n_layouts,
             "plans": "per-env descriptor, materials, weather, T0, actions",
             "stochastic_convection": "device-rng mode" if args.convection == "device" else "off"}
@@ -228,16 +233,21 @@ def run_sbx(args):
   # The other single-GPU configurations of BASELINE.json, measured briefly beside the
   # headline (N=1 only): configs[1]'s size class (4096 copies of one 744x1004 plan,
   # streaming path) and configs[2] (65536 randomised buildings on one GPU).
-  if world == 1 and args.others and args.workload == "randomized" and args.envs_per_gpu is None:
+  if args.others and args.workload == "randomized" and args.envs_per_gpu is None:
     others = []
-    for wl_name, envs, steps in (("office", 4096, 20), ("randomized", 65536, 50)):
+    todo = [("sac_rollout", 1024, 280, "default")]          # configs[4]: at every N
+    if world == 1:
+      todo = [("office", 4096, 16, "default"), ("office", 4096, 16, "off"),
+              ("randomized", 65536, 50, "default")] + todo
+    for wl_name, envs, steps, conv in todo:
       a2 = copy.copy(args)
-      a2.workload, a2.envs_per_gpu, a2.steps, a2.warmup = wl_name, envs, steps, 3
+      a2.workload, a2.envs_per_gpu, a2.steps, a2.warmup, a2.convection = wl_name, envs, steps, 3, conv
       try:
-        l2 = _measure(a2, torch, dist, rank, local_rank, world, dev, with_cpu=wl_name == "office")
+        l2 = _measure(a2, torch, dist, rank, local_rank, world, dev,
+                      with_cpu=(wl_name == "office" and conv == "default"))
         others.append({k: l2[k] for k in ("value", "unit", "steps", "warmup", "ms_per_step",
                                           "config", "gpu_launches", "roofline", "e2e",
-                                          "cpu_baseline") if k in l2})
+                                          "cpu_baseline", "with_allgather") if k in l2})
       except Exception as e:  # pylint: disable=broad-except
         others.append({"config": {"workload": wl_name, "envs_per_gpu": envs},
                        "error": f"{type(e).__name__}: {e}"})
@@ -264,17 +274,18 @@ def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
 
   gen = torch.Generator(device=dev)
   gen.manual_seed(3000 + rank)
-  actions = torch.rand((W + K, B, A), device=dev, generator=gen) * 2.0 - 1.0
-  obs = torch.zeros((B, D), device=dev)
-  rew = torch.zeros(B, device=dev)
-  st = torch.zeros(B, dtype=torch.int32, device=dev)
-  dis = torch.zeros(B, device=dev)
+  n_extra = 24 if world > 1 else 0       # steps of the all-gather variant timed after the main loop
+  if args.workload == "sac_rollout":     # tanh-Gaussian policy stub (the TF-Agents learner is not in this image)
+    actions = torch.tanh(torch.randn((W + K + n_extra, B, A), device=dev, generator=gen))
+  else:
+    actions = torch.rand((W + K + n_extra, B, A), device=dev, generator=gen) * 2.0 - 1.0
+  from sbsim_b200 import distributed
+  packed = distributed.PackedTimeStep(B, D, dev)   # [obs | reward | step_type | discount] in one block
+  obs, rew, st, dis = packed.obs, packed.reward, packed.step_type, packed.discount
   stream = torch.cuda.current_stream(dev)
   sptr = stream.cuda_stream
-  gathered = None
-  if world > 1 and args.allgather:
-    from sbsim_b200 import distributed
-    gathered = distributed.TimeStepGather(obs, rew, st)
+  gather = distributed.TimeStepGather(packed) if world > 1 else None
+  gathered = gather if (world > 1 and args.allgather) else None
 
   def barrier():
     if world > 1:
@@ -284,7 +295,7 @@ def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
   def one_step(i):
     env.step_device(actions[i], obs, rew, st, dis, stream=sptr)
     if gathered is not None:
-      gathered(obs, rew, st)
+      gathered()
 
   # ---- device-resident timing (value) ----
   env.reset_device(obs, rew, st, dis, stream=sptr)
@@ -312,6 +323,39 @@ def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
   sweeps = int(info1.sweeps_total - info0.sweeps_total)
   mean_sweeps = sweeps / float(B * K)
   value = world * B * K / (max_ms / 1e3)
+
+  # ---- the optional collective (BASELINE.json configs[3]: "optional NCCL obs all-gather"):
+  # the same steps continued with ONE ncclAllGather of the packed TimeStep block per step,
+  # and the collective alone for its bus bandwidth ----
+  allgather = None
+  if gather is not None and not args.allgather:
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(n_extra):
+      env.step_device(actions[W + K + i], obs, rew, st, dis, stream=sptr)
+      gather()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ag_ms = float(t.item()) / n_extra
+    barrier()
+    e0.record(stream)
+    for i in range(20):
+      gather()
+    e1.record(stream)
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1)], device=dev, dtype=torch.float64)
+    dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    coll_ms = float(t.item()) / 20
+    total_bytes = gather.bytes_per_rank * world
+    allgather = {"value": world * B / (ag_ms / 1e3), "unit": UNIT, "ms_per_step": ag_ms, "steps": n_extra,
+                 "collective": "ncclAllGather (torch.distributed.all_gather_into_tensor) of one packed "
+                               "[obs | reward | step_type | discount] block per rank, every step, to every rank",
+                 "bytes_per_rank": gather.bytes_per_rank, "collective_ms": coll_ms,
+                 "algbw_gbs": total_bytes / (coll_ms / 1e3) / 1e9,
+                 "busbw_gbs": total_bytes * (world - 1) / world / (coll_ms / 1e3) / 1e9}
 
   # ---- kernel-timing pass: CUDA events recorded by the library around every solve
   # launch, on the stream the kernel is launched on (sbx_timing_begin / _end) ----
@@ -417,6 +461,8 @@ def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
       "clocks": sampler.summary(), "gpu_launches": launches,
       "roofline": roofline,
   }
+  if allgather is not None:
+    line["with_allgather"] = allgather
   if e2e is not None:
     line["e2e"] = e2e
   if cpu is not None:

@@ -801,8 +801,11 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.obs_zone_order, int32_t, (size_t)c.n_plans * Z);
   ALLOC(p.desc_spk, uint16_t, h->path == SBX_PATH_STREAMING ? (size_t)c.n_plans * N : 1);
   h->v2_capable = 0;
+  // k_resident_step2 is opt-in (SBX_RESIDENT_V2=1): measured on B200 (32768 x 64x96) it ties
+  // k_resident_step at 2.5 sweeps per step (0.955 ms both) and loses 3 % at 2.6 (1.010 vs
+  // 0.981 ms): both are bound by the shared-memory pipe during the sweeps, see DESIGN.md 6
   if (h->path == SBX_PATH_RESIDENT && c.solver == SBX_SOLVER_TF_JACOBI && h->V == 4 && L.use_tmap &&
-      !getenv("SBX_RESIDENT_V1")) {
+      getenv("SBX_RESIDENT_V2") && atoi(getenv("SBX_RESIDENT_V2")) != 0) {
     p.g2 = resident2_geom(L, c.height, c.width, (int)Z);
     if (p.g2.total <= max_optin) {
       cudaError_t e2 = cudaFuncSetAttribute(k_resident_step2, cudaFuncAttributeMaxDynamicSharedMemorySize, p.g2.total);

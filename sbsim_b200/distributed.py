@@ -23,28 +23,49 @@ def rank_seed(base_seed: int, rank: int) -> int:
   return base_seed + rank
 
 
-class TimeStepGather:
-  """Pre-allocated all-gather of (observation, reward, step_type) over equal shards."""
+class PackedTimeStep:
+  """One device block [obs B*D | reward B | step_type B (int32) | discount B] with typed views:
+  the layout libsbx itself uses for a TimeStep (sbx_api.cu, `d_obs` block), so that a whole
+  TimeStep moves in ONE copy or ONE collective."""
 
-  def __init__(self, obs, reward, step_type, group=None):
+  def __init__(self, batch: int, obs_dim: int, device):
+    import torch
+    self.batch, self.obs_dim = int(batch), int(obs_dim)
+    self.block = torch.zeros(self.batch * (self.obs_dim + 3), dtype=torch.float32, device=device)
+    self.obs, self.reward, self.step_type, self.discount = self.views(self.block[None])
+    self.obs, self.reward = self.obs[0], self.reward[0]
+    self.step_type, self.discount = self.step_type[0], self.discount[0]
+
+  def views(self, blocks):
+    """Typed views of `blocks` [n, B*(D+3)] -> obs [n,B,D], reward [n,B], step_type [n,B], discount [n,B]."""
+    import torch
+    b, d = self.batch, self.obs_dim
+    obs = blocks[:, :b * d].view(blocks.shape[0], b, d)
+    reward = blocks[:, b * d:b * d + b]
+    step_type = blocks[:, b * d + b:b * d + 2 * b].view(torch.int32)
+    discount = blocks[:, b * d + 2 * b:b * d + 3 * b]
+    return obs, reward, step_type, discount
+
+
+class TimeStepGather:
+  """Pre-allocated all-gather of every rank's packed TimeStep block: ONE collective per step
+  (ncclAllGather through torch.distributed.all_gather_into_tensor; gloo in the CPU tests)."""
+
+  def __init__(self, packed: PackedTimeStep, group=None):
     import torch
     import torch.distributed as dist
     self._dist = dist
     self._group = group
+    self.packed = packed
     self.world = dist.get_world_size(group)
-    w = self.world
-    self.obs = torch.empty((w * obs.shape[0],) + tuple(obs.shape[1:]), dtype=obs.dtype,
-                           device=obs.device)
-    self.reward = torch.empty((w * reward.shape[0],), dtype=reward.dtype, device=reward.device)
-    self.step_type = torch.empty((w * step_type.shape[0],), dtype=step_type.dtype,
-                                 device=step_type.device)
+    self.blocks = torch.empty((self.world, packed.block.numel()), dtype=packed.block.dtype,
+                              device=packed.block.device)
+    self.obs, self.reward, self.step_type, self.discount = packed.views(self.blocks)
+    self.bytes_per_rank = packed.block.numel() * 4
 
-  def __call__(self, obs, reward, step_type):
-    d = self._dist
-    d.all_gather_into_tensor(self.obs, obs.contiguous(), group=self._group)
-    d.all_gather_into_tensor(self.reward, reward.contiguous(), group=self._group)
-    d.all_gather_into_tensor(self.step_type, step_type.contiguous(), group=self._group)
-    return self.obs, self.reward, self.step_type
+  def __call__(self):
+    self._dist.all_gather_into_tensor(self.blocks.view(-1), self.packed.block, group=self._group)
+    return self.obs, self.reward, self.step_type, self.discount
 
 
 def _selftest(rank: int, world: int, port: int, out_path: str) -> None:
@@ -63,15 +84,19 @@ def _selftest(rank: int, world: int, port: int, out_path: str) -> None:
     assert hi - lo == b
     # each rank generates ITS shard of the workload from its own seed
     wl = workloads.randomized(b, seed=rank_seed(2024, rank), n_layouts=2)
-    obs = torch.full((b, d), float(rank)) + torch.arange(b)[:, None]
-    rew = torch.tensor(wl.weather_low, dtype=torch.float32)
-    st = torch.full((b,), rank, dtype=torch.int32)
-    gather = TimeStepGather(obs, rew, st)
-    o, r, s = gather(obs, rew, st)
-    assert o.shape == (world * b, d) and r.shape == (world * b,) and s.shape == (world * b,)
+    ts = PackedTimeStep(b, d, "cpu")
+    ts.obs.copy_(torch.full((b, d), float(rank)) + torch.arange(b)[:, None])
+    ts.reward.copy_(torch.tensor(wl.weather_low, dtype=torch.float32))
+    ts.step_type.fill_(rank)
+    ts.discount.fill_(0.5 + rank)
+    gather = TimeStepGather(ts)
+    o, r, s, di = gather()
+    assert o.shape == (world, b, d) and r.shape == (world, b) and s.shape == (world, b)
+    assert s.dtype == torch.int32
     for k in range(world):
-      assert torch.all(s[k * b:(k + 1) * b] == k)
-      assert torch.all(o[k * b:(k + 1) * b, 0] == float(k) + torch.arange(b))
+      assert torch.all(s[k] == k) and torch.all(di[k] == 0.5 + k)
+      assert torch.all(o[k, :, 0] == float(k) + torch.arange(b))
+    r = r.reshape(-1)
     # the max-over-ranks timing reduction bench.py uses
     t = torch.tensor([1.0 + rank], dtype=torch.float64)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)

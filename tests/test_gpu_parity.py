@@ -42,6 +42,53 @@ def _dense_q(cp, qcv):
   return q
 
 
+@pytest.fixture(params=["k_resident_step", "k_resident_step2"])
+def resident_kernel(request, monkeypatch):
+  """The resident path has two kernels: k_resident_step (default) and the record-driven
+  k_resident_step2 (SBX_RESIDENT_V2=1, read when a handle is created)."""
+  if request.param == "k_resident_step2":
+    monkeypatch.setenv("SBX_RESIDENT_V2", "1")
+  else:
+    monkeypatch.delenv("SBX_RESIDENT_V2", raising=False)
+  return request.param
+
+
+def test_resident_kernels_agree_bit_for_bit(resident_kernel):
+  """Both resident kernels against the oracle on random 64x96 plans with per-env plans,
+  weather and actions: bit-identical fields and identical sweep counts on the first step,
+  1e-4 afterwards (the workload of BASELINE.json configs[2..4])."""
+  from oracle import bench_support
+  B = 6
+  wl = workloads.randomized(B, seed=5, n_layouts=B)
+  env, _ = workloads.make_randomized_env(B, workload=wl, episode_steps=16, histogram=True,
+                                         kernel_path=sbx.PATH_RESIDENT)
+  try:
+    oracles = [bench_support.make_oracle_env(
+        wl.plans[b], float(wl.weather_low[b]), float(wl.weather_high[b]), float(wl.convection[b]),
+        float(wl.initial_temp[b]), workloads.NORMALIZATION, workloads.HISTOGRAM, 16,
+        workloads.DEFAULT_START) for b in range(B)]
+    env.reset()
+    for o in oracles:
+      o.reset()
+    rng = np.random.default_rng(9)
+    for step in range(6):
+      a = rng.uniform(-1, 1, (B, 2)).astype(np.float32)
+      ts = env.step(a)
+      temp = env.handle.download("temp", (B, 64, 96))
+      sweeps = env.handle.download("n_sweeps", (B,))
+      for b, o in enumerate(oracles):
+        ots = o.step(a[b])
+        assert sweeps[b] == o.info["n_sweeps"], (step, b)
+        np.testing.assert_allclose(ts.observation[b], ots[3], rtol=RTOL, atol=2e-5)
+        np.testing.assert_allclose(ts.reward[b], ots[1], rtol=RTOL, atol=1e-6)
+        if step == 0:
+          np.testing.assert_array_equal(temp[b], np.asarray(o.temp, dtype=np.float32))
+        else:
+          np.testing.assert_allclose(temp[b], np.asarray(o.temp, dtype=np.float64), rtol=RTOL)
+  finally:
+    env.close()
+
+
 @pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("plan_name", list(_plans()))
 def test_fd_step_bit_exact(path, plan_name):

@@ -415,8 +415,10 @@ def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
   launch_ms = solve_ms
   achieved = bytes_launch / (launch_ms / 1e3) / 1e9
   if resident:
-    kernel = ("k_resident_step (the whole diffusion solve of every building; %d launch(es) per "
-              "step, one per pipelined share of the batch)" % tm.n_chunks)
+    kname = {1: "k_resident_step", 2: "k_resident_step2", 3: "k_resident_step3"}.get(
+        int(env.handle.info().resident_kernel), "k_resident_step")
+    kernel = ("%s (the whole diffusion solve of every building; %d launch(es) per "
+              "step, one per pipelined share of the batch)" % (kname, tm.n_chunks))
   else:
     kernel = "k_sweep (one Jacobi sweep of every active building per launch; %.2f launches per step)" % (
         tm.n_solve_launches / max(tm.n_steps, 1))

@@ -171,7 +171,7 @@ typedef struct {
   int32_t step_count;    /* Environment._step_count */
   int32_t episode_ended; /* Environment._episode_ended */
   int32_t time_index;    /* steps since the episode's start timestamp */
-  int32_t reserved;
+  int32_t resident_kernel; /* resident TF-Jacobi solve last launched: 0 none yet, 1 k_resident_step, 2 k_resident_step2, 3 k_resident_step3 */
 } sbx_info;
 
 /* ---- fields for sbx_upload / sbx_download (host pointers) ----------------

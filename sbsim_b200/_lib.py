@@ -134,7 +134,7 @@ class SbxInfo(C.Structure):
       ("resident_ctas_per_sm", C.c_int32), ("device_bytes", C.c_int64),
       ("kernel_launches", C.c_int64), ("sweeps_total", C.c_int64),
       ("env_steps_total", C.c_int64), ("step_count", C.c_int32),
-      ("episode_ended", C.c_int32), ("time_index", C.c_int32), ("reserved", C.c_int32),
+      ("episode_ended", C.c_int32), ("time_index", C.c_int32), ("resident_kernel", C.c_int32),
   ]
 
 

@@ -2,16 +2,18 @@
 
 from __future__ import annotations
 
+import glob
+import hashlib
 import os
 import subprocess
 import sys
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 SRC = os.path.join(_HERE, "csrc", "sbx_api.cu")
-DEPS = [SRC, os.path.join(_HERE, "csrc", "sbx_kernels.cuh"),
-        os.path.join(_HERE, "csrc", "sbx_device.cuh"),
-        os.path.join(os.path.dirname(_HERE), "include", "sbx.h")]
+DEPS = sorted(glob.glob(os.path.join(_HERE, "csrc", "*.cu")) + glob.glob(os.path.join(_HERE, "csrc", "*.cuh"))) + [
+    os.path.join(os.path.dirname(_HERE), "include", "sbx.h")]
 OUT = os.path.join(_HERE, "lib", "libsbx.so")
+STAMP = OUT + ".srchash"      # hash of the sources + flags the library was built from (travels with it)
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
@@ -21,11 +23,22 @@ NVCC_FLAGS = [
 ]
 
 
+def source_hash() -> str:
+  h = hashlib.sha256()
+  for d in DEPS:
+    h.update(os.path.basename(d).encode())
+    with open(d, "rb") as f:
+      h.update(f.read())
+  h.update(" ".join(NVCC_FLAGS + os.environ.get("NVCC_EXTRA", "").split()).encode())
+  return h.hexdigest()
+
+
 def needs_build() -> bool:
-  if not os.path.exists(OUT):
+  """True unless libsbx.so was built from exactly these sources and flags (content hash, not mtime)."""
+  if not os.path.exists(OUT) or not os.path.exists(STAMP):
     return True
-  t = os.path.getmtime(OUT)
-  return any(os.path.getmtime(d) > t for d in DEPS)
+  with open(STAMP) as f:
+    return f.read().strip() != source_hash()
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -42,6 +55,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
     raise RuntimeError("nvcc failed building libsbx.so")
   if verbose:
     sys.stderr.write(res.stderr)
+  if out == OUT:
+    with open(STAMP, "w") as f:
+      f.write(source_hash() + "\n")
   return out
 
 

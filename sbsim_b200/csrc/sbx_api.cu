@@ -27,6 +27,7 @@
 #include "../../include/sbx.h"
 #include "sbx_kernels.cuh"
 #include "sbx_resident2.cuh"
+#include "sbx_resident3.cuh"
 
 using namespace sbx;
 
@@ -57,6 +58,11 @@ struct sbx_env {
   // k_resident_step2 (persistent, record-driven) when the grid allows it and no plan
   // overflows its list capacities; otherwise k_resident_step
   int v2_capable = 0, use_v2 = 0, v1_allocated = 0;
+  // k_resident_step3 (one thread per 4x4 tile, field in registers): the default where the grid
+  // allows it; handles with stochastic convection run k_resident_step for those steps
+  int v3_capable = 0, use_v3 = 0, v1_ready = 0, v23_ready = 0;
+  int resident3_ctas_per_sm = 0;
+  int last_resident_kernel = 0;  // sbx_info.resident_kernel
   int resident2_ctas_per_sm = 0;
   Params P;
   // host-level episode state
@@ -237,6 +243,7 @@ void fill_params(sbx_handle h) {
   p.discount = c.discount_factor; p.occ_norm = c.occupancy_normalization_constant;
   p.episode_steps = c.episode_steps;
   p.fd_only = 0;
+  p.one = 1.0f;
 }
 
 // launch helpers --------------------------------------------------------------
@@ -495,26 +502,47 @@ int ensure_v1_buffers(sbx_handle h) {
   return SBX_OK;
 }
 
+static bool step_has_convection(const Params& p) {
+  return !p.fd_only && (p.conv_perm != nullptr || p.conv_p > 0.0);
+}
+
 int prepare_plans(sbx_handle h, cudaStream_t st) {
-  if (!h->plans_dirty) return SBX_OK;
   Params& p = h->P;
   cudaError_t e;
-  h->use_v2 = 0;
-  if (h->v2_capable) {
-    const size_t sm = prepare2_smem(p.H * (p.W / 4), p.Z);
-    e = cudaFuncSetAttribute(k_prepare_plan2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
-    if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
-    k_prepare_plan2<<<p.n_plans, kPrepThreads, sm, st>>>(p);
-    if (int rc = launch_check(h, "k_prepare_plan2")) return rc;
-    // any plan whose lists do not fit sends the handle back to k_resident_step
-    std::vector<int32_t> counts((size_t)p.n_plans * 8);
-    CUDA_TRY(h, cudaMemcpyAsync(counts.data(), p.counts2, counts.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    CUDA_TRY(h, cudaStreamSynchronize(st));
-    h->use_v2 = 1;
-    for (int i = 0; i < p.n_plans; ++i)
-      if (counts[(size_t)i * 8 + 7] < 0) { h->use_v2 = 0; break; }
+  if (h->plans_dirty) { h->v1_ready = 0; h->v23_ready = 0; h->plans_dirty = 0; }
+  if (!h->v23_ready) {
+    h->use_v2 = 0;
+    h->use_v3 = 0;
+    if (h->v3_capable) {
+      k_prepare_plan3<<<p.n_plans, kPrepThreads, 0, st>>>(p);
+      if (int rc = launch_check(h, "k_prepare_plan3")) return rc;
+      // any plan that exceeds a capacity (pair patterns, zone parts per tile) sends the handle
+      // back to k_resident_step
+      std::vector<int32_t> counts((size_t)p.n_plans * 4);
+      CUDA_TRY(h, cudaMemcpyAsync(counts.data(), p.counts3, counts.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(h, cudaStreamSynchronize(st));
+      h->use_v3 = 1;
+      for (int i = 0; i < p.n_plans; ++i)
+        if (counts[(size_t)i * 4 + kC3Capable] == 0) { h->use_v3 = 0; break; }
+    }
+    if (!h->use_v3 && h->v2_capable) {
+      const size_t sm = prepare2_smem(p.H * (p.W / 4), p.Z);
+      e = cudaFuncSetAttribute(k_prepare_plan2, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e));
+      k_prepare_plan2<<<p.n_plans, kPrepThreads, sm, st>>>(p);
+      if (int rc = launch_check(h, "k_prepare_plan2")) return rc;
+      // any plan whose lists do not fit sends the handle back to k_resident_step
+      std::vector<int32_t> counts((size_t)p.n_plans * 8);
+      CUDA_TRY(h, cudaMemcpyAsync(counts.data(), p.counts2, counts.size() * sizeof(int32_t), cudaMemcpyDeviceToHost, st));
+      CUDA_TRY(h, cudaStreamSynchronize(st));
+      h->use_v2 = 1;
+      for (int i = 0; i < p.n_plans; ++i)
+        if (counts[(size_t)i * 8 + 7] < 0) { h->use_v2 = 0; break; }
+    }
+    h->v23_ready = 1;
   }
-  if (!h->use_v2) {
+  const bool need_v1 = (!h->use_v2 && !h->use_v3) || (h->use_v3 && step_has_convection(p));
+  if (need_v1 && !h->v1_ready) {
     if (int rc = ensure_v1_buffers(h)) return rc;
     const size_t smem = (sizeof(uint32_t) + sizeof(uint16_t)) * (size_t)(p.H * p.W / h->V);
     if (h->V == 4) e = cudaFuncSetAttribute(k_prepare_plan<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -531,8 +559,8 @@ int prepare_plans(sbx_handle h, cudaStream_t st) {
     if (h->V == 4) k_prepare_reduce<4><<<p.n_plans, kPrepThreads, sm2, st>>>(p);
     else k_prepare_reduce<1><<<p.n_plans, kPrepThreads, sm2, st>>>(p);
     if (int rc = launch_check(h, "k_prepare_reduce")) return rc;
+    h->v1_ready = 1;
   }
-  h->plans_dirty = 0;
   return SBX_OK;
 }
 
@@ -554,14 +582,22 @@ int run_resident(sbx_handle h, cudaStream_t st, bool with_header) {
   }
   const unsigned grid = (unsigned)(p.b_end - p.b_begin);
   if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
+  if (h->use_v3 && !step_has_convection(p)) {
+    k_resident_step3<<<grid, (unsigned)p.g3.nt, p.g3.total, st>>>(p);
+    h->last_resident_kernel = 3;
+    if (int rc = launch_check(h, "k_resident_step3")) return rc;
+    return timing_record(h, h->t_solve, h->t_solve_used, st);
+  }
   if (h->use_v2) {
     // persistent CTAs: one per resident slot, each walks buildings b, b + grid, ...
     k_resident_step2<<<v2_grid(h), kR2Threads, p.g2.total, st>>>(p, h->tmap_t);
+    h->last_resident_kernel = 2;
     if (int rc = launch_check(h, "k_resident_step2")) return rc;
     return timing_record(h, h->t_solve, h->t_solve_used, st);
   }
   if (h->V == 4) k_resident_step<4><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
   else k_resident_step<1><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
+  h->last_resident_kernel = 1;
   if (int rc = launch_check(h, "k_resident_step")) return rc;
   return timing_record(h, h->t_solve, h->t_solve_used, st);
 }
@@ -825,6 +861,28 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
       }
     }
   }
+  // k_resident_step3: default where the grid allows it (SBX_RESIDENT_V3=0 turns it off)
+  h->v3_capable = 0;
+  if (h->path == SBX_PATH_RESIDENT && c.solver == SBX_SOLVER_TF_JACOBI && !h->v2_capable && Z < 255 &&
+      resident3_supported(c.height, c.width) && !(getenv("SBX_RESIDENT_V3") && atoi(getenv("SBX_RESIDENT_V3")) == 0)) {
+    p.g3 = resident3_geom(c.height, c.width, (int)Z);
+    if (p.g3.total <= max_optin) {
+      cudaError_t e3 = cudaFuncSetAttribute(k_resident_step3, cudaFuncAttributeMaxDynamicSharedMemorySize, p.g3.total);
+      int nb3 = 0;
+      if (e3 == cudaSuccess) e3 = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&nb3, k_resident_step3, p.g3.nt, p.g3.total);
+      if (e3 != cudaSuccess) { fail(h, SBX_E_CUDA, "k_resident_step3 set-up failed: %s", cudaGetErrorString(e3)); return bail(SBX_E_CUDA); }
+      if (nb3 > 0) {
+        h->v3_capable = 1;
+        h->resident3_ctas_per_sm = nb3;
+        ALLOC(p.ent3, uint32_t, (size_t)c.n_plans * p.g3.nt);
+        ALLOC(p.gen3a, uint4, (size_t)c.n_plans * p.g3.nt);
+        ALLOC(p.gen3b, uint4, (size_t)c.n_plans * p.g3.nt);
+        ALLOC(p.gen3q, uint4, (size_t)c.n_plans * p.g3.nt);
+        ALLOC(p.pat3, uint16_t, (size_t)c.n_plans * p.g3.pat_cap);
+        ALLOC(p.counts3, int32_t, (size_t)c.n_plans * 4);
+      }
+    }
+  }
   ALLOC(p.hdr, unsigned char, B * header_bytes((int)Z));
   ALLOC(p.reset_temps, float, (size_t)c.n_reset * N);
   ALLOC(p.initial_temp, float, B);
@@ -925,7 +983,8 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   // exposed HVAC kernels they hide.  The option stays for callers with other shapes.
   h->n_chunks = 1;
   if (h->path == SBX_PATH_RESIDENT && c.solver == SBX_SOLVER_TF_JACOBI) {
-    const int per_sm = h->v2_capable ? h->resident2_ctas_per_sm : h->resident_ctas_per_sm;
+    const int per_sm = h->v3_capable ? h->resident3_ctas_per_sm
+                                     : h->v2_capable ? h->resident2_ctas_per_sm : h->resident_ctas_per_sm;
     h->P.prefetch_dist = h->n_sms * (per_sm > 0 ? per_sm : 1);
   }
   h->h_comfort = new (std::nothrow) uint8_t[T]();
@@ -972,7 +1031,8 @@ int sbx_get_info(sbx_handle h, sbx_info* out) {
   out->obs_dim = h->D;
   out->kernel_path = h->path;
   out->n_sms = h->n_sms;
-  out->resident_ctas_per_sm = h->resident_ctas_per_sm;
+  out->resident_ctas_per_sm = h->use_v3 ? h->resident3_ctas_per_sm : h->resident_ctas_per_sm;
+  out->resident_kernel = h->last_resident_kernel;
   out->device_bytes = h->device_bytes;
   unsigned long long sw = 0, loops = 0;
   CUDA_TRY(h, cudaDeviceSynchronize());

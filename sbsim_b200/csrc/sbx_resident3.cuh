@@ -149,7 +149,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan3(const Params p) 
     uint32_t o = 0;
     for (int w = 0; w < 32; ++w) { prefix[w] = o; o += (uint32_t)__popc(bitmap[w]); }
     prefix[32] = o;
-    if ((int)o > g.pat_cap) s_bad = 1;
+    if ((int)o > g.pat_cap || (int)o * 6 > g.nt) s_bad = 1;      // the kernel builds the table one item per thread
   }
   // rank inside the (kind, group, residue) bucket
   for (int it = tid; it < n_tiles; it += kPrepThreads) {
@@ -193,7 +193,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan3(const Params p) 
         heat = heat || dq;
         qs[e2 >> 2] |= (dq ? (uint32_t)desc_zone(d) : (uint32_t)Z) << (8 * (e2 & 3));
         const uint32_t z = r3_zone_slot(d, Z);
-        if (z != 0xFFu) {
+        if (z < (uint32_t)Z) {        // CVs outside every zone only enter the grid total
           int k = 0;
           while (k < np && zs[k] != z) ++k;
           if (k == np) {
@@ -395,6 +395,10 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
   float* gT = p.tbuf[0] + (size_t)b * n_cv;
   const uint32_t hdr_bytes = (uint32_t)header_bytes(Z);
   const bool sums = !p.fd_only;
+#ifdef SBX_PROFILE_PHASES
+  long long phase_t0__ = clock64();
+  const long long cta_t0__ = phase_t0__;
+#endif
 
   // ---- stage 0: bulk loads (plane + header), static per-thread data straight from global ----
   if (tid == 0) {
@@ -409,6 +413,9 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
   const int n_pat = cnt.z;
   const int kind = (int)((ent >> kEntKindShift) & 3u);
   const bool heat = (ent & kEntHeat) != 0u;
+  // this thread's item of the pattern table build (stage 1): the pattern's two combo indices
+  const int pt_i = tid / 6, pt_j = tid - pt_i * 6;
+  const uint32_t pt_pr = pt_i < G.pat_cap ? (uint32_t)__ldg(p.pat3 + (size_t)plan * G.pat_cap + pt_i) : 0u;
   uint4 ga = make_uint4(0u, 0u, 0u, 0u), gq = make_uint4(0u, 0u, 0u, 0u);
   if (kind == kR3Gen) {
     ga = __ldg(p.gen3a + (size_t)plan * G.nt + tid);
@@ -429,27 +436,23 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
   for (int i = tid; i < 2 * (Z + 1); i += (int)blockDim.x) bins[i] = 0u;
   __syncthreads();
   mbar_wait(bar, 0);
+  SBX_PHASE(0);   // launch .. bulk loads and per-thread list entries have arrived
   const float t_inf = scal[0];
 
   // ---- stage 1: pair-pattern table of this building (coefficients change with h and T_inf) ----
-  {
-    const uint16_t* gpat = p.pat3 + (size_t)plan * G.pat_cap;
-    for (int i = tid; i < n_pat * 6; i += (int)blockDim.x) {
-      const int pi = i / 6, j = i - pi * 6;
-      const uint32_t pr = __ldg(gpat + pi);
-      const int ia = (int)(pr & 0xFFu), ib = (int)(pr >> 8);
-      const Combo& ca = tab[ia];
-      const Combo& cb = tab[ib];
-      float4 v;
-      if (j == 0) v = make_float4(ca.k1, cb.k1, ca.k3, cb.k3);
-      else if (j == 1) v = make_float4(ca.k2, cb.k2, ca.k4, cb.k4);
-      else if (j == 2) v = make_float4(ca.hh, cb.hh, ca.hv, cb.hv);
-      else if (j == 3) v = make_float4(-ca.den, -cb.den, ca.rden, cb.rden);
-      else if (j == 4) v = make_float4(ca.vz, cb.vz, ca.uz, cb.uz);
-      else v = make_float4(ca.cm, cb.cm, __uint_as_float(ia < kNumMaterials ? 0xFFFFFFFFu : 0u),
-                           __uint_as_float(ib < kNumMaterials ? 0xFFFFFFFFu : 0u));
-      ptab[i] = v;
-    }
+  if (pt_i < n_pat) {        // kR3PatCap * 6 <= kR3MaxThreads: one item per thread
+    const int ia = (int)(pt_pr & 0xFFu), ib = (int)(pt_pr >> 8);
+    const Combo& ca = tab[ia];
+    const Combo& cb = tab[ib];
+    float4 v;
+    if (pt_j == 0) v = make_float4(ca.k1, cb.k1, ca.k3, cb.k3);
+    else if (pt_j == 1) v = make_float4(ca.k2, cb.k2, ca.k4, cb.k4);
+    else if (pt_j == 2) v = make_float4(ca.hh, cb.hh, ca.hv, cb.hv);
+    else if (pt_j == 3) v = make_float4(-ca.den, -cb.den, ca.rden, cb.rden);
+    else if (pt_j == 4) v = make_float4(ca.vz, cb.vz, ca.uz, cb.uz);
+    else v = make_float4(ca.cm, cb.cm, __uint_as_float(ia < kNumMaterials ? 0xFFFFFFFFu : 0u),
+                         __uint_as_float(ib < kNumMaterials ? 0xFFFFFFFFu : 0u));
+    ptab[tid] = v;
   }
 
   // ---- stage 2: the thread's tile -> registers, rim -> exchange buffer 0 ----
@@ -476,6 +479,7 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     for (int i = 0; i < 4; ++i) T[i] = make_float4(0.f, 0.f, 0.f, 0.f);
   }
   __syncthreads();      // the pattern table is complete (and every thread has its tile: the plane is free)
+  SBX_PHASE(1);   // pattern table, tile -> registers
   {
     // n3 = (cm * T_prev) / dt (tf_simulator.py:743-749), kept for every sweep of this step
     const float rdt = __frcp_rn(p.dt);
@@ -507,6 +511,7 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
   };
   if (kind != kR3Idle) publish(X0);
   __syncthreads();
+  SBX_PHASE(2);   // thermal-mass terms, first rim exchange
 
   // ---- stage 3: Jacobi sweeps to convergence (simulator.py:348-364) ----
   const int limit = p.iteration_limit;
@@ -527,8 +532,18 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     }
     // max|dT| <= threshold  <=>  no thread saw a delta above it (simulator.py:362); the
     // barrier doubles as the fence between the two exchange buffers
+#ifdef SBX_PROFILE_PHASES
+    const long long t_arrive__ = clock64();
+#endif
     const int above = __syncthreads_or(lmax > thr);
+#ifdef SBX_PROFILE_PHASES
+    if (b == p.B / 2 && lane == 0 && k <= 3 && !p.fd_only) {   // one probe CTA: who waits for whom
+      p.phase_cycles[8 + (tid >> 5) * 8 + 2 * (k - 1)] = (unsigned long long)(t_arrive__ - cta_t0__);
+      p.phase_cycles[8 + (tid >> 5) * 8 + 2 * (k - 1) + 1] = (unsigned long long)(clock64() - cta_t0__);
+    }
+#endif
     float4* tmp = Xr; Xr = Xw; Xw = tmp;
+    if (k == 1) SBX_PHASE(3); else SBX_PHASE(4);   // first sweep / later sweeps
     if (!above) break;
   }
 
@@ -556,29 +571,47 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
       f[4 * i] = __float2int_rn(a0); f[4 * i + 1] = __float2int_rn(a1);
       f[4 * i + 2] = __float2int_rn(a2); f[4 * i + 3] = __float2int_rn(a3);
     }
-    const bool any_gen = __any_sync(0xffffffffu, kind == kR3Gen);
-    if (!any_gen) {
-      int sv = 0;
+    int total = 0;
 #pragma unroll
-      for (int e = 0; e < 16; ++e) sv += f[e];
-      r3_zone_add(bins, Z, (int)((ent >> kEntZoneShift) & 0xFFu), sv, kind == kR3Pure, lane);
+    for (int e = 0; e < 16; ++e) total += f[e];
+    // whole grid (slot Z): every CV of every tile (exterior space holds T_inf, the reference: 0)
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)total & 0xFFFFu);
+    const int hi = __reduce_add_sync(0xffffffffu, total >> 16);
+    const int zone = (int)((ent >> kEntZoneShift) & 0xFFu);
+    const int zone0 = __shfl_sync(0xffffffffu, zone, 0);
+    if (__all_sync(0xffffffffu, kind == kR3Pure && zone == zone0)) {
+      // the common PURE warp: one zone, the sums are the ones just taken
+      if (lane == 0) {
+        atomicAdd(&bins[Z], lo);
+        atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + Z]), hi);
+        atomicAdd(&bins[zone0], lo);
+        atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + zone0]), hi);
+      }
     } else {
-      const int np = kind == kR3Gen ? (int)((ent >> kEntZoneShift) & 0xFFu) : (kind == kR3Pure ? 1 : 0);
-      uint4 gb = make_uint4(0u, 0u, 0u, 0u);
-      if (np > 2) gb = __ldg(p.gen3b + (size_t)plan * G.nt + tid);
-      const uint32_t pure_part = ((ent >> kEntZoneShift) & 0xFFu) | 0xFFFF0000u;
-      const uint32_t part0 = kind == kR3Pure ? pure_part : ga.z;
-      const int np_max = __reduce_max_sync(0xffffffffu, np);
-      for (int k2 = 0; k2 < np_max; ++k2) {
-        const uint32_t part = k2 == 0 ? part0 : k2 == 1 ? ga.w : k2 == 2 ? gb.x : k2 == 3 ? gb.y : k2 == 4 ? gb.z : gb.w;
-        int sv = 0;
+      if (lane == 0) {
+        atomicAdd(&bins[Z], lo);
+        atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + Z]), hi);
+      }
+      r3_zone_add(bins, Z, zone, total, kind == kR3Pure, lane);      // PURE lanes of a mixed warp
+      if (kind == kR3Gen) {
+        // GEN tiles: zones are scattered over the warp, so each thread adds its own parts
+        const int np = zone;
+        uint4 gb = make_uint4(0u, 0u, 0u, 0u);
+        if (np > 2) gb = __ldg(p.gen3b + (size_t)plan * G.nt + tid);
+        for (int k2 = 0; k2 < np; ++k2) {
+          const uint32_t part = k2 == 0 ? ga.z : k2 == 1 ? ga.w : k2 == 2 ? gb.x : k2 == 3 ? gb.y : k2 == 4 ? gb.z : gb.w;
+          int sv = 0;
 #pragma unroll
-        for (int e = 0; e < 16; ++e) sv += (part & (0x10000u << e)) ? f[e] : 0;
-        r3_zone_add(bins, Z, (int)(part & 0xFFu), sv, k2 < np, lane);
+          for (int e = 0; e < 16; ++e) sv += (part & (0x10000u << e)) ? f[e] : 0;
+          const int z = (int)(part & 0xFFu);
+          atomicAdd(&bins[z], (unsigned)sv & 0xFFFFu);
+          atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + z]), sv >> 16);
+        }
       }
     }
   }
   __syncthreads();      // plane complete (TMA store), bins complete
+  SBX_PHASE(5);   // write-back to the plane, zone sums
   if (tid == 0) {
     tma_store_1d(gT, plane, (uint32_t)(n_cv * 4));
     tma_store_commit();
@@ -586,16 +619,9 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
   if (tid < 32) {
     if (sums) {
       long long* zs = p.zone_sum + (size_t)b * (Z + 1);
-      long long grid = 0;                                // slot Z collected the CVs outside every zone
-      for (int i = lane; i <= Z; i += 32) {
-        const long long v = (long long)(int)bins[Z + 1 + i] * 65536 + (long long)bins[i];
-        if (i < Z) zs[i] = v;
-        grid += v;
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) grid += __shfl_xor_sync(0xffffffffu, grid, o);
+      for (int i = lane; i <= Z; i += 32)                // slot Z: the whole grid
+        zs[i] = (long long)(int)bins[Z + 1 + i] * 65536 + (long long)bins[i];
       if (lane == 0) {
-        zs[Z] = grid;
         p.zone_ref[b] = t_inf;
         atomicAdd(p.sweeps_total, (unsigned long long)k);
       }
@@ -606,6 +632,7 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
       tma_store_wait();
     }
   }
+  SBX_PHASE(6);   // results out, TMA store drained
 }
 
 }  // namespace sbx

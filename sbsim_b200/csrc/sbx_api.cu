@@ -874,10 +874,9 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
       if (nb3 > 0) {
         h->v3_capable = 1;
         h->resident3_ctas_per_sm = nb3;
-        ALLOC(p.ent3, uint32_t, (size_t)c.n_plans * p.g3.nt);
-        ALLOC(p.gen3a, uint4, (size_t)c.n_plans * p.g3.nt);
-        ALLOC(p.gen3b, uint4, (size_t)c.n_plans * p.g3.nt);
-        ALLOC(p.gen3q, uint4, (size_t)c.n_plans * p.g3.nt);
+        ALLOC(p.ent3, uint32_t, (size_t)c.n_plans * 2 * p.g3.nt);
+        ALLOC(p.rec3, uint4, (size_t)c.n_plans * 2 * p.g3.nt);
+        ALLOC(p.recz3, uint2, (size_t)c.n_plans * 2 * p.g3.nt);
         ALLOC(p.pat3, uint16_t, (size_t)c.n_plans * p.g3.pat_cap);
         ALLOC(p.counts3, int32_t, (size_t)c.n_plans * 4);
       }

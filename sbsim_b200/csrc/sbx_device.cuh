@@ -69,15 +69,16 @@ struct Resident2Geom {
 };
 
 // Shared-memory layout and per-plan list strides of k_resident_step3 (sbx_resident3.cuh):
-// one thread per 4x4 TILE of control volumes, temperatures in registers across the sweeps
+// HALF-TILES of 2 x 4 control volumes, one or two per thread, temperatures in registers across
+// the sweeps
 struct Resident3Geom {
-  int th, tw;          // tiles per column / per row (H/4, W/4)
-  int Tq;              // pitch of the exchange arrays in tiles (odd: the 16-byte bank group rotates row to row)
-  int nt;              // threads per CTA: th*tw rounded up to a warp
+  int hh, tw;          // half-tiles per column / per row (H/2, W/4)
+  int Tq;              // pitch of the exchange arrays in half-tiles (odd: the 16-byte bank group rotates row to row)
+  int nt;              // threads per CTA
   unsigned tq_magic;   // slot / Tq == umulhi(slot, tq_magic)
   int pat_cap;         // pair patterns per plan
-  int xarr;            // bytes of one exchange array (th * Tq float4, 128 B multiple)
-  int off_x0, off_x1, off_hdr, off_ptab, off_bins, off_misc, off_bar, total;
+  int xarr;            // bytes of one exchange array (hh * Tq float4, 128 B multiple)
+  int off_x0, off_x1, off_hdr, off_ptab, off_bins, off_zparts, off_misc, off_bar, total;
 };
 
 // Everything a kernel needs; passed by value.
@@ -129,13 +130,13 @@ struct Params {
   uint16_t* zfull;           // [P, zfull_cap]
   uint32_t* zpart;           // [P, zpart_cap]
   uint8_t* zchunk;           // [P, zchunk_cap]
-  // k_resident_step3 (k_prepare_plan3): per-plan tile lists
-  uint32_t* ent3;            // [P, nt] thread -> tile: slot | kind << 10 | neighbour flags << 12 | zone (PURE) << 16 | heat << 24
-  uint4* gen3a;              // [P, nt] GEN tiles: {patterns rows 0-1, patterns rows 2-3, zone part 0, zone part 1}
-  uint4* gen3b;              // [P, nt] zone parts 2..5 (slot | CV mask << 16)
-  uint4* gen3q;              // [P, nt] heat slot per CV (16 bytes)
-  uint16_t* pat3;            // [P, pat_cap] pair patterns: combo a | combo b << 8
-  int32_t* counts3;          // [P, 4] n_pure, n_gen, n_pat, capable (0: a capacity was exceeded)
+  // k_resident_step3 (k_prepare_plan3): per-plan half-tile schedule; index t = first half-tile of
+  // thread t, nt + t = its second one
+  uint32_t* ent3;            // [P, 2*nt] slot | kind << 12 | neighbour flags << 14 | zone (PURE) or parts << 18 | heat << 26
+  uint4* rec3;               // [P, 2*nt] non-PURE half-tiles: {4 pair patterns, heat slots row 0, row 1, -}
+  uint2* recz3;              // [P, 2*nt] their zone parts 0-3 (zone | CV mask << 8, two per word)
+  uint16_t* pat3;            // [P, pat_cap] pair patterns of the boundary half-tiles: combo a | combo b << 8
+  int32_t* counts3;          // [P, 4] -, -, n_pat, capable (0: a capacity was exceeded)
   float one;                 // 1.0f, opaque to the compiler (see pair_add in sbx_resident3.cuh)
   const float* reset_temps;  // [n_reset,H,W]
   const float* initial_temp; // [B]

@@ -7,15 +7,15 @@
 // shared-memory pipe AND ~70 % of the issue slots (profiles/r01_ncu_full_randomized.txt,
 // profiles/r02_*), so neither fewer instructions (v2: -20 %) nor fewer wavefronts alone moved them.
 //
-// Here one thread owns a 4x4 TILE of control volumes for the whole solve:
-//   * its 16 temperatures and 16 thermal-mass terms n3 = (cm * T_prev) / dt live in registers
-//     from the first sweep to the last; 12 of the 16 CVs find all four neighbours in the
-//     thread's own registers;
-//   * per sweep a tile exchanges only its rim with its four neighbour tiles: top row, bottom
-//     row, left column, right column, each one float4 in a double-buffered exchange array --
-//     4 x LDS.128 + 4 x STS.128 per 16 CVs (8 wavefronts per 4 CVs instead of 20-28), all
-//     conflict-free (the thread -> tile list interleaves the slots' 16-byte bank groups);
-//   * no per-vector list entry, address arithmetic or thermal-mass load in the sweeps;
+// Here a thread owns one or two HALF-TILES of 2 x 4 control volumes for the whole solve:
+//   * their temperatures and thermal-mass terms n3 = (cm * T_prev) / dt live in registers from
+//     the first sweep to the last; no centre / n3 loads, no list entries, no address arithmetic
+//     in the sweeps;
+//   * per sweep a half-tile publishes its two rows and its left / right columns (three float4
+//     in double-buffered exchange arrays) and reads the facing rows / columns of its four
+//     neighbours (four float4): 7 x 128-bit shared-memory accesses per 8 CVs, all conflict-free
+//     (the schedule interleaves the slots' 16-byte bank groups), none of them the 4-way
+//     conflicted scalar neighbour loads of the vector kernels;
 //   * sums that consume packed PRODUCTS are packed too: ptxas contracts add.rn.f32x2 of a
 //     mul.rn.f32x2 result into FFMA2 (one rounding instead of two, even with --fmad=false), so the
 //     sum is written fma.rn.f32x2(x, ONE, y) with ONE = 1.0f read from the kernel parameters -- a
@@ -23,19 +23,27 @@
 //   * zone sums come straight from the registers (exact fixed point, integer REDUX per warp,
 //     32-bit shared-memory atomics on split lo / hi words), no zone-sum list.
 //
-// Tiles are of two kinds, fixed per plan (k_prepare_plan3):
-//   PURE  16 interior air CVs of one zone, no diffuser: uniform coefficients in registers;
-//   GEN   everything else (walls, diffusers, boundary ring, exterior space): every horizontal
-//         PAIR of CVs carries a pattern id into a per-building table of pair coefficients
-//         (the 30-entry (class, material) table of the solve header, interleaved for two CVs),
-//         so the general update (tf_simulator.py:719-754 incl. convection terms, half cells and
-//         the exterior override) also runs on packed pairs, branch-free.
-// Threads are sorted PURE first, then GEN, so warps do not diverge except one per building.
+// Half-tiles are of three kinds, fixed per plan (k_prepare_plan3):
+//   PURE  8 interior air CVs of one zone, no diffuser: uniform coefficients in registers;
+//   MED   8 interior-class CVs of any material, diffusers allowed: per-PAIR coefficients from the
+//         9-entry material-pair table of the solve header (two 128-bit loads per pair);
+//   SLOW  everything else (boundary ring, exterior space): every horizontal pair of CVs carries
+//         a pattern id into a per-building table of pair coefficients (the 30-entry
+//         (class, material) table of the header interleaved for two CVs), so the general update
+//         (tf_simulator.py:719-754 incl. convection terms, half cells and the exterior
+//         override) also runs on packed pairs, branch-free.
+// A sweep lasts as long as its slowest warp, so the schedule balances COST, not count: the
+// half-tiles are sorted by cost; thread t takes the t-th most expensive one, and the cheapest
+// n_b = (half-tiles - threads) -- PURE ones -- go as SECOND half-tiles to the threads whose
+// first one is cheapest.  With 448 threads for the 768 half-tiles of a 64x96 grid the boundary
+// threads carry one SLOW half-tile (~190 issue slots per sweep), the others MED + PURE or
+// PURE + PURE (~200).  Kinds are contiguous in thread order: warps diverge only where two
+// kinds meet.
 //
 // Arithmetic contract unchanged: every fp32 operation of tf_simulator.py:719-754 is one IEEE
 // rounding in the reference's order; bit-exact against the oracle (tests/test_gpu_parity.py).
 //
-// Scope: grids with H % 4 == 0, W % 4 == 0 and at most kR3MaxThreads tiles (64x96: 384), TF-Jacobi
+// Scope: grids with H % 2 == 0, W % 4 == 0 and at most 2 * kR3MaxThreads half-tiles, TF-Jacobi
 // solver, no stochastic convection (those handles run k_resident_step).
 #pragma once
 
@@ -43,42 +51,60 @@
 
 namespace sbx {
 
-constexpr int kR3MaxThreads = 384;
+#ifndef SBX_R3_MAX_THREADS
+#define SBX_R3_MAX_THREADS 448
+#endif
+constexpr int kR3MaxThreads = SBX_R3_MAX_THREADS;
 constexpr int kR3PatCap = 64;
-enum { kR3Pure = 0, kR3Gen = 1, kR3Idle = 3 };
-constexpr uint32_t kEntSlotMask = 0x3FFu;
-constexpr int kEntKindShift = 10, kEntFlagShift = 12, kEntZoneShift = 16;
-constexpr uint32_t kEntHeat = 1u << 24;
+constexpr int kR3PatStride = 7;      // float4 per pattern entry (28 words: distinct patterns -> distinct 16-byte bank groups)
+enum { kR3Pure = 0, kR3Med = 1, kR3Slow = 2, kR3Idle = 3 };
+constexpr uint32_t kEntSlotMask = 0xFFFu;
+constexpr int kEntKindShift = 12, kEntFlagShift = 14, kEntZoneShift = 18;
+constexpr uint32_t kEntHeat = 1u << 26;
 constexpr uint32_t kNbUp = 1u, kNbDown = 2u, kNbLeft = 4u, kNbRight = 8u;
 // counts3[plan*4 + i]
-enum { kC3Pure = 0, kC3Gen = 1, kC3Pat = 2, kC3Capable = 3 };
+enum { kC3Pat = 2, kC3Capable = 3 };
+// exchange arrays of one buffer
+enum { kXRow0 = 0, kXRow1 = 1, kXCol = 2, kXArrays = 3 };
+
+__host__ inline int resident3_threads(int H, int W) {
+  const int n_half = (H / 2) * (W / 4);
+  int nt = ((n_half * 7 + 11) / 12 + 31) & ~31;          // 7/12 of the half-tiles: 448 for 64x96
+  if (const char* e = getenv("SBX_R3_THREADS")) nt = (atoi(e) + 31) & ~31;
+  const int lo = ((n_half + 1) / 2 + 31) & ~31;
+  if (nt < lo) nt = lo;
+  if (nt > n_half) nt = (n_half + 31) & ~31;
+  return nt;
+}
 
 __host__ inline bool resident3_supported(int H, int W) {
-  if (H % 4 != 0 || W % 4 != 0 || H < 8 || W < 8) return false;
-  const int th = H / 4, tw = W / 4;
+  if (H % 2 != 0 || W % 4 != 0 || H < 4 || W < 8) return false;
+  const int hh = H / 2, tw = W / 4;
   const int Tq = (tw % 2 == 0) ? tw + 1 : tw;
-  return th * tw <= kR3MaxThreads && th * Tq <= (int)kEntSlotMask;
+  const int nt = resident3_threads(H, W);
+  return nt <= kR3MaxThreads && nt >= kR3PatCap * 6 && 2 * nt >= hh * tw && hh * Tq <= (int)kEntSlotMask;
 }
 
 __host__ inline Resident3Geom resident3_geom(int H, int W, int Z) {
   Resident3Geom g;
-  g.th = H / 4;
+  g.hh = H / 2;
   g.tw = W / 4;
   g.Tq = (g.tw % 2 == 0) ? g.tw + 1 : g.tw;
-  g.nt = (g.th * g.tw + 31) & ~31;
+  g.nt = resident3_threads(H, W);
   g.tq_magic = 0xFFFFFFFFu / (unsigned)g.Tq + 1u;
   g.pat_cap = kR3PatCap;
   auto al = [](size_t v) { return (int)((v + 15) & ~(size_t)15); };
   auto al128 = [](size_t v) { return (int)((v + 127) & ~(size_t)127); };
-  g.xarr = al128((size_t)g.th * g.Tq * 16);
+  g.xarr = al128((size_t)g.hh * g.Tq * 16);
   size_t o = 0;
-  g.off_x0 = (int)o; o = al128(o + (size_t)4 * g.xarr);
+  g.off_x0 = (int)o; o = al128(o + (size_t)kXArrays * g.xarr);
   // the input / output plane of the TMA copies aliases the second exchange buffer
-  const size_t x1 = (size_t)4 * g.xarr, plane = (size_t)H * W * 4;
+  const size_t x1 = (size_t)kXArrays * g.xarr, plane = (size_t)H * W * 4;
   g.off_x1 = (int)o; o = al128(o + (x1 > plane ? x1 : plane));
   g.off_hdr = (int)o; o = al(o + header_bytes(Z));
-  g.off_ptab = (int)o; o = al(o + (size_t)kR3PatCap * 96);
+  g.off_ptab = (int)o; o = al(o + (size_t)kR3PatCap * kR3PatStride * 16);
   g.off_bins = (int)o; o = al(o + (size_t)(Z + 1) * 8);
+  g.off_zparts = (int)o; o = al(o + (size_t)g.nt * 8);
   g.off_misc = (int)o; o = al(o + 32);
   g.off_bar = (int)o; o = al(o + 16);
   g.total = (int)o;
@@ -86,8 +112,9 @@ __host__ inline Resident3Geom resident3_geom(int H, int W, int Z) {
 }
 
 // ---------------------------------------------------------------------------
-// Once per uploaded plan: classify the tiles, number the pair patterns, sort the tiles into the
-// thread order.  One CTA per plan; positions by counting smaller keys (deterministic).
+// Once per uploaded plan: classify the half-tiles, number the pair patterns, build the
+// cost-balanced thread schedule.  One CTA per plan; positions by counting smaller keys
+// (deterministic).
 // ---------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t r3_zone_slot(uint32_t d, int Z) {
   if (desc_class(d) == SBX_CV_EXTERIOR) return 0xFFu;       // T == T_inf == the sums' reference: contributes 0
@@ -96,53 +123,59 @@ __device__ __forceinline__ uint32_t r3_zone_slot(uint32_t d, int Z) {
 }
 
 __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan3(const Params p) {
-  __shared__ uint32_t key[kR3MaxThreads];
-  __shared__ uint32_t key1[kR3MaxThreads];
-  __shared__ uint32_t bitmap[32];     // pair pattern a * 32 + b present
+  __shared__ uint32_t key[2 * kR3MaxThreads];
+  __shared__ uint32_t key1[2 * kR3MaxThreads];
+  __shared__ uint32_t bitmap[32];     // pair pattern a * 32 + b present (SLOW half-tiles)
   __shared__ uint32_t prefix[33];
-  __shared__ int s_bad, s_npure, s_ngen;
+  __shared__ int s_bad, s_cnt[3];      // half-tiles per kind rank: SLOW, MED, PURE
   const int plan = blockIdx.x, tid = threadIdx.x;
   const Resident3Geom& g = p.g3;
-  const int W = p.W, Z = p.Z, n_tiles = g.th * g.tw;
+  const int W = p.W, Z = p.Z, n_half = g.hh * g.tw;
   const uint16_t* raw = p.desc + (size_t)plan * p.H * W;
-  uint32_t* ent = p.ent3 + (size_t)plan * g.nt;
-  uint4* ga = p.gen3a + (size_t)plan * g.nt;
-  uint4* gb = p.gen3b + (size_t)plan * g.nt;
-  uint4* gq = p.gen3q + (size_t)plan * g.nt;
+  uint32_t* ent = p.ent3 + (size_t)plan * 2 * g.nt;
+  uint4* rec = p.rec3 + (size_t)plan * 2 * g.nt;
+  uint2* recz = p.recz3 + (size_t)plan * 2 * g.nt;
   uint16_t* pat = p.pat3 + (size_t)plan * g.pat_cap;
   if (tid < 32) bitmap[tid] = 0;
-  if (tid == 0) { s_bad = 0; s_npure = 0; s_ngen = 0; }
+  if (tid == 0) s_bad = 0;
   __syncthreads();
-  auto cv = [&](int it, int e) -> uint32_t {          // descriptor of CV e = 4 * row + col of tile it
-    const int tr = it / g.tw, tc = it - tr * g.tw;
-    return raw[(tr * 4 + (e >> 2)) * W + tc * 4 + (e & 3)];
+  auto cv = [&](int it, int e) -> uint32_t {          // descriptor of CV e = 4 * row + col of half-tile it
+    const int hr = it / g.tw, tc = it - hr * g.tw;
+    return raw[(hr * 2 + (e >> 2)) * W + tc * 4 + (e & 3)];
   };
-  // ---- kinds, groups, pattern bitmap ----
-  for (int it = tid; it < n_tiles; it += kPrepThreads) {
-    const int tr = it / g.tw, tc = it - tr * g.tw;
-    bool pure = true;
+  auto kind_of = [&](int it, uint32_t& group) -> int {
+    const int hr = it / g.tw, tc = it - hr * g.tw;
+    bool pure = true, interior = true, heat = false;
     const uint32_t z0 = r3_zone_slot(cv(it, 0), Z);
     uint32_t hsh = 0;
-    for (int e = 0; e < 16; ++e) {
+    for (int e = 0; e < 8; ++e) {
       const uint32_t d = cv(it, e);
       pure = pure && ((d & 0x007Fu) == kFastDesc) && r3_zone_slot(d, Z) == z0;
+      interior = interior && desc_class(d) == SBX_CV_INTERIOR;
+      heat = heat || (d & SBX_DESC_DIFFUSER);
       hsh = hsh * 31u + (uint32_t)combo_index(d);
     }
-    pure = pure && tr > 0 && tr < g.th - 1 && tc > 0 && tc < g.tw - 1;
-    bool heat = false;
-    if (!pure)
-      for (int e = 0; e < 16; e += 2) {
+    // interior-class CVs have all four neighbours inside the grid by construction
+    const bool inner = hr > 0 && hr < g.hh - 1 && tc > 0 && tc < g.tw - 1;
+    const int kind = (pure && inner) ? kR3Pure : (interior && inner) ? kR3Med : kR3Slow;
+    // PURE: by zone (zone sums of a warp in one REDUX); others: half-tiles with heat input first
+    // (the heat lookup is a per-thread branch), similar pattern sets next to each other
+    group = kind == kR3Pure ? z0 : ((heat ? 0u : 256u) | ((hsh ^ (hsh >> 7) ^ (hsh >> 13)) & 255u));
+    return kind;
+  };
+  // ---- kinds, groups, pattern bitmap ----
+  for (int it = tid; it < n_half; it += kPrepThreads) {
+    const int hr = it / g.tw, tc = it - hr * g.tw;
+    uint32_t group;
+    const int kind = kind_of(it, group);
+    if (kind == kR3Slow)
+      for (int e = 0; e < 8; e += 2) {
         const uint32_t k = (uint32_t)combo_index(cv(it, e)) * 32u + (uint32_t)combo_index(cv(it, e + 1));
         atomicOr(&bitmap[k >> 5], 1u << (k & 31u));
-        heat = heat || ((cv(it, e) | cv(it, e + 1)) & SBX_DESC_DIFFUSER);
       }
-    const int kind = pure ? kR3Pure : kR3Gen;
-    // GEN tiles: those with heat input last (the heat lookup is a per-thread branch), similar
-    // pattern sets next to each other (table reads of a warp then mostly broadcast)
-    const uint32_t group = pure ? z0 : ((heat ? 16u : 0u) | ((hsh ^ (hsh >> 7) ^ (hsh >> 13)) & 15u));
-    const int slot = tr * g.Tq + tc;
-    key1[it] = ((uint32_t)kind << 11) | (group << 3) | (uint32_t)(slot & 7);
-    atomicAdd(pure ? &s_npure : &s_ngen, 1);
+    const uint32_t ord = kind == kR3Slow ? 0u : kind == kR3Med ? 1u : 2u;      // most expensive first
+    const int slot = hr * g.Tq + tc;
+    key1[it] = (ord << 12) | (group << 3) | (uint32_t)(slot & 7);
   }
   __syncthreads();
   if (tid == 0) {
@@ -150,13 +183,22 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan3(const Params p) 
     for (int w = 0; w < 32; ++w) { prefix[w] = o; o += (uint32_t)__popc(bitmap[w]); }
     prefix[32] = o;
     if ((int)o > g.pat_cap || (int)o * 6 > g.nt) s_bad = 1;      // the kernel builds the table one item per thread
+    // Thread blocks per kind, each padded to whole warps (a warp that mixes two kinds runs
+    // both code paths): [SLOW | MED | PURE first half-tiles]; the remaining PURE half-tiles are
+    // SECOND half-tiles of the last threads (the kernel keeps no record for second ones).
+    int n[3] = {0, 0, 0};
+    for (int it = 0; it < n_half; ++it) ++n[key1[it] >> 12];
+    const int pad_s = (n[0] + 31) & ~31, pad_m = (n[1] + 31) & ~31;
+    const int n_a = g.nt - pad_s - pad_m;              // PURE first half-tiles
+    if (n_a < 0 || n[2] - n_a > g.nt) s_bad = 1;
+    s_cnt[0] = n[0]; s_cnt[1] = n[1]; s_cnt[2] = n[2];
   }
   // rank inside the (kind, group, residue) bucket
-  for (int it = tid; it < n_tiles; it += kPrepThreads) {
+  for (int it = tid; it < n_half; it += kPrepThreads) {
     const uint32_t k1 = key1[it];
     uint32_t m = 0;
     for (int j = 0; j < it; ++j) m += (key1[j] == k1) ? 1u : 0u;
-    key[it] = ((k1 >> 3) << 13) | (m << 3) | (k1 & 7u);          // kind | group | rank | residue
+    key[it] = ((k1 >> 3) << 14) | (m << 3) | (k1 & 7u);          // kind | group | rank | residue
   }
   __syncthreads();
   const int n_pat = (int)prefix[32];
@@ -166,28 +208,48 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan3(const Params p) 
   if (!s_bad)
     for (int k = tid; k < 1024; k += kPrepThreads)
       if (bitmap[k >> 5] & (1u << (k & 31))) pat[pat_id((uint32_t)k)] = (uint16_t)((k >> 5) | ((k & 31) << 8));
-  // ---- thread order and records ----
-  for (int it = tid; it < n_tiles; it += kPrepThreads) {
+  // ---- schedule and records ----
+  for (int i = tid; i < 2 * g.nt; i += kPrepThreads) ent[i] = (uint32_t)kR3Idle << kEntKindShift;
+  __syncthreads();
+  if (s_bad) {
+    if (tid == 0) p.counts3[(size_t)plan * 4 + kC3Capable] = 0;
+    return;
+  }
+  for (int it = tid; it < n_half; it += kPrepThreads) {
     const uint32_t k2 = key[it];
     int pos = 0;
-    for (int j = 0; j < n_tiles; ++j) pos += (key[j] < k2) ? 1 : 0;
-    const int tr = it / g.tw, tc = it - tr * g.tw;
-    const int kind = (int)(key1[it] >> 11);
-    const uint32_t flags = (tr > 0 ? kNbUp : 0u) | (tr < g.th - 1 ? kNbDown : 0u) | (tc > 0 ? kNbLeft : 0u) |
+    for (int j = 0; j < n_half; ++j) pos += (key[j] < k2) ? 1 : 0;
+    int idx;
+    {
+      const int n_s = s_cnt[0], n_m = s_cnt[1], n_p = s_cnt[2];
+      const int pad_s = (n_s + 31) & ~31, pad_m = (n_m + 31) & ~31;
+      const int n_a = g.nt - pad_s - pad_m, n_b = n_p - n_a;
+      if (pos < n_s) idx = pos;
+      else if (pos < n_s + n_m) idx = pad_s + (pos - n_s);
+      else if (pos - n_s - n_m < n_a) idx = pad_s + pad_m + (pos - n_s - n_m);
+      else idx = g.nt + (g.nt - n_b) + (pos - n_s - n_m - n_a);          // second half-tile of thread nt - n_b + j
+    }
+    const int hr = it / g.tw, tc = it - hr * g.tw;
+    uint32_t group;
+    const int kind = kind_of(it, group);
+    const uint32_t flags = (hr > 0 ? kNbUp : 0u) | (hr < g.hh - 1 ? kNbDown : 0u) | (tc > 0 ? kNbLeft : 0u) |
                            (tc < g.tw - 1 ? kNbRight : 0u);
-    uint32_t e = (uint32_t)(tr * g.Tq + tc) | ((uint32_t)kind << kEntKindShift) | (flags << kEntFlagShift);
+    uint32_t e = (uint32_t)(hr * g.Tq + tc) | ((uint32_t)kind << kEntKindShift) | (flags << kEntFlagShift);
     if (kind == kR3Pure) {
       e |= r3_zone_slot(cv(it, 0), Z) << kEntZoneShift;
     } else {
-      uint32_t pats[2] = {0u, 0u}, qs[4] = {0u, 0u, 0u, 0u};
-      uint32_t zs[6] = {0u, 0u, 0u, 0u, 0u, 0u}, zm[6] = {0u, 0u, 0u, 0u, 0u, 0u};   // four rooms + walls meet in one tile
+      uint32_t pats = 0u, qs[2] = {0u, 0u};
+      uint32_t zs[4] = {0u, 0u, 0u, 0u}, zm[4] = {0u, 0u, 0u, 0u};
       int np = 0;
       bool heat = false, bad = false;
-      for (int e2 = 0; e2 < 16; ++e2) {
+      for (int e2 = 0; e2 < 8; ++e2) {
         const uint32_t d = cv(it, e2);
         if ((e2 & 1) == 0) {
-          const uint32_t k = (uint32_t)combo_index(d) * 32u + (uint32_t)combo_index(cv(it, e2 + 1));
-          pats[e2 >> 3] |= (s_bad ? 0u : pat_id(k)) << (8 * ((e2 >> 1) & 3));
+          const uint32_t d1 = cv(it, e2 + 1);
+          uint32_t id;
+          if (kind == kR3Med) id = (uint32_t)(desc_material(d) * kNumMaterials + desc_material(d1));
+          else id = s_bad ? 0u : pat_id((uint32_t)combo_index(d) * 32u + (uint32_t)combo_index(d1));
+          pats |= id << (8 * (e2 >> 1));
         }
         const bool dq = (d & SBX_DESC_DIFFUSER) != 0;
         heat = heat || dq;
@@ -197,7 +259,7 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan3(const Params p) 
           int k = 0;
           while (k < np && zs[k] != z) ++k;
           if (k == np) {
-            if (np == 6) { bad = true; continue; }
+            if (np == 4) { bad = true; continue; }
             zs[np++] = z;
           }
           zm[k] |= 1u << e2;
@@ -206,18 +268,17 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan3(const Params p) 
       if (bad) atomicExch(&s_bad, 1);
       if (heat) e |= kEntHeat;
       e |= (uint32_t)np << kEntZoneShift;
-      ga[pos] = make_uint4(pats[0], pats[1], zs[0] | (zm[0] << 16), zs[1] | (zm[1] << 16));
-      gb[pos] = make_uint4(zs[2] | (zm[2] << 16), zs[3] | (zm[3] << 16), zs[4] | (zm[4] << 16), zs[5] | (zm[5] << 16));
-      gq[pos] = make_uint4(qs[0], qs[1], qs[2], qs[3]);
+      rec[idx] = make_uint4(pats, qs[0], qs[1], 0u);
+      recz[idx] = make_uint2((zs[0] | (zm[0] << 8)) | ((zs[1] | (zm[1] << 8)) << 16),
+                             (zs[2] | (zm[2] << 8)) | ((zs[3] | (zm[3] << 8)) << 16));
     }
-    ent[pos] = e;
+    ent[idx] = e;
   }
-  for (int i = n_tiles + tid; i < g.nt; i += kPrepThreads) ent[i] = (uint32_t)kR3Idle << kEntKindShift;
   __syncthreads();
   if (tid == 0) {
     int32_t* c = p.counts3 + (size_t)plan * 4;
-    c[kC3Pure] = s_npure;
-    c[kC3Gen] = s_ngen;
+    c[0] = 0;
+    c[1] = 0;
     c[kC3Pat] = n_pat;
     c[kC3Capable] = s_bad ? 0 : 1;
   }
@@ -229,6 +290,26 @@ __global__ void __launch_bounds__(kPrepThreads) k_prepare_plan3(const Params p) 
 struct PureCoef {
   f32x2 kq, vz, nden, rden, one;
 };
+// One half-tile: temperatures (2 rows x 4), thermal-mass terms (4 pairs), static description
+struct Half {
+  float4 t0, t1;
+  f32x2 n3[4];
+  uint32_t ent;
+};
+// static description of a non-PURE half-tile (first half-tiles only: second ones are PURE)
+struct HalfRec {
+  uint32_t pats, q0, q1;     // pair patterns, heat slots of row 0 / row 1
+};
+// shared-memory context of a sweep
+struct R3Ctx {
+  const float4* Xr;           // exchange buffer read by this sweep
+  float4* Xw;                 // ... written
+  const float4* ptab;         // SLOW pair patterns
+  const unsigned char* mtab;  // MED material pairs (header)
+  const float* qcv;           // heat per diffuser CV of each zone
+  int Tq, xq;
+  float t_inf;
+};
 
 __device__ __forceinline__ float absmax2(float lmax, f32x2 d) {
   float a, b;
@@ -236,7 +317,13 @@ __device__ __forceinline__ float absmax2(float lmax, f32x2 d) {
   return fmaxf(fmaxf(lmax, fabsf(a)), fabsf(b));
 }
 
-// One row of a PURE tile.  pu / pc / pd: kq * T of the row above, of this row, of the row
+__device__ __forceinline__ void publish_half(float4* X, const int xq, const int s, const float4 t0, const float4 t1) {
+  X[kXRow0 * xq + s] = t0;
+  X[kXRow1 * xq + s] = t1;
+  X[kXCol * xq + s] = make_float4(t0.x, t1.x, t0.w, t1.w);        // left column | right column
+}
+
+// One row of a PURE half-tile.  pu / pc / pd: kq * T of the row above, of this row, of the row
 // below (pairs of columns 0-1 and 2-3); pl / pr: kq * T of the left / right neighbour CV.
 // Same operations, same order as cv_update_fast / fast_core4.
 __device__ __forceinline__ float pure_row(float4& t, const f32x2 pua, const f32x2 pub, const f32x2 pca,
@@ -261,38 +348,49 @@ __device__ __forceinline__ float pure_row(float4& t, const f32x2 pua, const f32x
   return lmax;
 }
 
-__device__ __forceinline__ float pure_sweep(float4 (&T)[4], const f32x2 (&n3)[8], const float4* __restrict__ Xr,
-                                            const int s, const int Tq, const int xq, const PureCoef& c) {
-  const float4 U = Xr[xq + s - Tq];          // bottom row of the tile above
-  const float4 D = Xr[s + Tq];               // top row of the tile below
-  const float4 L = Xr[3 * xq + s - 1];       // right column of the tile to the left
-  const float4 R = Xr[2 * xq + s + 1];       // left column of the tile to the right
-  float pl[4], pr[4];
-  unpack2(mul2(c.kq, pack2(L.x, L.y)), pl[0], pl[1]);
-  unpack2(mul2(c.kq, pack2(L.z, L.w)), pl[2], pl[3]);
-  unpack2(mul2(c.kq, pack2(R.x, R.y)), pr[0], pr[1]);
-  unpack2(mul2(c.kq, pack2(R.z, R.w)), pr[2], pr[3]);
-  f32x2 pua = mul2(c.kq, pack2(U.x, U.y)), pub = mul2(c.kq, pack2(U.z, U.w));
-  f32x2 pca = mul2(c.kq, pack2(T[0].x, T[0].y)), pcb = mul2(c.kq, pack2(T[0].z, T[0].w));
-  float lmax = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 dn = i < 3 ? T[i + 1] : D;
-    const f32x2 pda = mul2(c.kq, pack2(dn.x, dn.y)), pdb = mul2(c.kq, pack2(dn.z, dn.w));
-    lmax = pure_row(T[i], pua, pub, pca, pcb, pda, pdb, pl[i], pr[i], n3[2 * i], n3[2 * i + 1], c, lmax);
-    pua = pca; pub = pcb;
-    pca = pda; pcb = pdb;
-  }
+__device__ __forceinline__ float pure_half(Half& h, const R3Ctx& x, const PureCoef& c, float lmax) {
+  const int s = (int)(h.ent & kEntSlotMask), xq = x.xq;
+  const float4 U = x.Xr[kXRow1 * xq + s - x.Tq];      // bottom row of the half-tile above
+  const float4 D = x.Xr[kXRow0 * xq + s + x.Tq];      // top row of the one below
+  const float4 CL = x.Xr[kXCol * xq + s - 1];         // .zw: right column of the left neighbour
+  const float4 CR = x.Xr[kXCol * xq + s + 1];         // .xy: left column of the right neighbour
+  float pl0, pl1, pr0, pr1;
+  unpack2(mul2(c.kq, pack2(CL.z, CL.w)), pl0, pl1);
+  unpack2(mul2(c.kq, pack2(CR.x, CR.y)), pr0, pr1);
+  const f32x2 pua = mul2(c.kq, pack2(U.x, U.y)), pub = mul2(c.kq, pack2(U.z, U.w));
+  const f32x2 p0a = mul2(c.kq, pack2(h.t0.x, h.t0.y)), p0b = mul2(c.kq, pack2(h.t0.z, h.t0.w));
+  const f32x2 p1a = mul2(c.kq, pack2(h.t1.x, h.t1.y)), p1b = mul2(c.kq, pack2(h.t1.z, h.t1.w));
+  const f32x2 pda = mul2(c.kq, pack2(D.x, D.y)), pdb = mul2(c.kq, pack2(D.z, D.w));
+  lmax = pure_row(h.t0, pua, pub, p0a, p0b, p1a, p1b, pl0, pr0, h.n3[0], h.n3[1], c, lmax);
+  lmax = pure_row(h.t1, p0a, p0b, p1a, p1b, pda, pdb, pl1, pr1, h.n3[2], h.n3[3], c, lmax);
+  publish_half(x.Xw, xq, s, h.t0, h.t1);
   return lmax;
 }
 
-// One horizontal pair of CVs of a GEN tile (cv_update_packed on two CVs at once): coefficient
-// pairs from the pattern table entry `e` (6 x float4, see the table build in the kernel).
-//   tjp / tjm: T(i,j+1) / T(i,j-1) of the two CVs, tip / tim: T(i+1,j) / T(i-1,j)
-__device__ __forceinline__ f32x2 gen_pair(const float4* __restrict__ e, const f32x2 tjp, const f32x2 tjm,
+// MED pair: two interior-class CVs of any material (tf_simulator.py:719-754 with
+// k1 = k2 = k3 = k4 = k/dx of the CV's OWN material, no convection terms: x + 0 == x).
+// `e`: entry of the header's material-pair table {kq_a, kq_b, -den_a, -den_b | 1/den_a, 1/den_b, cm_a, cm_b}
+__device__ __forceinline__ f32x2 med_pair(const unsigned char* __restrict__ e, const f32x2 tjp, const f32x2 tjm,
                                           const f32x2 tip, const f32x2 tim, const f32x2 n3, const f32x2 q,
-                                          const bool heat, const f32x2 one, const uint32_t tinf_bits) {
-  const float4 k13 = e[0], k24 = e[1], hhv = e[2], den = e[3], vu = e[4], cme = e[5];
+                                          const bool heat, const PureCoef& c) {
+  const float4 a0 = *reinterpret_cast<const float4*>(e);
+  const float2 a1 = *reinterpret_cast<const float2*>(e + 16);
+  const f32x2 kq = pack2(a0.x, a0.y);
+  const f32x2 n1 = mul2(c.vz, fma2(mul2(kq, tjp), c.one, mul2(kq, tjm)));
+  const f32x2 n2 = mul2(c.vz, fma2(mul2(kq, tip), c.one, mul2(kq, tim)));
+  f32x2 num = add2(fma2(n1, c.one, n2), n3);
+  if (heat) num = add2(num, q);                                                            // :754
+  return div_rn2(num, pack2(a0.z, a0.w), pack2(a1.x, a1.y));
+}
+
+// SLOW pair (cv_update_packed on two CVs at once): coefficient pairs from the pattern table
+// entry `e` (see the table build in the kernel).
+//   tjp / tjm: T(i,j+1) / T(i,j-1) of the two CVs, tip / tim: T(i+1,j) / T(i-1,j)
+__device__ __forceinline__ f32x2 slow_pair(const float4* __restrict__ e, const f32x2 tjp, const f32x2 tjm,
+                                           const f32x2 tip, const f32x2 tim, const f32x2 n3, const f32x2 q,
+                                           const bool heat, const f32x2 one, const uint32_t tinf_bits) {
+  const float4 k13 = e[0], k24 = e[1], hhv = e[2], den = e[3], vu = e[4];
+  const float2 em = *reinterpret_cast<const float2*>(&e[5].z);
   f32x2 n1 = fma2(mul2(pack2(k13.x, k13.y), tjp), one, mul2(pack2(k13.z, k13.w), tjm));   // :719-720, 731
   n1 = add2(n1, pack2(hhv.x, hhv.y));                                                      // :732-733
   n1 = mul2(pack2(vu.x, vu.y), n1);                                                        // :734
@@ -305,51 +403,98 @@ __device__ __forceinline__ f32x2 gen_pair(const float4* __restrict__ e, const f3
   // exterior space: T = T_inf (:847-849); the masks are all ones there
   float o0, o1;
   unpack2(o, o0, o1);
-  const uint32_t m0 = __float_as_uint(cme.z), m1 = __float_as_uint(cme.w);
+  const uint32_t m0 = __float_as_uint(em.x), m1 = __float_as_uint(em.y);
   o0 = __uint_as_float((__float_as_uint(o0) & ~m0) | (tinf_bits & m0));
   o1 = __uint_as_float((__float_as_uint(o1) & ~m1) | (tinf_bits & m1));
   return pack2(o0, o1);
 }
 
-__device__ __forceinline__ float gen_sweep(float4 (&T)[4], const f32x2 (&n3)[8], const float4* __restrict__ Xr,
-                                           const int s, const int Tq, const int xq, const uint32_t flags,
-                                           const uint32_t pat_lo, const uint32_t pat_hi, const bool heat,
-                                           const uint4 gq, const float* __restrict__ qcv,
-                                           const float4* __restrict__ ptab, const f32x2 one, const float t_inf) {
+template <int KIND>
+__device__ __forceinline__ float general_half(Half& h, const HalfRec& rec, const R3Ctx& x, const PureCoef& c,
+                                              float lmax) {
+  const int s = (int)(h.ent & kEntSlotMask), xq = x.xq;
+  const uint32_t flags = (h.ent >> kEntFlagShift) & 15u;
+  const bool heat = (h.ent & kEntHeat) != 0u;
+  const float t_inf = x.t_inf;
   const float4 inf4 = make_float4(t_inf, t_inf, t_inf, t_inf);
-  const float4 U = (flags & kNbUp) ? Xr[xq + s - Tq] : inf4;         // tf_simulator.py:642-644
-  const float4 D = (flags & kNbDown) ? Xr[s + Tq] : inf4;            // :646
-  const float4 L = (flags & kNbLeft) ? Xr[3 * xq + s - 1] : inf4;    // :638-640
-  const float4 R = (flags & kNbRight) ? Xr[2 * xq + s + 1] : inf4;   // :636
-  const float lf[4] = {L.x, L.y, L.z, L.w}, rf[4] = {R.x, R.y, R.z, R.w};
-  const uint32_t qw[4] = {gq.x, gq.y, gq.z, gq.w};
-  const uint32_t tinf_bits = __float_as_uint(t_inf);
-  float4 up = U;
-  float lmax = 0.f;
-#pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const float4 cur = T[i];
-    const float4 dn = i < 3 ? T[i + 1] : D;
-    const uint32_t pw = i < 2 ? pat_lo : pat_hi;
-    const uint32_t pa = (pw >> (16 * (i & 1))) & 0xFFu, pb = (pw >> (16 * (i & 1) + 8)) & 0xFFu;
-    f32x2 qa = 0ull, qb = 0ull;
-    if (heat) {
-      const uint32_t w = qw[i];
-      qa = pack2(qcv[w & 0xFFu], qcv[(w >> 8) & 0xFFu]);
-      qb = pack2(qcv[(w >> 16) & 0xFFu], qcv[w >> 24]);
-    }
-    const f32x2 mid = pack2(cur.y, cur.z);
-    const f32x2 oa = gen_pair(ptab + pa * 6, mid, pack2(lf[i], cur.x), pack2(dn.x, dn.y), pack2(up.x, up.y),
-                              n3[2 * i], qa, heat, one, tinf_bits);
-    const f32x2 ob = gen_pair(ptab + pb * 6, pack2(cur.w, rf[i]), mid, pack2(dn.z, dn.w), pack2(up.z, up.w),
-                              n3[2 * i + 1], qb, heat, one, tinf_bits);
-    lmax = absmax2(lmax, sub2(oa, pack2(cur.x, cur.y)));               // :851-853
-    lmax = absmax2(lmax, sub2(ob, pack2(cur.z, cur.w)));
-    unpack2(oa, T[i].x, T[i].y);
-    unpack2(ob, T[i].z, T[i].w);
-    up = cur;
+  float4 U, D, CL, CR;
+  if (KIND == kR3Med) {             // interior-class CVs: every neighbour exists
+    U = x.Xr[kXRow1 * xq + s - x.Tq];
+    D = x.Xr[kXRow0 * xq + s + x.Tq];
+    CL = x.Xr[kXCol * xq + s - 1];
+    CR = x.Xr[kXCol * xq + s + 1];
+  } else {
+    U = (flags & kNbUp) ? x.Xr[kXRow1 * xq + s - x.Tq] : inf4;          // tf_simulator.py:642-644
+    D = (flags & kNbDown) ? x.Xr[kXRow0 * xq + s + x.Tq] : inf4;        // :646
+    CL = (flags & kNbLeft) ? x.Xr[kXCol * xq + s - 1] : inf4;           // :638-640
+    CR = (flags & kNbRight) ? x.Xr[kXCol * xq + s + 1] : inf4;          // :636
   }
+  const uint32_t tinf_bits = __float_as_uint(t_inf);
+  const float4 r0 = h.t0, r1 = h.t1;
+  const uint32_t pats = rec.pats;
+  f32x2 q[4] = {0ull, 0ull, 0ull, 0ull};
+  if (heat) {
+    const uint32_t w0 = rec.q0, w1 = rec.q1;
+    q[0] = pack2(x.qcv[w0 & 0xFFu], x.qcv[(w0 >> 8) & 0xFFu]);
+    q[1] = pack2(x.qcv[(w0 >> 16) & 0xFFu], x.qcv[w0 >> 24]);
+    q[2] = pack2(x.qcv[w1 & 0xFFu], x.qcv[(w1 >> 8) & 0xFFu]);
+    q[3] = pack2(x.qcv[(w1 >> 16) & 0xFFu], x.qcv[w1 >> 24]);
+  }
+  auto pair = [&](const int j, const f32x2 tjp, const f32x2 tjm, const f32x2 tip, const f32x2 tim) -> f32x2 {
+    const uint32_t id = (pats >> (8 * j)) & 0xFFu;
+    if (KIND == kR3Med) return med_pair(x.mtab + id * 32u, tjp, tjm, tip, tim, h.n3[j], q[j], heat, c);
+    return slow_pair(x.ptab + id * kR3PatStride, tjp, tjm, tip, tim, h.n3[j], q[j], heat, c.one, tinf_bits);
+  };
+  const f32x2 mid0 = pack2(r0.y, r0.z), mid1 = pack2(r1.y, r1.z);
+  const f32x2 o0a = pair(0, mid0, pack2(CL.z, r0.x), pack2(r1.x, r1.y), pack2(U.x, U.y));
+  const f32x2 o0b = pair(1, pack2(r0.w, CR.x), mid0, pack2(r1.z, r1.w), pack2(U.z, U.w));
+  const f32x2 o1a = pair(2, mid1, pack2(CL.w, r1.x), pack2(D.x, D.y), pack2(r0.x, r0.y));
+  const f32x2 o1b = pair(3, pack2(r1.w, CR.y), mid1, pack2(D.z, D.w), pack2(r0.z, r0.w));
+  lmax = absmax2(lmax, sub2(o0a, pack2(r0.x, r0.y)));               // :851-853
+  lmax = absmax2(lmax, sub2(o0b, pack2(r0.z, r0.w)));
+  lmax = absmax2(lmax, sub2(o1a, pack2(r1.x, r1.y)));
+  lmax = absmax2(lmax, sub2(o1b, pack2(r1.z, r1.w)));
+  unpack2(o0a, h.t0.x, h.t0.y);
+  unpack2(o0b, h.t0.z, h.t0.w);
+  unpack2(o1a, h.t1.x, h.t1.y);
+  unpack2(o1b, h.t1.z, h.t1.w);
+  publish_half(x.Xw, xq, s, h.t0, h.t1);
   return lmax;
+}
+
+__device__ __forceinline__ float sweep_half(Half& h, const HalfRec& rec, const R3Ctx& x, const PureCoef& c,
+                                            float lmax) {
+  const int kind = (int)((h.ent >> kEntKindShift) & 3u);
+  if (kind == kR3Pure) return pure_half(h, x, c, lmax);
+  if (kind == kR3Med) return general_half<kR3Med>(h, rec, x, c, lmax);
+  if (kind == kR3Slow) return general_half<kR3Slow>(h, rec, x, c, lmax);
+  return lmax;
+}
+
+// n3 = (cm * T_prev) / dt (tf_simulator.py:743-749), kept for every sweep of this step
+__device__ __forceinline__ void init_half(Half& h, const uint32_t pats, const R3Ctx& x, const float cm_air,
+                                          const float dt) {
+  const int kind = (int)((h.ent >> kEntKindShift) & 3u);
+  const float rdt = __frcp_rn(dt);
+  const f32x2 ndt2 = pack2(-dt, -dt), rdt2 = pack2(rdt, rdt);
+  f32x2 cm[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    const uint32_t id = (pats >> (8 * j)) & 0xFFu;
+    if (kind == kR3Med) {
+      const float2 v = *reinterpret_cast<const float2*>(x.mtab + id * 32u + 24);
+      cm[j] = pack2(v.x, v.y);
+    } else if (kind == kR3Slow) {
+      const float2 v = *reinterpret_cast<const float2*>(&x.ptab[id * kR3PatStride + 5]);
+      cm[j] = pack2(v.x, v.y);
+    } else {
+      cm[j] = pack2(cm_air, cm_air);
+    }
+  }
+  h.n3[0] = div_rn2(mul2(cm[0], pack2(h.t0.x, h.t0.y)), ndt2, rdt2);
+  h.n3[1] = div_rn2(mul2(cm[1], pack2(h.t0.z, h.t0.w)), ndt2, rdt2);
+  h.n3[2] = div_rn2(mul2(cm[2], pack2(h.t1.x, h.t1.y)), ndt2, rdt2);
+  h.n3[3] = div_rn2(mul2(cm[3], pack2(h.t1.z, h.t1.w)), ndt2, rdt2);
 }
 
 // exact segmented warp sum: lanes with the same `slot` add their `v`; one lane per slot
@@ -357,6 +502,15 @@ __device__ __forceinline__ float gen_sweep(float4 (&T)[4], const f32x2 (&n3)[8],
 __device__ __forceinline__ void r3_zone_add(uint32_t* bins, int Z, const int slot, const int v, const bool valid,
                                             const int lane) {
   unsigned todo = __ballot_sync(0xffffffffu, valid);
+  if (todo == 0xffffffffu && __all_sync(0xffffffffu, slot == __shfl_sync(0xffffffffu, slot, 0))) {
+    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)v & 0xFFFFu);      // the common warp: one zone
+    const int hi = __reduce_add_sync(0xffffffffu, v >> 16);
+    if (lane == 0) {
+      atomicAdd(&bins[slot], lo);
+      atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + slot]), hi);
+    }
+    return;
+  }
   while (todo) {
     const int leader = __ffs(todo) - 1;
     const int z = __shfl_sync(0xffffffffu, slot, leader);
@@ -374,6 +528,39 @@ __device__ __forceinline__ void r3_zone_add(uint32_t* bins, int Z, const int slo
   }
 }
 
+// round((T - ref) * 2^16) of the 8 CVs of a half-tile: fma(T, 2^16, -ref * 2^16) is exact (to_fix32)
+__device__ __forceinline__ void fix_half(const Half& h, const f32x2 scale2, const f32x2 nref2, int (&f)[8]) {
+  float a[8];
+  unpack2(fma2(pack2(h.t0.x, h.t0.y), scale2, nref2), a[0], a[1]);
+  unpack2(fma2(pack2(h.t0.z, h.t0.w), scale2, nref2), a[2], a[3]);
+  unpack2(fma2(pack2(h.t1.x, h.t1.y), scale2, nref2), a[4], a[5]);
+  unpack2(fma2(pack2(h.t1.z, h.t1.w), scale2, nref2), a[6], a[7]);
+#pragma unroll
+  for (int e = 0; e < 8; ++e) f[e] = __float2int_rn(a[e]);
+}
+
+// zone sums of one half-tile slot of the warp: PURE half-tiles by REDUX (one zone per warp in
+// the common case), the others -- zones scattered over the warp -- by direct atomics
+__device__ __forceinline__ void zone_sums_half(const Half& h, const int (&f)[8], const int total, uint32_t* bins,
+                                               const int Z, const uint2* recz_g, const int lane) {
+  const int kind = (int)((h.ent >> kEntKindShift) & 3u);
+  const int zone = (int)((h.ent >> kEntZoneShift) & 0xFFu);
+  r3_zone_add(bins, Z, zone, total, kind == kR3Pure, lane);
+  if (kind == kR3Med || kind == kR3Slow) {
+    const int np = zone;
+    const uint2 pz = *recz_g;
+    for (int k2 = 0; k2 < np; ++k2) {
+      const uint32_t part = (k2 < 2 ? pz.x >> (16 * k2) : pz.y >> (16 * (k2 - 2))) & 0xFFFFu;
+      int sv = 0;
+#pragma unroll
+      for (int e = 0; e < 8; ++e) sv += (part & (0x100u << e)) ? f[e] : 0;
+      const int z = (int)(part & 0xFFu);
+      atomicAdd(&bins[z], (unsigned)sv & 0xFFFFu);
+      atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + z]), sv >> 16);
+    }
+  }
+}
+
 __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
@@ -381,9 +568,7 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
   const int b = p.b_begin + blockIdx.x;
   const int plan = p.n_plans == 1 ? 0 : b;
   const int Z = p.Z, W = p.W, n_cv = p.H * W;
-  const int Tq = G.Tq, xq = G.xarr / 16;
-  float4* X0 = reinterpret_cast<float4*>(smem + G.off_x0);
-  float4* X1 = reinterpret_cast<float4*>(smem + G.off_x1);
+  const int nt = G.nt;
   float* plane = reinterpret_cast<float*>(smem + G.off_x1);
   const Combo* tab = reinterpret_cast<const Combo*>(smem + G.off_hdr);
   const float* qcv = reinterpret_cast<const float*>(smem + G.off_hdr + sizeof(Combo) * kNumCombos);
@@ -408,18 +593,23 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     tma_load_1d(smem + G.off_hdr, p.hdr + (size_t)b * hdr_bytes, hdr_bytes, bar);
     misc[0] = 0u;
   }
-  const uint32_t ent = __ldg(p.ent3 + (size_t)plan * G.nt + tid);
-  const int4 cnt = __ldg(reinterpret_cast<const int4*>(p.counts3) + plan);     // n_pure, n_gen, n_pat, capable
-  const int n_pat = cnt.z;
-  const int kind = (int)((ent >> kEntKindShift) & 3u);
-  const bool heat = (ent & kEntHeat) != 0u;
+  const uint32_t* g_ent = p.ent3 + (size_t)plan * 2 * nt;
+  const uint4* g_rec = p.rec3 + (size_t)plan * 2 * nt;
+  Half ha, hb;
+  ha.ent = __ldg(g_ent + tid);
+  hb.ent = __ldg(g_ent + nt + tid);
+  const int n_pat = __ldg(p.counts3 + (size_t)plan * 4 + kC3Pat);
   // this thread's item of the pattern table build (stage 1): the pattern's two combo indices
   const int pt_i = tid / 6, pt_j = tid - pt_i * 6;
   const uint32_t pt_pr = pt_i < G.pat_cap ? (uint32_t)__ldg(p.pat3 + (size_t)plan * G.pat_cap + pt_i) : 0u;
-  uint4 ga = make_uint4(0u, 0u, 0u, 0u), gq = make_uint4(0u, 0u, 0u, 0u);
-  if (kind == kR3Gen) {
-    ga = __ldg(p.gen3a + (size_t)plan * G.nt + tid);
-    if (heat) gq = __ldg(p.gen3q + (size_t)plan * G.nt + tid);
+  const int kind_a = (int)((ha.ent >> kEntKindShift) & 3u), kind_b = (int)((hb.ent >> kEntKindShift) & 3u);
+  HalfRec ra;
+  ra.pats = ra.q0 = ra.q1 = 0u;
+  if (kind_a == kR3Med || kind_a == kR3Slow) {
+    const uint4 r = __ldg(g_rec + tid);
+    ra.pats = r.x; ra.q0 = r.y; ra.q1 = r.z;
+    // zone parts: only needed after the sweeps -- parked in shared memory, not in registers
+    reinterpret_cast<uint2*>(smem + G.off_zparts)[tid] = __ldg(p.recz3 + (size_t)plan * 2 * nt + tid);
   }
   // The CTA that takes over this SM slot works on building b + (CTAs in flight): pull its
   // inputs into L2 now
@@ -428,19 +618,21 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     l2_prefetch(p.tbuf[0] + (size_t)bn * n_cv, (uint32_t)(n_cv * 4));
     l2_prefetch(p.hdr + (size_t)bn * hdr_bytes, hdr_bytes & ~15u);
     if (p.n_plans != 1) {
-      l2_prefetch(p.ent3 + (size_t)bn * G.nt, (uint32_t)(G.nt * 4));
-      // (this plan's list sizes stand in for the next one's: a prefetch hint)
-      if (cnt.y > 0) l2_prefetch(p.gen3a + (size_t)bn * G.nt + cnt.x, (uint32_t)(cnt.y * 16));
+      l2_prefetch(p.ent3 + (size_t)bn * 2 * nt, (uint32_t)(2 * nt * 4));
+      l2_prefetch(p.rec3 + (size_t)bn * 2 * nt, (uint32_t)(nt / 2 * 16));     // the most expensive half-tiles come first
+      l2_prefetch(p.pat3 + (size_t)bn * G.pat_cap, (uint32_t)(G.pat_cap * 2));
+      l2_prefetch(p.counts3 + (size_t)bn * 4, 16u);
     }
   }
-  for (int i = tid; i < 2 * (Z + 1); i += (int)blockDim.x) bins[i] = 0u;
+  if (tid < 2 * (Z + 1)) bins[tid] = 0u;                       // Z <= 254, nt >= 384
+  if (tid + nt < 2 * (Z + 1)) bins[tid + nt] = 0u;
   __syncthreads();
   mbar_wait(bar, 0);
   SBX_PHASE(0);   // launch .. bulk loads and per-thread list entries have arrived
   const float t_inf = scal[0];
 
   // ---- stage 1: pair-pattern table of this building (coefficients change with h and T_inf) ----
-  if (pt_i < n_pat) {        // kR3PatCap * 6 <= kR3MaxThreads: one item per thread
+  if (pt_i < n_pat) {        // kR3PatCap * 6 <= nt: one item per thread
     const int ia = (int)(pt_pr & 0xFFu), ib = (int)(pt_pr >> 8);
     const Combo& ca = tab[ia];
     const Combo& cb = tab[ib];
@@ -452,84 +644,75 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     else if (pt_j == 4) v = make_float4(ca.vz, cb.vz, ca.uz, cb.uz);
     else v = make_float4(ca.cm, cb.cm, __uint_as_float(ia < kNumMaterials ? 0xFFFFFFFFu : 0u),
                          __uint_as_float(ib < kNumMaterials ? 0xFFFFFFFFu : 0u));
-    ptab[tid] = v;
+    ptab[pt_i * kR3PatStride + pt_j] = v;
   }
 
-  // ---- stage 2: the thread's tile -> registers, rim -> exchange buffer 0 ----
-  const int s = (int)(ent & kEntSlotMask);
-  const int tr = (int)__umulhi((unsigned)s, G.tq_magic);
-  const int tc = s - tr * Tq;
-  const uint32_t flags = (ent >> kEntFlagShift) & 15u;
-  float* tile = plane + (tr * 4) * W + tc * 4;
-  float4 T[4];
-  f32x2 n3[8];
+  // ---- stage 2: the thread's half-tiles -> registers, their rims -> exchange buffer 0 ----
+  R3Ctx x;
+  x.Tq = G.Tq;
+  x.xq = G.xarr / 16;
+  x.ptab = ptab;
+  x.mtab = smem + G.off_hdr + header_pair_offset(Z);
+  x.qcv = qcv;
+  x.t_inf = t_inf;
+  float4* X0 = reinterpret_cast<float4*>(smem + G.off_x0);
+  float4* X1 = reinterpret_cast<float4*>(smem + G.off_x1);
   PureCoef pc;
-  const float one = p.one;
-  pc.one = pack2(one, one);
   {
+    // Uniform coefficients of (interior, air).  The warp-wide maximum of a value every lane
+    // holds is that value -- and it comes back in a UNIFORM register (CREDUX), which the packed
+    // arithmetic takes as a broadcast operand: no vector registers spent on constants.
+    const float one = p.one;
+    pc.one = pack2(one, one);
     const Combo& c = tab[SBX_CV_INTERIOR * kNumMaterials + 0];
-    pc.kq = pack2(c.k1, c.k1); pc.vz = pack2(c.vz, c.vz);
-    pc.nden = pack2(-c.den, -c.den); pc.rden = pack2(c.rden, c.rden);
+    const float kq = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(c.k1)));
+    const float vz = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(c.vz)));
+    const float den = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(c.den)));
+    const float rden = __uint_as_float(__reduce_max_sync(0xffffffffu, __float_as_uint(c.rden)));
+    pc.kq = pack2(kq, kq); pc.vz = pack2(vz, vz);
+    pc.nden = pack2(-den, -den); pc.rden = pack2(rden, rden);
   }
-  if (kind != kR3Idle) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) T[i] = *reinterpret_cast<const float4*>(tile + i * W);
-  } else {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) T[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  __syncthreads();      // the pattern table is complete (and every thread has its tile: the plane is free)
-  SBX_PHASE(1);   // pattern table, tile -> registers
-  {
-    // n3 = (cm * T_prev) / dt (tf_simulator.py:743-749), kept for every sweep of this step
-    const float rdt = __frcp_rn(p.dt);
-    const f32x2 ndt2 = pack2(-p.dt, -p.dt), rdt2 = pack2(rdt, rdt);
-    if (kind == kR3Gen) {
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        const uint32_t pw = i < 2 ? ga.x : ga.y;
-        const uint32_t pa = (pw >> (16 * (i & 1))) & 0xFFu, pb = (pw >> (16 * (i & 1) + 8)) & 0xFFu;
-        const float4 ea = ptab[pa * 6 + 5], eb = ptab[pb * 6 + 5];
-        n3[2 * i] = div_rn2(mul2(pack2(ea.x, ea.y), pack2(T[i].x, T[i].y)), ndt2, rdt2);
-        n3[2 * i + 1] = div_rn2(mul2(pack2(eb.x, eb.y), pack2(T[i].z, T[i].w)), ndt2, rdt2);
-      }
-    } else {
-      const float cmf = tab[SBX_CV_INTERIOR * kNumMaterials + 0].cm;
-      const f32x2 cm2 = pack2(cmf, cmf);
-#pragma unroll
-      for (int i = 0; i < 4; ++i) {
-        n3[2 * i] = div_rn2(mul2(cm2, pack2(T[i].x, T[i].y)), ndt2, rdt2);
-        n3[2 * i + 1] = div_rn2(mul2(cm2, pack2(T[i].z, T[i].w)), ndt2, rdt2);
-      }
-    }
-  }
-  auto publish = [&](float4* X) {
-    X[s] = T[0];
-    X[xq + s] = T[3];
-    X[2 * xq + s] = make_float4(T[0].x, T[1].x, T[2].x, T[3].x);
-    X[3 * xq + s] = make_float4(T[0].w, T[1].w, T[2].w, T[3].w);
+  auto half_ptr = [&](const Half& h) -> float* {
+    const int s = (int)(h.ent & kEntSlotMask);
+    const int hr = (int)__umulhi((unsigned)s, G.tq_magic);
+    return plane + (hr * 2) * W + (s - hr * G.Tq) * 4;
   };
-  if (kind != kR3Idle) publish(X0);
+  const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
+  ha.t0 = ha.t1 = hb.t0 = hb.t1 = zero4;
+  if (kind_a != kR3Idle) {
+    const float* q = half_ptr(ha);
+    ha.t0 = *reinterpret_cast<const float4*>(q);
+    ha.t1 = *reinterpret_cast<const float4*>(q + W);
+  }
+  if (kind_b != kR3Idle) {
+    const float* q = half_ptr(hb);
+    hb.t0 = *reinterpret_cast<const float4*>(q);
+    hb.t1 = *reinterpret_cast<const float4*>(q + W);
+  }
+  if (kind_a != kR3Idle) publish_half(X0, x.xq, (int)(ha.ent & kEntSlotMask), ha.t0, ha.t1);
+  if (kind_b != kR3Idle) publish_half(X0, x.xq, (int)(hb.ent & kEntSlotMask), hb.t0, hb.t1);
+  // one barrier: the pattern table is complete, every rim is in exchange buffer 0, and every
+  // thread has its half-tiles (the plane, which aliases exchange buffer 1, is free)
   __syncthreads();
-  SBX_PHASE(2);   // thermal-mass terms, first rim exchange
+  SBX_PHASE(1);   // pattern table, half-tiles -> registers, first rim exchange
+  {
+    const float cm_air = tab[SBX_CV_INTERIOR * kNumMaterials + 0].cm;
+    init_half(ha, ra.pats, x, cm_air, p.dt);
+    init_half(hb, 0u, x, cm_air, p.dt);
+  }
+  SBX_PHASE(2);   // thermal-mass terms
 
   // ---- stage 3: Jacobi sweeps to convergence (simulator.py:348-364) ----
   const int limit = p.iteration_limit;
   const float thr = p.threshold;
-  float4* Xr = X0;
-  float4* Xw = X1;
+  x.Xr = X0;
+  x.Xw = X1;
   int k = 0;
   float lmax = 0.f;
   while (k < limit) {
     ++k;
-    lmax = 0.f;
-    if (kind == kR3Pure) {
-      lmax = pure_sweep(T, n3, Xr, s, Tq, xq, pc);
-      publish(Xw);
-    } else if (kind == kR3Gen) {
-      lmax = gen_sweep(T, n3, Xr, s, Tq, xq, flags, ga.x, ga.y, heat, gq, qcv, ptab, pc.one, t_inf);
-      publish(Xw);
-    }
+    lmax = sweep_half(ha, ra, x, pc, 0.f);
+    if (kind_b == kR3Pure) lmax = pure_half(hb, x, pc, lmax);
     // max|dT| <= threshold  <=>  no thread saw a delta above it (simulator.py:362); the
     // barrier doubles as the fence between the two exchange buffers
 #ifdef SBX_PROFILE_PHASES
@@ -542,15 +725,25 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
       p.phase_cycles[8 + (tid >> 5) * 8 + 2 * (k - 1) + 1] = (unsigned long long)(clock64() - cta_t0__);
     }
 #endif
-    float4* tmp = Xr; Xr = Xw; Xw = tmp;
+    {
+      float4* tmp = x.Xw;
+      x.Xw = const_cast<float4*>(x.Xr);
+      x.Xr = tmp;
+    }
     if (k == 1) SBX_PHASE(3); else SBX_PHASE(4);   // first sweep / later sweeps
     if (!above) break;
   }
 
   // ---- stage 4: write back (plane aliases exchange buffer 1: nobody reads it any more) ----
-  if (kind != kR3Idle) {
-#pragma unroll
-    for (int i = 0; i < 4; ++i) *reinterpret_cast<float4*>(tile + i * W) = T[i];
+  if (kind_a != kR3Idle) {
+    float* q = half_ptr(ha);
+    *reinterpret_cast<float4*>(q) = ha.t0;
+    *reinterpret_cast<float4*>(q + W) = ha.t1;
+  }
+  if (kind_b != kR3Idle) {
+    float* q = half_ptr(hb);
+    *reinterpret_cast<float4*>(q) = hb.t0;
+    *reinterpret_cast<float4*>(q + W) = hb.t1;
   }
   tma_store_fence();
   {
@@ -562,53 +755,26 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     const f32x2 scale2 = pack2(kFixScaleF, kFixScaleF);
     const float nref = -__fmul_rn(t_inf, kFixScaleF);
     const f32x2 nref2 = pack2(nref, nref);
-    int f[16];
+    int fa[8], fb[8];
+    fix_half(ha, scale2, nref2, fa);
+    fix_half(hb, scale2, nref2, fb);      // (idle: temperatures 0 -> garbage, never used)
+    int ta = 0, tb = 0;
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      float a0, a1, a2, a3;
-      unpack2(fma2(pack2(T[i].x, T[i].y), scale2, nref2), a0, a1);      // (T - ref) * 2^16, exact (to_fix32)
-      unpack2(fma2(pack2(T[i].z, T[i].w), scale2, nref2), a2, a3);
-      f[4 * i] = __float2int_rn(a0); f[4 * i + 1] = __float2int_rn(a1);
-      f[4 * i + 2] = __float2int_rn(a2); f[4 * i + 3] = __float2int_rn(a3);
-    }
-    int total = 0;
-#pragma unroll
-    for (int e = 0; e < 16; ++e) total += f[e];
-    // whole grid (slot Z): every CV of every tile (exterior space holds T_inf, the reference: 0)
-    const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)total & 0xFFFFu);
-    const int hi = __reduce_add_sync(0xffffffffu, total >> 16);
-    const int zone = (int)((ent >> kEntZoneShift) & 0xFFu);
-    const int zone0 = __shfl_sync(0xffffffffu, zone, 0);
-    if (__all_sync(0xffffffffu, kind == kR3Pure && zone == zone0)) {
-      // the common PURE warp: one zone, the sums are the ones just taken
-      if (lane == 0) {
-        atomicAdd(&bins[Z], lo);
-        atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + Z]), hi);
-        atomicAdd(&bins[zone0], lo);
-        atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + zone0]), hi);
-      }
-    } else {
+    for (int e = 0; e < 8; ++e) { ta += fa[e]; tb += fb[e]; }
+    if (kind_a == kR3Idle) ta = 0;
+    if (kind_b == kR3Idle) tb = 0;
+    // whole grid (slot Z): every CV of every half-tile (exterior space holds T_inf, the reference: 0)
+    {
+      const int total = ta + tb;
+      const unsigned lo = __reduce_add_sync(0xffffffffu, (unsigned)total & 0xFFFFu);
+      const int hi = __reduce_add_sync(0xffffffffu, total >> 16);
       if (lane == 0) {
         atomicAdd(&bins[Z], lo);
         atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + Z]), hi);
       }
-      r3_zone_add(bins, Z, zone, total, kind == kR3Pure, lane);      // PURE lanes of a mixed warp
-      if (kind == kR3Gen) {
-        // GEN tiles: zones are scattered over the warp, so each thread adds its own parts
-        const int np = zone;
-        uint4 gb = make_uint4(0u, 0u, 0u, 0u);
-        if (np > 2) gb = __ldg(p.gen3b + (size_t)plan * G.nt + tid);
-        for (int k2 = 0; k2 < np; ++k2) {
-          const uint32_t part = k2 == 0 ? ga.z : k2 == 1 ? ga.w : k2 == 2 ? gb.x : k2 == 3 ? gb.y : k2 == 4 ? gb.z : gb.w;
-          int sv = 0;
-#pragma unroll
-          for (int e = 0; e < 16; ++e) sv += (part & (0x10000u << e)) ? f[e] : 0;
-          const int z = (int)(part & 0xFFu);
-          atomicAdd(&bins[z], (unsigned)sv & 0xFFFFu);
-          atomicAdd(reinterpret_cast<int*>(&bins[Z + 1 + z]), sv >> 16);
-        }
-      }
     }
+    zone_sums_half(ha, fa, ta, bins, Z, reinterpret_cast<const uint2*>(smem + G.off_zparts) + tid, lane);
+    r3_zone_add(bins, Z, (int)((hb.ent >> kEntZoneShift) & 0xFFu), tb, kind_b == kR3Pure, lane);
   }
   __syncthreads();      // plane complete (TMA store), bins complete
   SBX_PHASE(5);   // write-back to the plane, zone sums

@@ -583,7 +583,7 @@ int run_resident(sbx_handle h, cudaStream_t st, bool with_header) {
   const unsigned grid = (unsigned)(p.b_end - p.b_begin);
   if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
   if (h->use_v3 && !step_has_convection(p)) {
-    k_resident_step3<<<grid, (unsigned)p.g3.nt, p.g3.total, st>>>(p);
+    k_resident_step3<<<grid, (unsigned)p.g3.nt, p.g3.total, st>>>(p, h->tmap_t);
     h->last_resident_kernel = 3;
     if (int rc = launch_check(h, "k_resident_step3")) return rc;
     return timing_record(h, h->t_solve, h->t_solve_used, st);
@@ -861,11 +861,14 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
       }
     }
   }
-  // k_resident_step3: default where the grid allows it (SBX_RESIDENT_V3=0 turns it off)
+  // k_resident_step3 is opt-in (SBX_RESIDENT_V3=1): measured on B200 (32768 x 64x96) it needs 1.06 ms
+  // per launch against 0.96 ms of k_resident_step -- 24 % fewer instructions, but its phases are
+  // short and separated by barriers, and at 72 registers the two half-tiles of a thread cannot be
+  // interleaved, so it issues on 50 % of the cycles where k_resident_step reaches 77 %
   h->v3_capable = 0;
   if (h->path == SBX_PATH_RESIDENT && c.solver == SBX_SOLVER_TF_JACOBI && !h->v2_capable && Z < 255 &&
-      resident3_supported(c.height, c.width) && !(getenv("SBX_RESIDENT_V3") && atoi(getenv("SBX_RESIDENT_V3")) == 0)) {
-    p.g3 = resident3_geom(c.height, c.width, (int)Z);
+      L.use_tmap && resident3_supported(c.height, c.width) && getenv("SBX_RESIDENT_V3") && atoi(getenv("SBX_RESIDENT_V3")) != 0) {
+    p.g3 = resident3_geom(c.height, c.width, (int)Z, L.P);
     if (p.g3.total <= max_optin) {
       cudaError_t e3 = cudaFuncSetAttribute(k_resident_step3, cudaFuncAttributeMaxDynamicSharedMemorySize, p.g3.total);
       int nb3 = 0;

@@ -78,7 +78,8 @@ struct Resident3Geom {
   unsigned tq_magic;   // slot / Tq == umulhi(slot, tq_magic)
   int pat_cap;         // pair patterns per plan
   int xarr;            // bytes of one exchange array (hh * Tq float4, 128 B multiple)
-  int off_x0, off_x1, off_hdr, off_ptab, off_bins, off_zparts, off_misc, off_bar, total;
+  int plane_pitch;     // row pitch (floats) of the TMA-loaded input plane (ResidentGeom::P)
+  int off_x0, off_x1, off_hdr, off_ptab, off_mtab, off_bins, off_zparts, off_misc, off_bar, total;
 };
 
 // Everything a kernel needs; passed by value.
@@ -430,7 +431,13 @@ __device__ __forceinline__ f32x2 div_rn2(f32x2 a, f32x2 nb, f32x2 y) {
 }
 struct FastCoef2 {
   f32x2 kq, vz, nden, rden, cm, ndt, rdt;
+  f32x2 one;     // (1.0f, 1.0f) from Params::one: pair_add below
 };
+// x + y on pairs where x (and possibly y) is a packed PRODUCT.  ptxas contracts
+// add.rn.f32x2(mul.rn.f32x2(..), y) into FFMA2 (one rounding instead of two) even with
+// --fmad=false; written as fma(x, ONE, y) with ONE = 1.0f read from the kernel parameters -- a value
+// the compiler cannot see -- there is nothing to contract or simplify, and RN(x * 1 + y) == RN(x + y).
+__device__ __forceinline__ f32x2 pair_add(f32x2 x, f32x2 one, f32x2 y) { return fma2(x, one, y); }
 
 // Zone / grid sums are accumulated as integers: each temperature enters as
 // round((T - T_ref) * 2^16), T_ref a per-building reference (the ambient

@@ -530,24 +530,14 @@ __device__ __forceinline__ float fast_core4(const float4 c4, const float4 up4, c
   f32x2 n1b = pack2(add(m3, m1), add(mr, m2));
   n1a = mul2(f.vz, n1a);
   n1b = mul2(f.vz, n1b);
-  // vertical: kq*T(i+1) + kq*T(i-1).  ptxas contracts add.rn.f32x2 of a
-  // mul.rn.f32x2 result into FFMA2 (even with --fmad=false; it leaves scalar
-  // add.rn alone), which would drop a rounding: every sum that consumes a packed
-  // PRODUCT is therefore taken with scalar adds on the halves.
-  float a0, a1, a2, a3, b0, b1, b2, b3;
-  unpack2(mul2(f.kq, pack2(dn4.x, dn4.y)), a0, a1);
-  unpack2(mul2(f.kq, pack2(dn4.z, dn4.w)), a2, a3);
-  unpack2(mul2(f.kq, pack2(up4.x, up4.y)), b0, b1);
-  unpack2(mul2(f.kq, pack2(up4.z, up4.w)), b2, b3);
-  const f32x2 n2a = mul2(f.vz, pack2(add(a0, b0), add(a1, b1)));
-  const f32x2 n2b = mul2(f.vz, pack2(add(a2, b2), add(a3, b3)));
-  float p0, p1, p2, p3, q0, q1, q2, q3;
-  unpack2(n1a, p0, p1);
-  unpack2(n1b, p2, p3);
-  unpack2(n2a, q0, q1);
-  unpack2(n2b, q2, q3);
-  const f32x2 suma = pack2(add(p0, q0), add(p1, q1));
-  const f32x2 sumb = pack2(add(p2, q2), add(p3, q3));
+  // vertical: kq*T(i+1) + kq*T(i-1), and n1 + n2: sums of packed PRODUCTS, taken with pair_add
+  // (a plain add.rn.f32x2 would be contracted into FFMA2 and lose a rounding)
+  const f32x2 va = pair_add(mul2(f.kq, pack2(dn4.x, dn4.y)), f.one, mul2(f.kq, pack2(up4.x, up4.y)));
+  const f32x2 vb = pair_add(mul2(f.kq, pack2(dn4.z, dn4.w)), f.one, mul2(f.kq, pack2(up4.z, up4.w)));
+  const f32x2 n2a = mul2(f.vz, va);
+  const f32x2 n2b = mul2(f.vz, vb);
+  const f32x2 suma = pair_add(n1a, f.one, n2a);
+  const f32x2 sumb = pair_add(n1b, f.one, n2b);
   const f32x2 oa = div_rn2(add2(suma, n3a), f.nden, f.rden);
   const f32x2 ob = div_rn2(add2(sumb, n3b), f.nden, f.rden);
   unpack2(oa, o4.x, o4.y);
@@ -906,6 +896,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   sc.fc2.nden = pack2(-sc.fc.den, -sc.fc.den); sc.fc2.rden = pack2(sc.fc.rden, sc.fc.rden);
   sc.fc2.cm = pack2(sc.cm_fast, sc.cm_fast);
   sc.fc2.ndt = pack2(-sc.dt, -sc.dt); sc.fc2.rdt = pack2(sc.rdt, sc.rdt);
+  sc.fc2.one = pack2(p.one, p.one);
   sc.n_items = n_items; sc.H = H; sc.P = P; sc.Pq = L.Pq; sc.wq = W / V; sc.Z = Z;
   sc.pq_magic = L.pq_magic;
 

@@ -531,6 +531,7 @@ __device__ __forceinline__ float resident2_sweep(const float* __restrict__ in, f
       const float rdt = __frcp_rn(p.dt);
       fc2.ndt = pack2(-p.dt, -p.dt);
       fc2.rdt = pack2(rdt, rdt);
+      fc2.one = pack2(p.one, p.one);
     }
     // register-resident HEAD vectors (see HeadVec): the warp's first chunks, full FAST ones
     const int nh = R2_CNT(s, p)[kC2Heads];

@@ -57,6 +57,7 @@ namespace sbx {
 constexpr int kR3MaxThreads = SBX_R3_MAX_THREADS;
 constexpr int kR3PatCap = 64;
 constexpr int kR3PatStride = 7;      // float4 per pattern entry (28 words: distinct patterns -> distinct 16-byte bank groups)
+constexpr int kR3MedStride = 48;     // bytes per material-pair entry (3 bank groups: the 9 entries do not collide)
 enum { kR3Pure = 0, kR3Med = 1, kR3Slow = 2, kR3Idle = 3 };
 constexpr uint32_t kEntSlotMask = 0xFFFu;
 constexpr int kEntKindShift = 12, kEntFlagShift = 14, kEntZoneShift = 18;
@@ -85,7 +86,7 @@ __host__ inline bool resident3_supported(int H, int W) {
   return nt <= kR3MaxThreads && nt >= kR3PatCap * 6 && 2 * nt >= hh * tw && hh * Tq <= (int)kEntSlotMask;
 }
 
-__host__ inline Resident3Geom resident3_geom(int H, int W, int Z) {
+__host__ inline Resident3Geom resident3_geom(int H, int W, int Z, int plane_pitch) {
   Resident3Geom g;
   g.hh = H / 2;
   g.tw = W / 4;
@@ -98,11 +99,14 @@ __host__ inline Resident3Geom resident3_geom(int H, int W, int Z) {
   g.xarr = al128((size_t)g.hh * g.Tq * 16);
   size_t o = 0;
   g.off_x0 = (int)o; o = al128(o + (size_t)kXArrays * g.xarr);
-  // the input / output plane of the TMA copies aliases the second exchange buffer
-  const size_t x1 = (size_t)kXArrays * g.xarr, plane = (size_t)H * W * 4;
+  // the input plane of the TMA load (rows at the pitch of k_resident_step's tensor map) aliases
+  // the second exchange buffer
+  const size_t x1 = (size_t)kXArrays * g.xarr, plane = (size_t)H * plane_pitch * 4;
   g.off_x1 = (int)o; o = al128(o + (x1 > plane ? x1 : plane));
+  g.plane_pitch = plane_pitch;
   g.off_hdr = (int)o; o = al(o + header_bytes(Z));
   g.off_ptab = (int)o; o = al(o + (size_t)kR3PatCap * kR3PatStride * 16);
+  g.off_mtab = (int)o; o = al(o + (size_t)kNumMaterials * kNumMaterials * kR3MedStride);
   g.off_bins = (int)o; o = al(o + (size_t)(Z + 1) * 8);
   g.off_zparts = (int)o; o = al(o + (size_t)g.nt * 8);
   g.off_misc = (int)o; o = al(o + 32);
@@ -442,7 +446,7 @@ __device__ __forceinline__ float general_half(Half& h, const HalfRec& rec, const
   }
   auto pair = [&](const int j, const f32x2 tjp, const f32x2 tjm, const f32x2 tip, const f32x2 tim) -> f32x2 {
     const uint32_t id = (pats >> (8 * j)) & 0xFFu;
-    if (KIND == kR3Med) return med_pair(x.mtab + id * 32u, tjp, tjm, tip, tim, h.n3[j], q[j], heat, c);
+    if (KIND == kR3Med) return med_pair(x.mtab + id * kR3MedStride, tjp, tjm, tip, tim, h.n3[j], q[j], heat, c);
     return slow_pair(x.ptab + id * kR3PatStride, tjp, tjm, tip, tim, h.n3[j], q[j], heat, c.one, tinf_bits);
   };
   const f32x2 mid0 = pack2(r0.y, r0.z), mid1 = pack2(r1.y, r1.z);
@@ -482,7 +486,7 @@ __device__ __forceinline__ void init_half(Half& h, const uint32_t pats, const R3
   for (int j = 0; j < 4; ++j) {
     const uint32_t id = (pats >> (8 * j)) & 0xFFu;
     if (kind == kR3Med) {
-      const float2 v = *reinterpret_cast<const float2*>(x.mtab + id * 32u + 24);
+      const float2 v = *reinterpret_cast<const float2*>(x.mtab + id * kR3MedStride + 24);
       cm[j] = pack2(v.x, v.y);
     } else if (kind == kR3Slow) {
       const float2 v = *reinterpret_cast<const float2*>(&x.ptab[id * kR3PatStride + 5]);
@@ -561,7 +565,8 @@ __device__ __forceinline__ void zone_sums_half(const Half& h, const int (&f)[8],
   }
 }
 
-__global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Params p) {
+__global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Params p,
+                                                                        const __grid_constant__ CUtensorMap tmap_t) {
   extern __shared__ __align__(128) unsigned char smem[];
   const int tid = threadIdx.x, lane = tid & 31;
   const Resident3Geom& G = p.g3;
@@ -569,7 +574,6 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
   const int plan = p.n_plans == 1 ? 0 : b;
   const int Z = p.Z, W = p.W, n_cv = p.H * W;
   const int nt = G.nt;
-  float* plane = reinterpret_cast<float*>(smem + G.off_x1);
   const Combo* tab = reinterpret_cast<const Combo*>(smem + G.off_hdr);
   const float* qcv = reinterpret_cast<const float*>(smem + G.off_hdr + sizeof(Combo) * kNumCombos);
   const float* scal = qcv + header_q_slots(Z);
@@ -585,11 +589,13 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
   const long long cta_t0__ = phase_t0__;
 #endif
 
-  // ---- stage 0: bulk loads (plane + header), static per-thread data straight from global ----
+  // ---- stage 0: bulk loads (plane + header); the schedule straight from global, every load
+  // independent of the others (one L2 round trip) ----
+  float* plane = reinterpret_cast<float*>(smem + G.off_x1);
   if (tid == 0) {
     mbar_init(bar, 1);
-    mbar_expect_tx(bar, (uint32_t)(n_cv * 4) + hdr_bytes);
-    tma_load_1d(plane, gT, (uint32_t)(n_cv * 4), bar);
+    mbar_expect_tx(bar, (uint32_t)(p.H * G.plane_pitch * 4) + hdr_bytes);
+    tma_load_plane(plane, &tmap_t, b, bar);
     tma_load_1d(smem + G.off_hdr, p.hdr + (size_t)b * hdr_bytes, hdr_bytes, bar);
     misc[0] = 0u;
   }
@@ -603,13 +609,27 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
   const int pt_i = tid / 6, pt_j = tid - pt_i * 6;
   const uint32_t pt_pr = pt_i < G.pat_cap ? (uint32_t)__ldg(p.pat3 + (size_t)plan * G.pat_cap + pt_i) : 0u;
   const int kind_a = (int)((ha.ent >> kEntKindShift) & 3u), kind_b = (int)((hb.ent >> kEntKindShift) & 3u);
+  // records of the non-PURE half-tiles: those threads come first, so the first nt/2 load theirs
+  // without waiting for the schedule entry (a PURE thread in that range reads a stale record it
+  // never uses)
   HalfRec ra;
   ra.pats = ra.q0 = ra.q1 = 0u;
-  if (kind_a == kR3Med || kind_a == kR3Slow) {
-    const uint4 r = __ldg(g_rec + tid);
-    ra.pats = r.x; ra.q0 = r.y; ra.q1 = r.z;
+  const bool eager = tid < nt / 2;
+  uint4 r4 = make_uint4(0u, 0u, 0u, 0u);
+  uint2 z2 = make_uint2(0u, 0u);
+  if (eager) {
+    r4 = __ldg(g_rec + tid);
+    z2 = __ldg(p.recz3 + (size_t)plan * 2 * nt + tid);
+  }
+  const bool general_a = kind_a == kR3Med || kind_a == kR3Slow;
+  if (general_a && !eager) {
+    r4 = __ldg(g_rec + tid);
+    z2 = __ldg(p.recz3 + (size_t)plan * 2 * nt + tid);
+  }
+  if (general_a) {
+    ra.pats = r4.x; ra.q0 = r4.y; ra.q1 = r4.z;
     // zone parts: only needed after the sweeps -- parked in shared memory, not in registers
-    reinterpret_cast<uint2*>(smem + G.off_zparts)[tid] = __ldg(p.recz3 + (size_t)plan * 2 * nt + tid);
+    reinterpret_cast<uint2*>(smem + G.off_zparts)[tid] = z2;
   }
   // The CTA that takes over this SM slot works on building b + (CTAs in flight): pull its
   // inputs into L2 now
@@ -646,13 +666,18 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
                          __uint_as_float(ib < kNumMaterials ? 0xFFFFFFFFu : 0u));
     ptab[pt_i * kR3PatStride + pt_j] = v;
   }
+  if (tid >= nt - 2 * kNumMaterials * kNumMaterials) {      // material-pair table at a conflict-free stride
+    const int j = nt - 1 - tid;
+    *reinterpret_cast<float4*>(smem + G.off_mtab + (j >> 1) * kR3MedStride + (j & 1) * 16) =
+        *reinterpret_cast<const float4*>(smem + G.off_hdr + header_pair_offset(Z) + j * 16);
+  }
 
   // ---- stage 2: the thread's half-tiles -> registers, their rims -> exchange buffer 0 ----
   R3Ctx x;
   x.Tq = G.Tq;
   x.xq = G.xarr / 16;
   x.ptab = ptab;
-  x.mtab = smem + G.off_hdr + header_pair_offset(Z);
+  x.mtab = smem + G.off_mtab;
   x.qcv = qcv;
   x.t_inf = t_inf;
   float4* X0 = reinterpret_cast<float4*>(smem + G.off_x0);
@@ -672,27 +697,27 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     pc.kq = pack2(kq, kq); pc.vz = pack2(vz, vz);
     pc.nden = pack2(-den, -den); pc.rden = pack2(rden, rden);
   }
-  auto half_ptr = [&](const Half& h) -> float* {
+  auto half_offset = [&](const Half& h, const int pitch) -> int {
     const int s = (int)(h.ent & kEntSlotMask);
     const int hr = (int)__umulhi((unsigned)s, G.tq_magic);
-    return plane + (hr * 2) * W + (s - hr * G.Tq) * 4;
+    return (hr * 2) * pitch + (s - hr * G.Tq) * 4;
   };
   const float4 zero4 = make_float4(0.f, 0.f, 0.f, 0.f);
   ha.t0 = ha.t1 = hb.t0 = hb.t1 = zero4;
   if (kind_a != kR3Idle) {
-    const float* q = half_ptr(ha);
+    const float* q = plane + half_offset(ha, G.plane_pitch);
     ha.t0 = *reinterpret_cast<const float4*>(q);
-    ha.t1 = *reinterpret_cast<const float4*>(q + W);
+    ha.t1 = *reinterpret_cast<const float4*>(q + G.plane_pitch);
   }
   if (kind_b != kR3Idle) {
-    const float* q = half_ptr(hb);
+    const float* q = plane + half_offset(hb, G.plane_pitch);
     hb.t0 = *reinterpret_cast<const float4*>(q);
-    hb.t1 = *reinterpret_cast<const float4*>(q + W);
+    hb.t1 = *reinterpret_cast<const float4*>(q + G.plane_pitch);
   }
   if (kind_a != kR3Idle) publish_half(X0, x.xq, (int)(ha.ent & kEntSlotMask), ha.t0, ha.t1);
   if (kind_b != kR3Idle) publish_half(X0, x.xq, (int)(hb.ent & kEntSlotMask), hb.t0, hb.t1);
-  // one barrier: the pattern table is complete, every rim is in exchange buffer 0, and every
-  // thread has its half-tiles (the plane, which aliases exchange buffer 1, is free)
+  // one barrier: every thread has its half-tiles (the plane, which aliases exchange buffer 1, is
+  // free), the coefficient tables are complete and every rim is in exchange buffer 0
   __syncthreads();
   SBX_PHASE(1);   // pattern table, half-tiles -> registers, first rim exchange
   {
@@ -734,18 +759,17 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     if (!above) break;
   }
 
-  // ---- stage 4: write back (plane aliases exchange buffer 1: nobody reads it any more) ----
+  // ---- stage 4: write back, straight from the registers ----
   if (kind_a != kR3Idle) {
-    float* q = half_ptr(ha);
+    float* q = gT + half_offset(ha, W);
     *reinterpret_cast<float4*>(q) = ha.t0;
     *reinterpret_cast<float4*>(q + W) = ha.t1;
   }
   if (kind_b != kR3Idle) {
-    float* q = half_ptr(hb);
+    float* q = gT + half_offset(hb, W);
     *reinterpret_cast<float4*>(q) = hb.t0;
     *reinterpret_cast<float4*>(q + W) = hb.t1;
   }
-  tma_store_fence();
   {
     const uint32_t wm = __reduce_max_sync(0xffffffffu, __float_as_uint(lmax));
     if (lane == 0) atomicMax(&misc[0], wm);
@@ -776,12 +800,8 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     zone_sums_half(ha, fa, ta, bins, Z, reinterpret_cast<const uint2*>(smem + G.off_zparts) + tid, lane);
     r3_zone_add(bins, Z, (int)((hb.ent >> kEntZoneShift) & 0xFFu), tb, kind_b == kR3Pure, lane);
   }
-  __syncthreads();      // plane complete (TMA store), bins complete
-  SBX_PHASE(5);   // write-back to the plane, zone sums
-  if (tid == 0) {
-    tma_store_1d(gT, plane, (uint32_t)(n_cv * 4));
-    tma_store_commit();
-  }
+  __syncthreads();      // bins complete
+  SBX_PHASE(5);   // write-back, zone sums
   if (tid < 32) {
     if (sums) {
       long long* zs = p.zone_sum + (size_t)b * (Z + 1);
@@ -795,10 +815,9 @@ __global__ void __launch_bounds__(kR3MaxThreads, 2) k_resident_step3(const Param
     if (lane == 0) {
       p.n_sweeps[b] = k;
       p.max_delta[b] = __uint_as_float(misc[0]);
-      tma_store_wait();
     }
   }
-  SBX_PHASE(6);   // results out, TMA store drained
+  SBX_PHASE(6);   // results out
 }
 
 }  // namespace sbx

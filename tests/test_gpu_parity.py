@@ -44,16 +44,16 @@ def _dense_q(cp, qcv):
 
 @pytest.fixture(params=["k_resident_step", "k_resident_step2", "k_resident_step3"])
 def resident_kernel(request, monkeypatch):
-  """The resident path has three kernels: k_resident_step3 (register tiles; the default where
-  the grid is a multiple of 4x4 tiles), k_resident_step (SBX_RESIDENT_V3=0, and every other
-  grid) and the record-driven k_resident_step2 (SBX_RESIDENT_V2=1); the switches are read when a
-  handle is created."""
+  """The resident path has three kernels: k_resident_step (the default), the record-driven
+  k_resident_step2 (SBX_RESIDENT_V2=1) and k_resident_step3 (half-tiles in registers,
+  SBX_RESIDENT_V3=1, grids with even height and width a multiple of 4); the switches are read
+  when a handle is created."""
   monkeypatch.delenv("SBX_RESIDENT_V2", raising=False)
   monkeypatch.delenv("SBX_RESIDENT_V3", raising=False)
   if request.param == "k_resident_step2":
     monkeypatch.setenv("SBX_RESIDENT_V2", "1")
-  elif request.param == "k_resident_step":
-    monkeypatch.setenv("SBX_RESIDENT_V3", "0")
+  elif request.param == "k_resident_step3":
+    monkeypatch.setenv("SBX_RESIDENT_V3", "1")
   return request.param
 
 
@@ -137,6 +137,13 @@ def test_fd_step_bit_exact(path, plan_name):
       assert sweeps[0] <= 4
   finally:
     env.close()
+
+
+def test_resident_kernels_solve_only_and_many_rooms(resident_kernel):
+  """sbx_fd_step (no zone sums) on a random 64x96 plan and the plan with several rooms per 4-CV
+  vector, under each resident kernel."""
+  test_fd_step_bit_exact("resident", "rand_64x96")
+  test_many_rooms_per_vector("resident")
 
 
 def _compare_step(env, oracles, ts, B, cp, step, check_temp=True):

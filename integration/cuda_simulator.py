@@ -147,6 +147,27 @@ def upload_plan(handle: "_lib.Handle", plan: floorplan.CompiledPlan) -> None:
 # ---------------------------------------------------------------------------
 
 
+def cuda_fd_timestep(handle: "_lib.Handle", plan: floorplan.CompiledPlan, building, solver: str,
+                     ambient_temperature: float, convection_coefficient: float,
+                     iteration_limit: int, convergence_threshold: float) -> bool:
+  """finite_differences_timestep (simulator.py:318-371) of ONE building on libsbx: uploads
+  `building.temp` and the per-zone diffuser heat of `building.input_q`, solves to convergence,
+  stores the result in `building.temp`; returns the reference's `converged` flag.  `building`
+  only needs the attributes temp / input_q, so this is testable without the reference."""
+  shape = (1, plan.height, plan.width)
+  if solver == "gauss_seidel":
+    handle.upload("temp64", np.ascontiguousarray(building.temp, dtype=np.float64)[None])
+    handle.upload("q_cv64", diffuser_heat_per_zone(building, plan).astype(np.float64))
+  else:
+    handle.upload("temp", np.ascontiguousarray(building.temp, dtype=np.float32)[None])   # tf.convert_to_tensor(.., float32)
+    handle.upload("q_cv", diffuser_heat_per_zone(building, plan))
+  handle.fd_step(np.array([float(ambient_temperature)]), np.array([float(convection_coefficient)]))
+  building.temp = (handle.download("temp64", shape)[0] if solver == "gauss_seidel"
+                   else handle.download("temp", shape)[0])                                # simulator.py:369
+  n = int(handle.download("n_sweeps", (1,))[0])
+  return n < iteration_limit or float(handle.download("max_delta", (1,))[0]) <= convergence_threshold
+
+
 def make_cuda_simulator(solver: str = "tf_jacobi", device: int = 0):
   """Returns class CudaSimulator(SimulatorFlexibleGeometries).  solver='tf_jacobi' reproduces
   TFSimulator.update_temperature_estimates (tf_simulator.py:573-853, fp32 Jacobi),
@@ -170,19 +191,9 @@ def make_cuda_simulator(solver: str = "tf_jacobi", device: int = 0):
 
     def finite_differences_timestep(self, *, ambient_temperature: float,
                                     convection_coefficient: float) -> bool:
-      b, h, plan = self._building, self._sbx, self._sbx_plan
-      if self._sbx_solver == "gauss_seidel":
-        h.upload("temp64", np.ascontiguousarray(b.temp, dtype=np.float64)[None])
-        h.upload("q_cv64", diffuser_heat_per_zone(b, plan).astype(np.float64))
-      else:
-        h.upload("temp", np.ascontiguousarray(b.temp, dtype=np.float32)[None])   # tf.convert_to_tensor(.., float32)
-        h.upload("q_cv", diffuser_heat_per_zone(b, plan))
-      h.fd_step(np.array([float(ambient_temperature)]), np.array([float(convection_coefficient)]))
-      shape = (1, plan.height, plan.width)
-      b.temp = (h.download("temp64", shape)[0] if self._sbx_solver == "gauss_seidel"
-                else h.download("temp", shape)[0])                                   # simulator.py:369
-      n = int(h.download("n_sweeps", (1,))[0])
-      return n < self._iteration_limit or float(h.download("max_delta", (1,))[0]) <= self._convergence_threshold
+      return cuda_fd_timestep(self._sbx, self._sbx_plan, self._building, self._sbx_solver,
+                              ambient_temperature, convection_coefficient, self._iteration_limit,
+                              self._convergence_threshold)
 
   return CudaSimulator
 

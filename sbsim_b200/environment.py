@@ -19,6 +19,8 @@ moves I/O buffers.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import os
+import warnings
 from typing import List, Optional, Sequence, Union
 
 import numpy as np
@@ -139,21 +141,43 @@ class Environment:
                observation_histogram_reducer: Optional[config_lib.HistogramReducer] = None,
                time_zone: str = "US/Pacific",
                step_interval: pd.Timedelta = pd.Timedelta(5, unit="minutes"),
+               writer_factory=None,
+               device_action_tuples=None,
+               metrics_reporting_interval: float = 100,
+               run_command_predictors=None,
+               image_generator=None,
                *,
                device: int = 0,
-               kernel_path: int = _lib.PATH_AUTO):
+               kernel_path: int = _lib.PATH_AUTO,
+               metrics_env_indices: Sequence[int] = (0,)):
     if discount_factor <= 0 or discount_factor > 1:
       raise ValueError("Discount factor must be in (0,1]")   # environment.py:445-446
     if num_hod_features != 1 or num_dow_features != 1:
       raise NotImplementedError("one hod and one dow feature pair, as in sim_config.gin:597-598")
-    if metrics_path is not None:
-      raise NotImplementedError("episode logging (utils/controller_writer.py) is out of scope")
+    # Constructor arguments of the reference (environment.py:355-383) that have no batched
+    # counterpart are accepted, so that a call site written for the reference keeps working, and
+    # reported once: the action set comes from `action_config` (all envs share it), TensorBoard
+    # summaries / run-command predictors / building images are host-side tooling around the path.
+    for name, value in (("device_action_tuples", device_action_tuples),
+                        ("run_command_predictors", run_command_predictors),
+                        ("image_generator", image_generator)):
+      if value:
+        warnings.warn(f"sbsim_b200.Environment ignores {name}", stacklevel=2)
+    del metrics_reporting_interval      # TensorBoard reporting period of the reference: nothing to report to
     self.building = building
     self.reward_function = reward_function
     self.discount_factor = float(discount_factor)
     self._label = label
     self._time_zone = time_zone
-    self._metrics_path = None
+    # Episode logs (environment.py:1181-1198): with `metrics_path`, every reset() opens
+    # <metrics_path>/<label>_<yymmdd_HHMMSS>/ and step() logs the buildings `metrics_env_indices`
+    # in the reference ProtoWriter's shard format (sbsim_b200/episode_writer.py).  `writer_factory`
+    # of the reference produces writers that take protobuf messages; here the records are
+    # serialized directly, so a factory is accepted but only its presence is honoured.
+    self._metrics_path = metrics_path
+    self._writer_factory = writer_factory
+    self._metrics_env_indices = tuple(int(i) for i in metrics_env_indices)
+    self._metrics_writer = None
     self._occupancy_normalization_constant = float(occupancy_normalization_constant)
     self._observation_normalizer = observation_normalizer
     self._observation_histogram_reducer = observation_histogram_reducer
@@ -372,6 +396,7 @@ class Environment:
       raise ValueError(f"ambient table shape {amb.shape} != {(self._cfg.n_weather, T)}")
     h.upload("ambient", amb)
     h.upload("convection", conv)
+    self._ambient_table = amb            # host copies, read by integration/cuda_simulator.py
     sched = b.hvac.schedule
     h.upload("comfort", sched.table(ts))
     soon = pd.Timedelta(60, unit="minute")
@@ -398,6 +423,7 @@ class Environment:
       raise ValueError("occupancy tables shorter than the episode")
     h.upload("occ_reward", occ_r[:T])
     h.upload("occ_obs", occ_o[:T])
+    self._occ_reward_table, self._occ_obs_table = occ_r[:T], occ_o[:T]
     if occ_z is not None:      # per-building count of the zones each plan really has
       h.upload("occ_obs_zone", occ_z[:T])
     self._occupancy_episodes = getattr(self, "_occupancy_episodes", 0) + 1
@@ -490,6 +516,11 @@ class Environment:
     self._step_count = 0
     self._time_index = 0
     self._current_time_step = self._time_step()
+    if self._metrics_path:
+      from sbsim_b200 import episode_writer      # pylint: disable=g-import-not-at-top
+      now = pd.Timestamp.now("UTC")
+      out = os.path.join(self._metrics_path, f"{self._label}_{now:%y%m%d_%H%M%S}")
+      self._metrics_writer = episode_writer.EpisodeWriter(self, out, self._metrics_env_indices)
     return self._current_time_step
 
   def _validate_action(self, action) -> np.ndarray:
@@ -526,6 +557,8 @@ class Environment:
       self._step_count += 1
     self._time_index += 1
     self._current_time_step = self._time_step()
+    if self._metrics_writer is not None:
+      self._metrics_writer.log_step(a, self._current_time_step)
     return self._current_time_step
 
   def _upload_convection(self):

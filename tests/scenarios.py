@@ -148,7 +148,7 @@ def make_oracle(sc: Scenario, cp: Optional[floorplan.CompiledPlan] = None,
 
 def make_env(sc: Scenario, n_envs: int = 1, plans=None, weather=None, initial_temp=None,
              kernel_path: int = sbx.PATH_AUTO, device: int = 0,
-             solver: str = "tf_jacobi") -> sbx.Environment:
+             solver: str = "tf_jacobi", **env_kwargs) -> sbx.Environment:
   plans = plans or sc.compiled()
   schedule = sbx.SetpointSchedule(6, 19, (294, 297), (289, 298), time_zone=sc.schedule_tz)
   weather = weather or sbx.WeatherController(sc.weather_low, sc.weather_high,
@@ -186,7 +186,7 @@ def make_env(sc: Scenario, n_envs: int = 1, plans=None, weather=None, initial_te
       discount_factor=sc.discount, num_days_in_episode=sc.num_days,
       occupancy_normalization_constant=sc.occupancy_norm,
       observation_histogram_reducer=sbx.HistogramReducer(HISTOGRAM) if sc.histogram else None,
-      device=device, kernel_path=kernel_path)
+      device=device, kernel_path=kernel_path, **env_kwargs)
 
 
 def small_plan(h=24, w=34) -> np.ndarray:

@@ -66,9 +66,9 @@ def test_create_fails_loudly_without_cuda_or_with_bad_config():
 
 
 def test_no_oracle_in_product():
-  """Nothing under sbsim_b200/ may import or execute the oracle."""
-  pkg = os.path.join(ROOT, "sbsim_b200")
-  for dirpath, _, files in os.walk(pkg):
+  """Nothing under sbsim_b200/ or integration/ may import or execute the oracle."""
+  walks = [w for pkg in ("sbsim_b200", "integration") for w in os.walk(os.path.join(ROOT, pkg))]
+  for dirpath, _, files in walks:
     for f in files:
       if f.endswith((".py", ".cu", ".cuh", ".h")):
         src = open(os.path.join(dirpath, f)).read()

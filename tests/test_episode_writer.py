@@ -180,3 +180,61 @@ def test_episode_writer_on_the_cuda_environment(tmp_path):
     np.testing.assert_allclose([g[2] for g in got_acts], want, rtol=1e-6)
   finally:
     env.close()
+
+
+@pytest.mark.skipif(not refshim.available(), reason="reference tree not mounted")
+def test_shards_read_back_with_the_reference_proto_reader(tmp_path):
+  """Shards written by ProtoShardWriter are read by the reference's own ProtoReader
+  (utils/controller_reader.py:39-175): file names, record framing and messages."""
+  refshim.install()
+  from smart_buildings.smart_control.utils import controller_reader
+  w = ew.ProtoShardWriter(str(tmp_path))
+  for k in range(3):                        # 09:05, 09:55, 10:45 UTC: two hourly shards
+    ts = TS + k * pd.Timedelta(50, unit="min")
+    w.write(ew.REWARD_INFO_PREFIX, ts, ew.encode_reward_info(
+        ts, ts + DT, ZONES, {"air_handler_id_0": (1200.0 + k, -350.5)}, {"boiler_id_0": (5000.0, 12.5)}))
+    w.write(ew.REWARD_RESPONSE_PREFIX, ts, ew.encode_reward_response(ts, ts + DT, agent_reward_value=-0.25 * k))
+    w.write(ew.OBSERVATION_RESPONSE_FILE_PREFIX, ts, ew.encode_observation_response(ts, OBS))
+    w.write(ew.ACTION_RESPONSE_FILE_PREFIX, ts, ew.encode_action_response(ts, ACTS))
+  reader = controller_reader.ProtoReader(str(tmp_path))
+  naive = TS.tz_localize(None)             # shard serials are wall-clock hours without a zone
+  t0, t1 = naive - pd.Timedelta(1, unit="h"), naive + pd.Timedelta(3, unit="h")
+  infos = reader.read_reward_infos(t0, t1)
+  assert [i.air_handler_reward_infos["air_handler_id_0"].blower_electrical_energy_rate for i in infos] == [
+      1200.0, 1201.0, 1202.0]
+  assert [r.agent_reward_value for r in reader.read_reward_responses(t0, t1)] == [0.0, -0.25, -0.5]
+  obs = reader.read_observation_responses(t0, t1)
+  assert len(obs) == 3 and obs[0].single_observation_responses[2].continuous_value == np.float32(293.25)
+  acts = reader.read_action_responses(t0, t1)
+  assert [a.request.single_action_requests[0].setpoint_name for a in acts] == ["supply_water_setpoint"] * 3
+  # the reader selects shards by hour: a window that ends before 10:00 sees the first two records
+  assert len(reader.read_reward_infos(t0, naive + pd.Timedelta(30, unit="min"))) == 2
+
+
+@pytest.mark.gpu
+def test_environment_metrics_path_writes_the_episode_logs(tmp_path):
+  """Environment(metrics_path=...) (environment.py:362, 1181-1198): reset() opens
+  <metrics_path>/<label>_<stamp>/ and every step() logs the chosen buildings; the reference's
+  other constructor arguments are accepted."""
+  import scenarios as S
+  sc = S.Scenario(floor_plan=S.small_plan(), occupancy="step", start="2023-07-06 08:50:00")
+  with pytest.warns(UserWarning, match="device_action_tuples"):
+    env = S.make_env(sc, n_envs=2, metrics_path=str(tmp_path), label="run", metrics_env_indices=(1,),
+                     device_action_tuples=[("BLR", "supply_water_setpoint")], metrics_reporting_interval=10)
+  try:
+    env.reset()
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+      ts = env.step(rng.uniform(-1, 1, (2, 2)).astype(np.float32))
+    runs = os.listdir(str(tmp_path))
+    assert len(runs) == 1 and runs[0].startswith("run_")
+    d = os.path.join(str(tmp_path), runs[0], "env_1")
+    files = sorted(os.listdir(d))
+    assert {f.split("_2023")[0] for f in files} == {"reward_info", "reward_response",
+                                                    "observation_response", "action_response"}
+    resp = [r for f in files if f.startswith("reward_response") for r in ew.read_shard(os.path.join(d, f))]
+    assert len(resp) == 3
+    got = [v for f, wt, v in _decode(resp[-1]) if f == 1 and wt == 5][0]
+    assert got == np.float32(ts.reward[1])
+  finally:
+    env.close()

@@ -989,29 +989,37 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     // touched once per warp at the end.  No atomics (a shared-memory 64-bit atomic is
     // a CAS loop on this hardware), no per-element zone decoding.
     if constexpr (use_tma) mbar_wait(bar + 1, 0);
-    long long acc = 0;
-    int acc_zone = lane;          // the zone this lane currently accumulates
-    for (int chunk = warp; chunk < n_chunks; chunk += NW) {
+    // Each warp takes a CONTIGUOUS run of chunks: consecutive chunks mostly belong to one
+    // zone, so the lanes accumulate 32-bit partial sums over the run and the warp pays the REDUX
+    // pair once per zone change instead of once per chunk.  (T - ref) * 2^16 by one FFMA:
+    // fma(T, 2^16, -ref * 2^16) is exact, like to_fix32.
+    const float nref = -__fmul_rn(t_inf, kFixScaleF);
+    const int per = (n_chunks + NW - 1) / NW;
+    const int c_lo = min(n_chunks, warp * per), c_hi = min(n_chunks, c_lo + per);
+    int acc = 0, cur_z = -1;          // a run holds at most `per` * 4 CVs per lane: no overflow
+    for (int chunk = c_lo; chunk < c_hi; ++chunk) {
       const uint32_t en = rlist[chunk * 32 + lane];
       float t[V];
       load_f<V>(in + (en & 0xFFFFu) * V, t);
       int sl = 0;
 #pragma unroll
       for (int e = 0; e < V; ++e)
-        if (en & (0x10000u << e)) sl += to_fix32(t[e], t_inf);
-      const long long sum = warp_sum_i32(sl);
+        if (en & (0x10000u << e)) sl += __float2int_rn(__fmaf_rn(t[e], kFixScaleF, nref));
       const int z0 = (int)(__shfl_sync(0xffffffffu, en, 0) >> 20);
-      if (lane == (z0 & 31)) {
-        if (z0 != acc_zone) {          // only with more than 32 zones
-          wbins[acc_zone] += acc;      // warp-private, this lane owns zones = lane mod 32
-          acc_zone = z0;
-          acc = 0;
+      if (z0 != cur_z) {               // warp-uniform
+        if (cur_z >= 0) {
+          const long long sum = warp_sum_i32(acc);
+          if (lane == 0) wbins[cur_z] += sum;
         }
-        acc += sum;
+        cur_z = z0;
+        acc = 0;
       }
+      acc += sl;
     }
-    __syncwarp();
-    if (acc_zone <= Z && acc != 0) wbins[acc_zone] += acc;
+    if (cur_z >= 0) {
+      const long long sum = warp_sum_i32(acc);
+      if (lane == 0) wbins[cur_z] += sum;
+    }
   } else if (!p.fd_only) {
     // generic loop (plans whose zone-sum list does not fit): per-CV atomics
     for (int i = tid; i < n_cv; i += NT) {

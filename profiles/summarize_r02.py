@@ -127,7 +127,8 @@ if os.path.exists(f"{SRC}/r02_randomized_v3.ncu-rep"):
 h2, u2, d2 = summarize(f"{SRC}/r02_office.ncu-rep", "profiles/r02_ncu_full_office.txt",
                        "ncu --set full --clock-control none --import-source on, `python bench.py --workload office "
                        "--envs-per-gpu 512` (calibrated sb1 plan 744x1004, 512 copies so that the ~40 replays stay short, "
-                       "device-RNG convection as shipped): k_sweep<4>, k_convect_reduce / k_zone_reduce (profiles/capture_r02.sh)",
+                       "device-RNG convection as shipped; host-polled sweep loop, see profiles/capture_r02_office.sh): k_sweep<4>, "
+                       "k_convect_reduce (profiles/capture_r02_office.sh)",
                        "k_sweep")
 for name in ("randomized", "office"):
   rows = list(csv.reader(open(f"{SRC}/r02_launches_{name}.csv")))
@@ -135,7 +136,8 @@ for name in ("randomized", "office"):
          for r in rows if len(r) > 10 and (r[0] == "ID" or "sbx::" in r[4])]
   csv.writer(open(f"profiles/r02_launches_{name}.csv", "w", newline="")).writerows(out)
 ir = row_of(h1, d1, "k_resident_step")
-isw = row_of(h2, d2, "k_sweep")
+sweeps = [i for i, r in enumerate(d2) if "k_sweep" in r[h2.index("Kernel Name")]]
+isw = max(sweeps, key=lambda i: col(h2, u2, d2, "dram__bytes_read.sum", i))   # a sweep >= 2 (reads T_est and T_prev)
 traffic = {
     "randomized": {"kernel": "k_resident_step<4>", "launch_envs": 32768,
                    "dram_bytes_read": col(h1, u1, d1, "dram__bytes_read.sum", ir),
@@ -144,8 +146,8 @@ traffic = {
     "office": {"kernel": "k_sweep<4>", "launch_envs": 512,
                "dram_bytes_read": col(h2, u2, d2, "dram__bytes_read.sum", isw),
                "dram_bytes_write": col(h2, u2, d2, "dram__bytes_write.sum", isw),
-               "source": "profiles/r02_ncu_full_office.txt (ncu --set full, 512 buildings per launch, first captured "
-                         "k_sweep launch)"}}
+               "source": "profiles/r02_ncu_full_office.txt (ncu --set full, 512 buildings per launch, a sweep >= 2: reads "
+                         "T_est and T_prev)"}}
 json.dump(traffic, open("profiles/traffic.json", "w"), indent=1)
 for f in ("r02_bench.json", "r02_bench_reference.json"):
   if os.path.exists(f"{SRC}/{f}"):

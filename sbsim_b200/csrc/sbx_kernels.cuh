@@ -1661,89 +1661,157 @@ __global__ void __launch_bounds__(kStreamThreads, 4) k_convect_reduce(const Para
       runL += sl;
       runR += sr;
       // ---- the swap pattern ----
-      // candidate partner values / zones of the V CVs: the same columns of row r +- m
-      // (vertical pattern: one more vector load of T and of the descriptor), or the columns
-      // c +- m of this row (horizontal: this thread's vector and its lane neighbours' by
-      // shuffle; the two lanes at the warp's ends read the adjacent tile from memory)
-      float pt[V];
-      int pz[V];
-#pragma unroll
-      for (int e = 0; e < V; ++e) { pt[e] = tv[e]; pz[e] = -1; }
-      if (cp.vertical) {
-        const int tmod = (r + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
-        const int rp = tmod < cp.m ? r + cp.m : r - cp.m;
-        if (rp >= 0 && rp < H && col_ok) {
-          uint32_t dp[V];
-          load_f<V>(t + (size_t)rp * W + c0, pt);
-          load_d<V>(dsc + (size_t)rp * W + c0, dp);
-#pragma unroll
-          for (int e = 0; e < V; ++e) pz[e] = desc_zone(dp[e]);
-        }
-      } else {
-        // window of V + 4 columns around the vector: [c0 - 2, c0 + V + 2)
-        float wt[V + 4];
-        int wz[V + 4];
-#pragma unroll
-        for (int e = 0; e < V; ++e) { wt[2 + e] = tv[e]; wz[2 + e] = desc_zone(d[e]); }
-        if constexpr (V == 4) {
-          wt[0] = __shfl_up_sync(0xffffffffu, tv[2], 1); wt[1] = __shfl_up_sync(0xffffffffu, tv[3], 1);
-          wt[6] = __shfl_down_sync(0xffffffffu, tv[0], 1); wt[7] = __shfl_down_sync(0xffffffffu, tv[1], 1);
-          const int zlo = wz[4] | (wz[5] << 8), zhi = wz[2] | (wz[3] << 8);
-          const int zl = __shfl_up_sync(0xffffffffu, zlo, 1), zr = __shfl_down_sync(0xffffffffu, zhi, 1);
-          wz[0] = zl & 0xFF; wz[1] = zl >> 8; wz[6] = zr & 0xFF; wz[7] = zr >> 8;
+      if constexpr (V == 4) {
+        // Zones of the four CVs and of their partners as BYTES of one word: "same room" is one
+        // byte-wise compare for the vector.  Partner = the same columns of row r +- m (vertical
+        // pattern: one more vector load of T and of the descriptor) or the columns c +- m of this
+        // row (horizontal: a window of 8 columns around the vector, the outer 2 + 2 from the lane
+        // neighbours by shuffle -- the lanes at the warp's ends read them from memory -- and a
+        // per-(m, phase) selection with static indices: the phase is uniform over the building).
+        const uint32_t zw = __byte_perm(d[0] | (d[1] << 16), d[2] | (d[3] << 16), 0x7531);
+        float pt0 = tv[0], pt1 = tv[1], pt2 = tv[2], pt3 = tv[3];
+        uint32_t pzw = 0xFFFFFFFFu;                       // no partner: zone NONE everywhere
+        if (cp.vertical) {
+          const int tmod = (r + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
+          const int rp = tmod < cp.m ? r + cp.m : r - cp.m;
+          if (rp >= 0 && rp < H && col_ok) {
+            const float4 pv = *reinterpret_cast<const float4*>(t + (size_t)rp * W + c0);
+            const uint2 dp = *reinterpret_cast<const uint2*>(dsc + (size_t)rp * W + c0);
+            pt0 = pv.x; pt1 = pv.y; pt2 = pv.z; pt3 = pv.w;
+            pzw = __byte_perm(dp.x, dp.y, 0x7531);
+          }
+        } else {
+          // window columns c0-2 .. c0+5: w0 w1 | tv | w6 w7, zones zlo = (w0 w1 tv0 tv1), zhi = (tv2 tv3 w6 w7)
+          float w0 = __shfl_up_sync(0xffffffffu, tv[2], 1), w1 = __shfl_up_sync(0xffffffffu, tv[3], 1);
+          float w6 = __shfl_down_sync(0xffffffffu, tv[0], 1), w7 = __shfl_down_sync(0xffffffffu, tv[1], 1);
+          uint32_t zl = __shfl_up_sync(0xffffffffu, zw, 1) >> 16, zr = __shfl_down_sync(0xffffffffu, zw, 1) & 0xFFFFu;
           if (col_ok && (lane == 0 || lane == 31 || c0 + V >= W)) {     // the window leaves the warp's columns
-#pragma unroll
-            for (int k = 0; k < 2; ++k) {
-              const int cl = c0 - 2 + k, cr = c0 + V + k;
-              if (lane == 0) {
-                wz[k] = cl >= 0 ? desc_zone(dsc[(size_t)r * W + cl]) : -1;
-                wt[k] = cl >= 0 ? t[(size_t)r * W + cl] : 0.f;
-              }
-              if (lane == 31 || c0 + V >= W) {
-                wz[6 + k] = cr < W ? desc_zone(dsc[(size_t)r * W + cr]) : -1;
-                wt[6 + k] = cr < W ? t[(size_t)r * W + cr] : 0.f;
-              }
+            if (lane == 0) {
+              const bool in = c0 >= 2;
+              w0 = in ? t[off - 2] : 0.f; w1 = in ? t[off - 1] : 0.f;
+              zl = in ? ((uint32_t)desc_zone(dsc[off - 2]) | ((uint32_t)desc_zone(dsc[off - 1]) << 8)) : 0xFFFFu;
+            }
+            if (lane == 31 || c0 + V >= W) {
+              const bool in0 = c0 + V < W, in1 = c0 + V + 1 < W;
+              w6 = in0 ? t[off + V] : 0.f; w7 = in1 ? t[off + V + 1] : 0.f;
+              zr = (in0 ? (uint32_t)desc_zone(dsc[off + V]) : 0xFFu) | ((in1 ? (uint32_t)desc_zone(dsc[off + V + 1]) : 0xFFu) << 8);
             }
           }
-        } else if (col_ok) {
-#pragma unroll
-          for (int k = 0; k < 2; ++k) {                     // V == 1: plain loads
-            const int cl = c0 - 2 + k, cr = c0 + V + k;
-            wz[k] = cl >= 0 ? desc_zone(dsc[(size_t)r * W + cl]) : -1;
-            wt[k] = cl >= 0 ? t[(size_t)r * W + cl] : 0.f;
-            wz[V + 2 + k] = cr < W ? desc_zone(dsc[(size_t)r * W + cr]) : -1;
-            wt[V + 2 + k] = cr < W ? t[(size_t)r * W + cr] : 0.f;
+          const uint32_t zlo = zl | (zw << 16), zhi = (zw >> 16) | (zr << 16);
+          // partner window index of element e: 2 + e + m where ((e - phi) mod 2m) < m, else 2 + e - m
+          switch (cp.m * 4 + cp.phi) {
+            case 4 + 0: pt0 = tv[1]; pt1 = tv[0]; pt2 = tv[3]; pt3 = tv[2]; pzw = __byte_perm(zlo, zhi, 0x4523); break;
+            case 4 + 1: pt0 = w1; pt1 = tv[2]; pt2 = tv[1]; pt3 = w6; pzw = __byte_perm(zlo, zhi, 0x6341); break;
+            case 8 + 0: pt0 = tv[2]; pt1 = tv[3]; pt2 = tv[0]; pt3 = tv[1]; pzw = __byte_perm(zlo, zhi, 0x3254); break;
+            case 8 + 1: pt0 = w0; pt1 = tv[3]; pt2 = w6; pt3 = tv[1]; pzw = __byte_perm(zlo, zhi, 0x3650); break;
+            case 8 + 2: pt0 = w0; pt1 = w1; pt2 = w6; pt3 = w7; pzw = __byte_perm(zlo, zhi, 0x7610); break;
+            default:    pt0 = tv[2]; pt1 = w1; pt2 = tv[0]; pt3 = w7; pzw = __byte_perm(zlo, zhi, 0x7214); break;   // m = 2, phase 3
           }
         }
+        // swap where the CV is in a room and its partner is in the same room
+        uint32_t sw = __vcmpeq4(zw, pzw) & ~__vcmpeq4(zw, 0xFFFFFFFFu);
+        if (!always && sw != 0u) {
 #pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const int c = c0 + e;
+            const int sc = cp.vertical ? r : c;
+            const int tmod = (sc + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
+            const int sp = tmod < cp.m ? sc + cp.m : sc - cp.m;
+            const size_t self = (size_t)r * W + c;
+            const size_t poff = cp.vertical ? (size_t)sp * W + c : (size_t)r * W + sp;
+            const uint32_t key = (uint32_t)(self < poff ? self : poff);
+            if (mix32(key ^ cp.pair_key) >= thr) sw &= ~(0xFFu << (8 * e));
+          }
+        }
+        o[0] = (sw & 0x000000FFu) ? pt0 : tv[0];
+        o[1] = (sw & 0x0000FF00u) ? pt1 : tv[1];
+        o[2] = (sw & 0x00FF0000u) ? pt2 : tv[2];
+        o[3] = (sw & 0xFF000000u) ? pt3 : tv[3];
+      } else {
+        // candidate partner values / zones of the V CVs: the same columns of row r +- m
+        // (vertical pattern: one more vector load of T and of the descriptor), or the columns
+        // c +- m of this row (horizontal: this thread's vector and its lane neighbours' by
+        // shuffle; the two lanes at the warp's ends read the adjacent tile from memory)
+        float pt[V];
+        int pz[V];
+  #pragma unroll
+        for (int e = 0; e < V; ++e) { pt[e] = tv[e]; pz[e] = -1; }
+        if (cp.vertical) {
+          const int tmod = (r + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
+          const int rp = tmod < cp.m ? r + cp.m : r - cp.m;
+          if (rp >= 0 && rp < H && col_ok) {
+            uint32_t dp[V];
+            load_f<V>(t + (size_t)rp * W + c0, pt);
+            load_d<V>(dsc + (size_t)rp * W + c0, dp);
+  #pragma unroll
+            for (int e = 0; e < V; ++e) pz[e] = desc_zone(dp[e]);
+          }
+        } else {
+          // window of V + 4 columns around the vector: [c0 - 2, c0 + V + 2)
+          float wt[V + 4];
+          int wz[V + 4];
+  #pragma unroll
+          for (int e = 0; e < V; ++e) { wt[2 + e] = tv[e]; wz[2 + e] = desc_zone(d[e]); }
+          if constexpr (V == 4) {
+            wt[0] = __shfl_up_sync(0xffffffffu, tv[2], 1); wt[1] = __shfl_up_sync(0xffffffffu, tv[3], 1);
+            wt[6] = __shfl_down_sync(0xffffffffu, tv[0], 1); wt[7] = __shfl_down_sync(0xffffffffu, tv[1], 1);
+            const int zlo = wz[4] | (wz[5] << 8), zhi = wz[2] | (wz[3] << 8);
+            const int zl = __shfl_up_sync(0xffffffffu, zlo, 1), zr = __shfl_down_sync(0xffffffffu, zhi, 1);
+            wz[0] = zl & 0xFF; wz[1] = zl >> 8; wz[6] = zr & 0xFF; wz[7] = zr >> 8;
+            if (col_ok && (lane == 0 || lane == 31 || c0 + V >= W)) {     // the window leaves the warp's columns
+  #pragma unroll
+              for (int k = 0; k < 2; ++k) {
+                const int cl = c0 - 2 + k, cr = c0 + V + k;
+                if (lane == 0) {
+                  wz[k] = cl >= 0 ? desc_zone(dsc[(size_t)r * W + cl]) : -1;
+                  wt[k] = cl >= 0 ? t[(size_t)r * W + cl] : 0.f;
+                }
+                if (lane == 31 || c0 + V >= W) {
+                  wz[6 + k] = cr < W ? desc_zone(dsc[(size_t)r * W + cr]) : -1;
+                  wt[6 + k] = cr < W ? t[(size_t)r * W + cr] : 0.f;
+                }
+              }
+            }
+          } else if (col_ok) {
+  #pragma unroll
+            for (int k = 0; k < 2; ++k) {                     // V == 1: plain loads
+              const int cl = c0 - 2 + k, cr = c0 + V + k;
+              wz[k] = cl >= 0 ? desc_zone(dsc[(size_t)r * W + cl]) : -1;
+              wt[k] = cl >= 0 ? t[(size_t)r * W + cl] : 0.f;
+              wz[V + 2 + k] = cr < W ? desc_zone(dsc[(size_t)r * W + cr]) : -1;
+              wt[V + 2 + k] = cr < W ? t[(size_t)r * W + cr] : 0.f;
+            }
+          }
+  #pragma unroll
+          for (int e = 0; e < V; ++e) {
+            const int tmod = (c0 + e + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
+            const int sh = tmod < cp.m ? cp.m : -cp.m;       // +-1 or +-2
+            // select from the window without dynamic indexing
+            const float a1 = sh > 0 ? wt[2 + e + 1] : wt[2 + e - 1];
+            const float a2 = sh > 0 ? wt[2 + e + 2] : wt[2 + e - 2];
+            const int b1 = sh > 0 ? wz[2 + e + 1] : wz[2 + e - 1];
+            const int b2 = sh > 0 ? wz[2 + e + 2] : wz[2 + e - 2];
+            pt[e] = cp.m == 1 ? a1 : a2;
+            pz[e] = cp.m == 1 ? b1 : b2;
+          }
+        }
+  #pragma unroll
         for (int e = 0; e < V; ++e) {
-          const int tmod = (c0 + e + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
-          const int sh = tmod < cp.m ? cp.m : -cp.m;       // +-1 or +-2
-          // select from the window without dynamic indexing
-          const float a1 = sh > 0 ? wt[2 + e + 1] : wt[2 + e - 1];
-          const float a2 = sh > 0 ? wt[2 + e + 2] : wt[2 + e - 2];
-          const int b1 = sh > 0 ? wz[2 + e + 1] : wz[2 + e - 1];
-          const int b2 = sh > 0 ? wz[2 + e + 2] : wz[2 + e - 2];
-          pt[e] = cp.m == 1 ? a1 : a2;
-          pz[e] = cp.m == 1 ? b1 : b2;
+          o[e] = tv[e];
+          const int z = desc_zone(d[e]);
+          if (z == SBX_ZONE_NONE || pz[e] != z) continue;      // only room CVs move, inside their room
+          if (!always) {
+            const int c = c0 + e;
+            const int sc = cp.vertical ? r : c;
+            const int tmod = (sc + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
+            const int sp = tmod < cp.m ? sc + cp.m : sc - cp.m;
+            const size_t self = (size_t)r * W + c;
+            const size_t poff = cp.vertical ? (size_t)sp * W + c : (size_t)r * W + sp;
+            const uint32_t key = (uint32_t)(self < poff ? self : poff);
+            if (mix32(key ^ cp.pair_key) >= thr) continue;
+          }
+          o[e] = pt[e];
         }
-      }
-#pragma unroll
-      for (int e = 0; e < V; ++e) {
-        o[e] = tv[e];
-        const int z = desc_zone(d[e]);
-        if (z == SBX_ZONE_NONE || pz[e] != z) continue;      // only room CVs move, inside their room
-        if (!always) {
-          const int c = c0 + e;
-          const int sc = cp.vertical ? r : c;
-          const int tmod = (sc + 2 * cp.m - cp.phi) & (2 * cp.m - 1);
-          const int sp = tmod < cp.m ? sc + cp.m : sc - cp.m;
-          const size_t self = (size_t)r * W + c;
-          const size_t poff = cp.vertical ? (size_t)sp * W + c : (size_t)r * W + sp;
-          const uint32_t key = (uint32_t)(self < poff ? self : poff);
-          if (mix32(key ^ cp.pair_key) >= thr) continue;
-        }
-        o[e] = pt[e];
       }
       if (col_ok) store_f<V>(tout + off, o);
     }

@@ -141,3 +141,38 @@ def test_device_rng_convection_invariants(path, p_swap, distance):
   assert not np.array_equal(b[0] != a[0], b[1] != a[1]) or p_swap == 1.0   # per-building draws
   # the second step draws a new pattern (and keeps conserving the rooms' sums)
   assert conv[1][0].shape == b.shape
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("p_swap,distance", [(1.0, 5), (0.6, 5), (1.0, 2)])
+def test_device_rng_convection_is_the_same_on_both_kernel_paths(p_swap, distance):
+  """The resident kernels apply the pattern CV by CV (convect_source), the streaming path
+  vector by vector with byte-wise zone compares and a per-(offset, phase) window selection
+  (k_convect_reduce): same pattern, same field, bit for bit, over several steps (every offset /
+  phase combination turns up)."""
+  import sbsim_b200 as sbx
+  import scenarios as S
+  plan = np.full((32, 48), 2, dtype=np.int64)
+  plan[2:30, 2:46] = 1
+  plan[3:29, 3:45] = 0
+  plan[15, 3:45] = 1
+  plan[3:29, 22] = 1
+  B, steps = 8, 6
+  fields = {}
+  for name, path in (("streaming", sbx.PATH_STREAMING), ("resident", sbx.PATH_RESIDENT)):
+    sc = S.Scenario(floor_plan=plan, buffer_from_walls=2)
+    env = S.make_env(sc, n_envs=B, plans=sc.compiled(), kernel_path=path)
+    env.handle.set_device_convection(p_swap, distance, 11)
+    try:
+      env.reset()
+      rng = np.random.default_rng(3)
+      env.handle.upload("temp", rng.uniform(288, 296, (B, 32, 48)).astype(np.float32))
+      out = []
+      for _ in range(steps):
+        env.step(np.zeros((B, 2), dtype=np.float32))
+        out.append(env.handle.download("temp", (B, 32, 48)).copy())
+      fields[name] = out
+    finally:
+      env.close()
+  for k in range(steps):
+    np.testing.assert_array_equal(fields["streaming"][k], fields["resident"][k], err_msg=f"step {k}")

@@ -193,16 +193,22 @@ class SetpointSchedule:
 
 
 @functools.cache
-def _us_holidays():
-  # The reference uses the third-party `holidays.US()` (unpinned, not in this
-  # image); federal holidays are what it contains for plain `US()`.
-  from pandas.tseries.holiday import USFederalHolidayCalendar
-  cal = USFederalHolidayCalendar()
-  return frozenset(d.date() for d in cal.holidays(start="2000-01-01", end="2040-12-31"))
+def _us_holidays_of_year(year: int):
+  """US public holidays of one year.  The reference asks the third-party `holidays.US()`
+  (unpinned); it is used when importable.  Otherwise -- it is not in this image -- the federal
+  holidays of pandas' USFederalHolidayCalendar, which is what plain `US()` contains (observed-day
+  rules may differ between versions of either package: the deviation is in this one lookup)."""
+  try:
+    import holidays      # pylint: disable=g-import-not-at-top
+    return frozenset(holidays.US(years=year).keys())
+  except ImportError:
+    from pandas.tseries.holiday import USFederalHolidayCalendar      # pylint: disable=g-import-not-at-top
+    cal = USFederalHolidayCalendar()
+    return frozenset(d.date() for d in cal.holidays(start=f"{year}-01-01", end=f"{year}-12-31"))
 
 
 def is_work_day(ts: pd.Timestamp) -> bool:
-  return ts.weekday() < 5 and ts.date() not in _us_holidays()
+  return ts.weekday() < 5 and ts.date() not in _us_holidays_of_year(ts.year)
 
 
 def time_feature_table(timestamps: Sequence[pd.Timestamp]) -> np.ndarray:

@@ -9,7 +9,7 @@ behind the C ABI of include/sbx.h.  See DESIGN.md and INTEGRATION.md.
 from sbsim_b200._lib import (LIB_PATH, PATH_AUTO, PATH_RESIDENT, PATH_STREAMING,
                              SbxLibraryError)
 from sbsim_b200.config import (ActionConfig, AirHandler, Boiler, BoundedActionNormalizer,
-                               FloorPlanBasedHvac, HistogramReducer,
+                               FloorPlanBasedHvac, HistogramReducer, Hvac,
                                SetpointEnergyCarbonRegretFunction,
                                SetpointEnergyCarbonRewardFunction,
                                StandardScoreObservationNormalizer)
@@ -26,7 +26,7 @@ from sbsim_b200.floorplan import (CompiledPlan, MaterialProperties, compile_plan
 __all__ = [
     "ActionConfig", "AirHandler", "BatchedWeather", "Boiler", "BoundedActionNormalizer",
     "CompiledPlan", "ConstantOccupancy", "ElectricityEnergyCost", "Environment",
-    "FloorPlanBasedHvac", "HistogramReducer", "LIB_PATH", "MaterialProperties",
+    "FloorPlanBasedHvac", "HistogramReducer", "Hvac", "LIB_PATH", "MaterialProperties",
     "NaturalGasEnergyCost", "PATH_AUTO", "PATH_RESIDENT", "PATH_STREAMING",
     "RandomizedArrivalDepartureOccupancy",
     "ReplayWeatherController", "SbxLibraryError", "SetpointEnergyCarbonRegretFunction",

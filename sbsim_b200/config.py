@@ -73,6 +73,25 @@ class FloorPlanBasedHvac:
 
 
 @dataclasses.dataclass
+class Hvac:
+  """The deprecated `Hvac` (simulator/hvac.py:35-123): one boiler, one air handler and one VAV
+  per zone of the rectangular `Building`, zones addressed by (row, column).  Same devices and
+  algebra as FloorPlanBasedHvac; what differs is the naming: device `vav_<i>_<j>` and zone id
+  `zone_id_(i, j)` (conversion_utils.zone_coordinates_to_id).  Use with `legacy_building()`."""
+  zone_coordinates: Sequence[Tuple[int, int]]
+  air_handler: AirHandler
+  boiler: Boiler
+  schedule: exogenous.SetpointSchedule
+  vav_max_air_flow_rate: float
+  vav_reheat_max_water_flow_rate: float
+
+  def __post_init__(self):
+    self.zone_coordinates = [(int(i), int(j)) for i, j in self.zone_coordinates]
+    if len(set(self.zone_coordinates)) != len(self.zone_coordinates):
+      raise ValueError("zone_coordinates must be distinct")
+
+
+@dataclasses.dataclass
 class SetpointEnergyCarbonRegretFunction:
   max_productivity_personhour_usd: float
   min_productivity_personhour_usd: float

@@ -19,6 +19,7 @@ moves I/O buffers.  There is no CPU fallback.
 from __future__ import annotations
 
 import ctypes as C
+import dataclasses
 import os
 import warnings
 from typing import List, Optional, Sequence, Union
@@ -88,6 +89,22 @@ class SimulatorBuilding:
       raise ValueError("pass one plan (shared by every env) or one plan per env")
     self.n_envs = int(n_envs)
     self.hvac = hvac
+    # The deprecated Hvac (hvac.py:35-123) addresses zones by (row, column) and names its devices
+    # `vav_<i>_<j>`: the rooms of a legacy_building() plan (raster order = row-major) take those
+    # names, and the observation order follows the new device ids.
+    self._legacy_coordinates = None
+    if isinstance(hvac, config_lib.Hvac):
+      coords = sorted(hvac.zone_coordinates)
+      renamed = []
+      for pl in self.plans:
+        if len(coords) != pl.n_zones:
+          raise ValueError(f"Hvac has {len(coords)} zone coordinates, the building {pl.n_zones} rooms; build "
+                           "the plan with legacy_building(room_shape, building_shape)")
+        names = [f"{i}_{j}" for i, j in coords]
+        order = np.array(sorted(range(len(names)), key=lambda k: "vav_" + names[k]), dtype=np.int32)
+        renamed.append(dataclasses.replace(pl, zone_names=names, obs_zone_order=order))
+      self.plans = renamed
+      self._legacy_coordinates = {f"{i}_{j}": (i, j) for i, j in coords}
     if isinstance(weather_controller, (list, tuple)):
       if len(weather_controller) != self.n_envs:
         raise ValueError("pass one weather controller or one per env")
@@ -106,7 +123,10 @@ class SimulatorBuilding:
 
   @property
   def zone_ids(self) -> List[str]:
-    """zone ids of plan 0 (conversion_utils.floor_plan_based_zone_identifier_to_id)."""
+    """zone ids of plan 0 (conversion_utils.floor_plan_based_zone_identifier_to_id; with the
+    deprecated Hvac: conversion_utils.zone_coordinates_to_id, 'zone_id_(i, j)')."""
+    if self._legacy_coordinates is not None:
+      return ["zone_id_" + str(self._legacy_coordinates[n]) for n in self.plans[0].zone_names]
     return ["zone_id_" + n.replace("room_", "") for n in self.plans[0].zone_names]
 
 

@@ -249,8 +249,10 @@ class EpisodeWriter:
       obs += [(self.air_handler_id, n, v) for n, v in zip(AHU_FIELDS, ahu_vals)]
       obs += [(self.boiler_id, n, v) for n, v in zip(
           BOILER_FIELDS, (diag[b, D["heating_requests"]], boiler_sp[b], diag[b, D["tank_temp"]]))]
+      zone_ids = env.building.zone_ids if plan is env.building.plans[0] else [
+          "zone_id_" + n.replace("room_", "") for n in plan.zone_names]
       for zi, name in enumerate(plan.zone_names):
-        zid = "zone_id_" + name.replace("room_", "")
+        zid = zone_ids[zi]
         occ = self._occ[s1, zi if self._occ.shape[1] > 1 else 0]
         zones[zid] = (window[0], window[1], zone_mean[b, zi], cfg.vav_max_air_flow_rate, flow, occ)
         damper = 1.0 if mode[b, zi] in (1, 2) else 0.1         # vav.py:230-243

@@ -148,15 +148,19 @@ def make_oracle(sc: Scenario, cp: Optional[floorplan.CompiledPlan] = None,
 
 def make_env(sc: Scenario, n_envs: int = 1, plans=None, weather=None, initial_temp=None,
              kernel_path: int = sbx.PATH_AUTO, device: int = 0,
-             solver: str = "tf_jacobi", **env_kwargs) -> sbx.Environment:
+             solver: str = "tf_jacobi", legacy_hvac_coordinates=None, **env_kwargs) -> sbx.Environment:
   plans = plans or sc.compiled()
   schedule = sbx.SetpointSchedule(6, 19, (294, 297), (289, 298), time_zone=sc.schedule_tz)
   weather = weather or sbx.WeatherController(sc.weather_low, sc.weather_high,
                                              convection_coefficient=sc.convection_coefficient)
-  hvac = sbx.FloorPlanBasedHvac(
+  hvac_args = dict(
       air_handler=sbx.AirHandler(0.3, 285, 298, 10000.0, 0.9, max_air_flow_rate=8.67),
       boiler=sbx.Boiler(360.0, 6.0, 0.98, heating_rate=0.5, cooling_rate=0.1),
       schedule=schedule, vav_max_air_flow_rate=0.035, vav_reheat_max_water_flow_rate=0.03)
+  if legacy_hvac_coordinates is not None:       # the deprecated Hvac (simulator/hvac.py:35-123)
+    hvac = sbx.Hvac(zone_coordinates=legacy_hvac_coordinates, **hvac_args)
+  else:
+    hvac = sbx.FloorPlanBasedHvac(**hvac_args)
   if sc.occupancy == "step":
     occ = sbx.StepFunctionOccupancy(pd.Timedelta(9, unit="h"), pd.Timedelta(17, unit="h"),
                                     1.0, 0.1)

@@ -555,3 +555,34 @@ def test_gauss_seidel_on_the_legacy_rectangular_building():
       np.testing.assert_array_equal(got[b], want)
   finally:
     env.close()
+
+
+def test_legacy_hvac_on_the_legacy_building_changes_names_not_numbers():
+  """The deprecated `Hvac(zone_coordinates, ...)` (simulator/hvac.py:35-123) on
+  the rectangular Building: devices `vav_<i>_<j>`, zone ids `zone_id_(i, j)`; the same devices and
+  algebra as FloorPlanBasedHvac, so a rollout gives the same numbers."""
+  cp = floorplan.legacy_building(
+      20.0, (8, 10), (2, 3), floorplan.MaterialProperties(50.0, 700.0, 1.0),
+      floorplan.MaterialProperties(5.0, 800.0, 1800.0), floorplan.MaterialProperties(5.0, 800.0, 3000.0))
+  sc = S.Scenario(floor_plan=np.zeros((4, 4), dtype=np.int64), cv_size_cm=20.0, occupancy="step",
+                  start="2023-07-06 08:30:00")
+  coords = [(i, j) for i in range(2) for j in range(3)]
+  outs = {}
+  for name, kw in (("floor_plan", {}), ("legacy", dict(legacy_hvac_coordinates=coords))):
+    env = S.make_env(sc, n_envs=2, plans=cp, solver="gauss_seidel", **kw)
+    try:
+      env.reset()
+      rng = np.random.default_rng(4)
+      rows = []
+      for _ in range(12):
+        ts = env.step(rng.uniform(-1, 1, (2, 2)).astype(np.float32))
+        rows.append((ts.observation.copy(), ts.reward.copy()))
+      outs[name] = (rows, list(env.field_names), env.building.zone_ids)
+    finally:
+      env.close()
+  for (oa, ra), (ob, rb) in zip(outs["floor_plan"][0], outs["legacy"][0]):
+    np.testing.assert_array_equal(oa, ob)
+    np.testing.assert_array_equal(ra, rb)
+  assert "vav_0_0_zone_air_temperature_sensor" in outs["legacy"][1]
+  assert "vav_room_1_zone_air_temperature_sensor" in outs["floor_plan"][1]
+  assert outs["legacy"][2][:2] == ["zone_id_(0, 0)", "zone_id_(0, 1)"]

@@ -221,3 +221,31 @@ def test_randomized_occupancy_tz_aware_matches_oracle_restatement():
       for z, zid in enumerate(zone_ids):
         assert rew[s, z] == b.average_zone_occupancy(zid, t, t + dt)
   assert obs.max() > 5 and obs.min() == 0
+
+
+def test_legacy_hvac_names_zones_by_coordinates():
+  """The deprecated Hvac (simulator/hvac.py:35-123): devices `vav_<i>_<j>`, zone ids
+  `zone_id_(i, j)` (conversion_utils.zone_coordinates_to_id), rooms of the rectangular Building
+  in row-major order; observation slots follow the sorted device ids."""
+  import sbsim_b200 as sbx
+  from sbsim_b200 import floorplan
+  air = floorplan.MaterialProperties(50.0, 700.0, 1.0)
+  wall = floorplan.MaterialProperties(5.0, 800.0, 1800.0)
+  cp = floorplan.legacy_building(20.0, (6, 8), (3, 4), air, wall, wall)
+  coords = [(i, j) for i in range(3) for j in range(4)]
+  hvac = sbx.Hvac(coords[::-1], sbx.AirHandler(0.3, 285, 298, 10000.0, 0.9, max_air_flow_rate=8.67),
+                  sbx.Boiler(360.0, 6.0, 0.98), sbx.SetpointSchedule(6, 19, (294, 297), (289, 298)), 0.035, 0.03)
+  b = sbx.SimulatorBuilding(cp, hvac, sbx.WeatherController(280.0, 290.0), sbx.ConstantOccupancy(1.0),
+                            start_timestamp=pd.Timestamp("2023-07-06 07:00:00"), solver="gauss_seidel")
+  assert b.plans[0].zone_names == [f"{i}_{j}" for i, j in coords]
+  assert b.zone_ids == [f"zone_id_({i}, {j})" for i, j in coords]
+  # room k of the plan (raster order of its first CV) is coordinate k in row-major order
+  zid = b.plans[0].zone_id
+  for k, (i, j) in enumerate(coords):
+    r, c = np.argwhere(zid == k)[0]
+    assert (r, c) == (3 + 7 * i, 3 + 9 * j)
+  assert list(b.plans[0].obs_zone_order) == sorted(range(12), key=lambda k: "vav_%d_%d" % coords[k])
+  with pytest.raises(ValueError):
+    sbx.SimulatorBuilding(cp, sbx.Hvac(coords[:5], hvac.air_handler, hvac.boiler, hvac.schedule, 0.035, 0.03),
+                          sbx.WeatherController(280.0, 290.0), sbx.ConstantOccupancy(1.0),
+                          start_timestamp=pd.Timestamp("2023-07-06 07:00:00"))

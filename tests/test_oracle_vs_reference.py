@@ -130,3 +130,28 @@ def test_legacy_building_plan_matches_reference_building(ref, room_shape, buildi
       block = cp.zone_id[1:-1, 1:-1][x0:x0 + room_shape[0], y0:y0 + room_shape[1]]
       assert np.all(block == zi), (zx, zy)
       zi += 1
+
+
+def test_legacy_hvac_naming_matches_reference(ref):
+  """sbx.Hvac + legacy_building() name devices and zones like the deprecated
+  simulator/hvac.py:Hvac (`vav_<i>_<j>`, `zone_id_(i, j)`), room k <-> coordinate k row-major."""
+  import importlib
+  import sbsim_b200 as sbx
+  hvac_mod = importlib.import_module("smart_buildings.smart_control.simulator.hvac")
+  coords = [(i, j) for i in range(2) for j in range(3)]
+  weather = ref["wc"].WeatherController(275.0, 290.0, convection_coefficient=60.0)
+  sched = ref["ss"].SetpointSchedule(6, 19, (294, 297), (289, 298))
+  boiler = ref["bl"].Boiler(360.0, 6.0, 0.98, heating_rate=0.5, cooling_rate=0.1, device_id="boiler_id_x")
+  ahu = ref["ah"].AirHandler(0.3, 285, 298, 10000.0, 0.9, max_air_flow_rate=8.67, device_id="air_handler_id_x",
+                             sim_weather_controller=weather)
+  rh = hvac_mod.Hvac(coords, ahu, boiler, sched, 0.035, 0.03)
+  air = floorplan.MaterialProperties(50.0, 700.0, 1.0)
+  wall = floorplan.MaterialProperties(5.0, 800.0, 1800.0)
+  cp = floorplan.legacy_building(20.0, (6, 8), (2, 3), air, wall, wall)
+  b = sbx.SimulatorBuilding(
+      cp, sbx.Hvac(coords, sbx.AirHandler(0.3, 285, 298, 10000.0, 0.9, max_air_flow_rate=8.67),
+                   sbx.Boiler(360.0, 6.0, 0.98), sbx.SetpointSchedule(6, 19, (294, 297), (289, 298)), 0.035, 0.03),
+      sbx.WeatherController(275.0, 290.0), sbx.ConstantOccupancy(1.0),
+      start_timestamp=pd.Timestamp("2023-07-06 07:00:00"), solver="gauss_seidel")
+  assert ["vav_" + n for n in b.plans[0].zone_names] == [rh.vavs[z].device_id() for z in coords]
+  assert b.zone_ids == [rh.zone_infos[z].zone_id for z in coords]

@@ -193,22 +193,34 @@ class SetpointSchedule:
 
 
 @functools.cache
-def _us_holidays_of_year(year: int):
-  """US public holidays of one year.  The reference asks the third-party `holidays.US()`
-  (unpinned); it is used when importable.  Otherwise -- it is not in this image -- the federal
-  holidays of pandas' USFederalHolidayCalendar, which is what plain `US()` contains (observed-day
-  rules may differ between versions of either package: the deviation is in this one lookup)."""
+def _us_holidays_package():
+  """`holidays.US()` as the reference uses it (conversion_utils.py:62-70; the object fills in
+  a year's holidays on the first lookup of a date of that year), or None when the package is
+  not installed -- it is not in this image."""
   try:
     import holidays      # pylint: disable=g-import-not-at-top
-    return frozenset(holidays.US(years=year).keys())
+    return holidays.US()
   except ImportError:
-    from pandas.tseries.holiday import USFederalHolidayCalendar      # pylint: disable=g-import-not-at-top
-    cal = USFederalHolidayCalendar()
-    return frozenset(d.date() for d in cal.holidays(start=f"{year}-01-01", end=f"{year}-12-31"))
+    return None
+
+
+@functools.cache
+def _us_federal_holidays_of_year(year: int):
+  """Without the `holidays` package: the federal holidays of pandas' USFederalHolidayCalendar,
+  which is what plain `holidays.US()` contains (observed-day rules may differ between versions
+  of either package: the deviation is confined to this lookup)."""
+  from pandas.tseries.holiday import USFederalHolidayCalendar      # pylint: disable=g-import-not-at-top
+  cal = USFederalHolidayCalendar()
+  return frozenset(d.date() for d in cal.holidays(start=f"{year}-01-01", end=f"{year}-12-31"))
 
 
 def is_work_day(ts: pd.Timestamp) -> bool:
-  return ts.weekday() < 5 and ts.date() not in _us_holidays_of_year(ts.year)
+  if ts.weekday() >= 5:
+    return False
+  cal = _us_holidays_package()
+  if cal is not None:
+    return ts.date() not in cal
+  return ts.date() not in _us_federal_holidays_of_year(ts.year)
 
 
 def time_feature_table(timestamps: Sequence[pd.Timestamp]) -> np.ndarray:

@@ -55,6 +55,7 @@ struct sbx_env {
   size_t resident_smem = 0;
   CUtensorMap tmap_t;            // [B, H, W] temperature field, box [1, H, P] (k_resident_step)
   size_t gs_smem = 0;
+  int gs_global = 0;             // Gauss-Seidel on a grid too large for shared memory: wavefront in global memory
   // k_resident_step2 (persistent, record-driven) when the grid allows it and no plan
   // overflows its list capacities; otherwise k_resident_step
   int v2_capable = 0, use_v2 = 0, v1_allocated = 0;
@@ -571,7 +572,8 @@ int run_resident(sbx_handle h, cudaStream_t st, bool with_header) {
   const Params& p = h->P;
   if (h->cfg.solver == SBX_SOLVER_GAUSS_SEIDEL) {
     if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
-    k_resident_gs<<<p.B, kGsThreads, h->gs_smem, st>>>(p);
+    if (h->gs_global) k_resident_gs<true><<<p.B, kGsGlobalThreads, h->gs_smem, st>>>(p);
+    else k_resident_gs<false><<<p.B, kGsThreads, h->gs_smem, st>>>(p);
     if (int rc = launch_check(h, "k_resident_gs")) return rc;
     return timing_record(h, h->t_solve, h->t_solve_used, st);
   }
@@ -791,24 +793,27 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   int max_optin = 0;
   cudaDeviceGetAttribute(&max_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
   const bool fits = L.total <= max_optin && L.plane_cv / h->V <= 32767;
-  if (c.kernel_path == SBX_PATH_RESIDENT && !fits) {
+  if (c.kernel_path == SBX_PATH_RESIDENT && !fits && c.solver != SBX_SOLVER_GAUSS_SEIDEL) {
     fail(h, SBX_E_INVALID, "resident path needs %d B of shared memory per CTA; device allows %d", L.total, max_optin);
     return bail(SBX_E_INVALID);
   }
   h->path = (c.kernel_path == SBX_PATH_AUTO) ? (fits ? SBX_PATH_RESIDENT : SBX_PATH_STREAMING) : c.kernel_path;
   h->resident_smem = L.total;
   if (c.solver == SBX_SOLVER_GAUSS_SEIDEL) {
-    const GsLayout G = gs_layout((int)N, (int)Z);
-    if (G.total > (size_t)max_optin || c.kernel_path == SBX_PATH_STREAMING) {
-      fail(h, SBX_E_INVALID, "the Gauss-Seidel solver keeps the grid in shared memory: %zu B needed, %d available", G.total, max_optin);
-      return bail(SBX_E_INVALID);
-    }
+    // one CTA per building runs the raster sweep as an anti-diagonal wavefront: on the grid in
+    // shared memory where it fits, else (sim_config_legacy.gin on the 744x1004 plan) on the fp64
+    // field in global memory -- same arithmetic, a parity path
+    GsLayout G = gs_layout((int)N, (int)Z);
+    h->gs_global = (G.total > (size_t)max_optin || c.kernel_path == SBX_PATH_STREAMING) ? 1 : 0;
+    if (h->gs_global) G = gs_layout(0, (int)Z);
     h->path = SBX_PATH_RESIDENT;
     h->gs_smem = G.total;
-    cudaError_t e = cudaFuncSetAttribute(k_resident_gs, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
+    cudaError_t e = h->gs_global
+        ? cudaFuncSetAttribute(k_resident_gs<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total)
+        : cudaFuncSetAttribute(k_resident_gs<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G.total);
     if (e != cudaSuccess) { fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return bail(SBX_E_CUDA); }
   }
-  if (h->path == SBX_PATH_RESIDENT) {
+  if (h->path == SBX_PATH_RESIDENT && c.solver != SBX_SOLVER_GAUSS_SEIDEL) {
     cudaError_t e;
     if (h->V == 4) e = cudaFuncSetAttribute(k_resident_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     else e = cudaFuncSetAttribute(k_resident_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
@@ -918,6 +923,7 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   ALLOC(p.qcv64, double, B * Z);
   ALLOC(p.qcv64_next, double, B * Z);
   if (c.solver == SBX_SOLVER_GAUSS_SEIDEL) ALLOC(p.temp64, double, B * N);
+  if (h->gs_global) ALLOC(p.temp64_prev, double, B * N);
   ALLOC(p.therm_mode, uint8_t, B * Z);
   ALLOC(p.ahu_heat_sp, double, B);
   ALLOC(p.ahu_cool_sp, double, B);

@@ -168,6 +168,7 @@ struct Params {
   double* qcv64;             // same two, fp64 (Gauss-Seidel solver reads fp64 input_q)
   double* qcv64_next;
   double* temp64;            // [B,H,W] fp64 building.temp, Gauss-Seidel solver only
+  double* temp64_prev;       // [B,H,W] previous-step plane of the global-memory Gauss-Seidel wavefront (large grids)
   double threshold64, dt_double, z_double;
   uint8_t* therm_mode;       // [B,Z]
   double* ahu_heat_sp;

@@ -1105,24 +1105,35 @@ __device__ __forceinline__ unsigned gs_neighbor_mask(int cls) {
   }
 }
 
-__global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
+// IN_GLOBAL: grids that do not fit one SM's shared memory (sim_config_legacy.gin runs this solver
+// on the 744x1004 plan) -- the same wavefront, one CTA per building, on the fp64 field in global
+// memory (L2-resident: 6 MB per plane for that plan), in place; the previous-step plane lives
+// in Params::temp64_prev.  A barrier per anti-diagonal makes it a parity path, not a fast one.
+constexpr int kGsGlobalThreads = 1024;
+template <bool IN_GLOBAL>
+__global__ void __launch_bounds__(IN_GLOBAL ? kGsGlobalThreads : kGsThreads) k_resident_gs(const Params p) {
   extern __shared__ __align__(128) unsigned char smem[];
+  constexpr int kGsThreads = IN_GLOBAL ? kGsGlobalThreads : sbx::kGsThreads;     // stride of every loop below
   const int b = blockIdx.x, tid = threadIdx.x;
   const int H = p.H, W = p.W, Z = p.Z, n_cv = H * W;
   const int plan = p.n_plans == 1 ? 0 : b;
-  const GsLayout L = gs_layout(n_cv, Z);
-  double* T = reinterpret_cast<double*>(smem + L.off_t);
-  double* Tp = reinterpret_cast<double*>(smem + L.off_prev);
-  double* qz = reinterpret_cast<double*>(smem + L.off_q);
-  long long* bins = reinterpret_cast<long long*>(smem + L.off_bins);
-  uint16_t* dsc = reinterpret_cast<uint16_t*>(smem + L.off_desc);
+  const GsLayout L = gs_layout(IN_GLOBAL ? 0 : n_cv, Z);
   double* gT = p.temp64 + (size_t)b * n_cv;
   const uint16_t* gD = p.desc + (size_t)plan * n_cv;
+  // (volatile in global memory: every access goes to L2, where the CTA's own earlier stores are)
+  volatile double* T = IN_GLOBAL ? gT : reinterpret_cast<double*>(smem + L.off_t);
+  volatile double* Tp = IN_GLOBAL ? p.temp64_prev + (size_t)b * n_cv : reinterpret_cast<double*>(smem + L.off_prev);
+  double* qz = reinterpret_cast<double*>(smem + L.off_q);
+  long long* bins = reinterpret_cast<long long*>(smem + L.off_bins);
+  uint16_t* dsc_s = reinterpret_cast<uint16_t*>(smem + L.off_desc);
+  const uint16_t* dsc = IN_GLOBAL ? gD : dsc_s;
   for (int i = tid; i < n_cv; i += kGsThreads) {
     const double v = gT[i];
-    T[i] = v;
+    if constexpr (!IN_GLOBAL) {
+      T[i] = v;
+      dsc_s[i] = gD[i];
+    }
     Tp[i] = v;
-    dsc[i] = gD[i];
   }
   for (int i = tid; i <= Z; i += kGsThreads) {
     qz[i] = i < Z ? p.qcv64[(size_t)b * Z + i] : 0.0;
@@ -1225,7 +1236,7 @@ __global__ void __launch_bounds__(kGsThreads) k_resident_gs(const Params p) {
   long long total = 0;
   for (int i = tid; i < n_cv; i += kGsThreads) {
     const double v = T[i];
-    gT[i] = v;
+    if constexpr (!IN_GLOBAL) gT[i] = v;
     g32[i] = (float)v;
     const long long f = to_fix(v);
     total += f;

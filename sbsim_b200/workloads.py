@@ -221,16 +221,16 @@ def synthetic_office_plan(height: int = 744, width: int = 1004, rooms_y: int = 9
 def make_shared_plan_env(plan: floorplan.CompiledPlan, n_envs: int, episode_steps: int = 288,
                          reset_temp_values=None, initial_temp=294.0, weather=None,
                          histogram: bool = True, device: int = 0,
-                         kernel_path: int = sbx.PATH_AUTO, start: str = DEFAULT_START
-                         ) -> sbx.Environment:
+                         kernel_path: int = sbx.PATH_AUTO, start: str = DEFAULT_START,
+                         solver: str = "tf_jacobi", iteration_limit: int = 100) -> sbx.Environment:
   """Config 2: n_envs copies of one plan (descriptor shared, L2-resident)."""
   weather = weather or sbx.WeatherController(283.0, 296.0, convection_coefficient=100.0)
   occ = sbx.StepFunctionOccupancy(pd.Timedelta(9, unit="h"), pd.Timedelta(17, unit="h"),
                                   1.0, 0.1)
   building = sbx.SimulatorBuilding(
       plan, calibrated_hvac(), weather, occ, n_envs=n_envs, time_step_sec=300.0,
-      convergence_threshold=0.1, iteration_limit=100, start_timestamp=pd.Timestamp(start),
-      floor_height_cm=300.0, initial_temp=initial_temp, reset_temp_values=reset_temp_values)
+      convergence_threshold=0.1, iteration_limit=iteration_limit, start_timestamp=pd.Timestamp(start),
+      floor_height_cm=300.0, initial_temp=initial_temp, reset_temp_values=reset_temp_values, solver=solver)
   return sbx.Environment(
       building, calibrated_reward(), sbx.StandardScoreObservationNormalizer(NORMALIZATION),
       calibrated_action_config(), discount_factor=0.9,

@@ -586,3 +586,57 @@ def test_legacy_hvac_on_the_legacy_building_changes_names_not_numbers():
   assert "vav_0_0_zone_air_temperature_sensor" in outs["legacy"][1]
   assert "vav_room_1_zone_air_temperature_sensor" in outs["floor_plan"][1]
   assert outs["legacy"][2][:2] == ["zone_id_(0, 0)", "zone_id_(0, 1)"]
+
+
+def test_gauss_seidel_on_a_grid_larger_than_shared_memory():
+  """SURVEY row a9 at the legacy config's scale (sim_config_legacy.gin:182, 208 runs the
+  Gauss-Seidel simulator on the 744x1004 plan): grids whose fp64 planes do not fit one SM run
+  the same anti-diagonal wavefront on the field in global memory.  136x200 = 27 200 CVs here
+  (the shared-memory variant ends at ~13 k): field bit-identical to the oracle's sequential
+  raster sweep, same sweep count, and a short Environment rollout within 1e-4."""
+  from oracle import gs_solver
+  plan = S.small_plan(136, 200)
+  plan[40, 3:197] = 1
+  plan[3:133, 66] = 1
+  plan[3:133, 131] = 1
+  sc = S.Scenario(floor_plan=plan, buffer_from_walls=2, occupancy="step", start="2023-07-06 08:40:00")
+  cp = sc.compiled()
+  B = 2
+  env = S.make_env(sc, n_envs=B, plans=cp, solver="gauss_seidel")
+  try:
+    env.reset()
+    rng = np.random.default_rng(12)
+    H, W, Z = cp.height, cp.width, env.building.n_zones
+    temp = rng.uniform(289, 295, (B, H, W))
+    qcv = rng.uniform(-20, 200, (B, Z))
+    ambient = rng.uniform(275, 290, B)
+    conv = rng.uniform(10, 60, B)
+    env.handle.upload("temp64", temp)
+    env.handle.upload("q_cv64", qcv)
+    env.handle.fd_step(ambient, conv)
+    got = env.handle.download("temp64", (B, H, W))
+    sweeps = env.handle.download("n_sweeps", (B,))
+    gs = gs_solver.GaussSeidel(S.oracle_plan(cp, sc.floor_height_cm), sc.time_step_sec,
+                               sc.convergence_threshold, sc.iteration_limit)
+    for b in range(B):
+      want, n, _, _ = gs.fd_step(temp[b], _dense_q(cp, qcv[b]), ambient[b], conv[b])
+      assert sweeps[b] == n and n >= 2
+      np.testing.assert_array_equal(got[b], want)
+  finally:
+    env.close()
+  # and through Environment.step: 3 free-running steps against the oracle environment
+  env = S.make_env(sc, n_envs=1, plans=cp, solver="gauss_seidel")
+  try:
+    oracle = S.make_oracle(sc, cp, solver="gs")
+    env.reset()
+    oracle.reset()
+    rng = np.random.default_rng(13)
+    for step in range(3):
+      a = rng.uniform(-1, 1, (1, 2)).astype(np.float32)
+      ts = env.step(a)
+      ots = oracle.step(a[0])
+      np.testing.assert_allclose(ts.observation[0], ots[3], rtol=RTOL, atol=2e-5)
+      np.testing.assert_allclose(ts.reward[0], ots[1], rtol=RTOL, atol=5e-5)
+      assert int(env.handle.download("n_sweeps", (1,))[0]) == oracle.info["n_sweeps"]
+  finally:
+    env.close()

@@ -70,6 +70,8 @@ def parse_args():
                   help="stochastic convection: the office workload runs the shipped model "
                        "(p=1, distance=5, seed=5; sim_config.gin:37-39) in device-RNG mode by "
                        "default, the randomized workload has it off (SURVEY 8d config 3)")
+  ap.add_argument("--zone-means", choices=["exact-integer", "numpy"], default="exact-integer",
+                  help="numpy: SBX_OPT_NUMPY_MEANS, means summed in the order of the reference's np.mean (bit-identical)")
   ap.add_argument("--host-shares", type=int, default=0,
                   help="SBX_OPT_HOST_SHARES override (0 = the library's choice)")
   ap.add_argument("--chunks", type=int, default=0,
@@ -184,7 +186,8 @@ def build_env(args, rank, local_rank):
     env, wl = workloads.make_randomized_env(
         n, seed=2024 + rank, episode_steps=episode, n_layouts=args.layouts,
         histogram=bool(args.histogram), device=local_rank, kernel_path=path,
-        convergence_threshold=args.convergence_threshold, iteration_limit=args.iteration_limit)
+        convergence_threshold=args.convergence_threshold, iteration_limit=args.iteration_limit,
+        numpy_zone_means=args.zone_means == "numpy")
     if args.convection == "device":
       env.handle.set_device_convection(*workloads.CALIBRATED_CONVECTION)
     desc = {"workload": ("SAC rollout: randomized-64x96 buildings, one-day (288-step) episode, actions from a "
@@ -193,7 +196,8 @@ def build_env(args, rank, local_rank):
                          "randomized-64x96 (BASELINE.json configs[3] per-GPU shard)"),
             "envs_per_gpu": n, "grid": [64, 96], "layouts": wl.n_layouts,
             "plans": "per-env descriptor, materials, weather, T0, actions",
-            "stochastic_convection": "device-rng mode" if args.convection == "device" else "off"}
+            "stochastic_convection": "device-rng mode" if args.convection == "device" else "off",
+            "zone_means": args.zone_means}
     return env, wl, desc
   n = args.envs_per_gpu or 4096
   cal = workloads.load_calibrated(CALIBRATED_FIXTURE)
@@ -203,14 +207,16 @@ def build_env(args, rank, local_rank):
           if conv_on else None)
   env = workloads.make_calibrated_env(cal, n, episode_steps=episode,
                                       histogram=bool(args.histogram), device=local_rank,
-                                      kernel_path=path, convection=conv)
+                                      kernel_path=path, convection=conv,
+                                      numpy_zone_means=args.zone_means == "numpy")
   desc = {"workload": "calibrated sb1 building 744x1004 x copies (BASELINE.json configs[1]; "
                       "sim_config.gin:160-196: TF-Jacobi, reset_temps.npy, Moffett replay weather, "
                       "US/Pacific schedule, RandomizedArrivalDepartureOccupancy seed 17321)",
           "envs_per_gpu": n, "grid": [cp.height, cp.width], "zones": cp.n_zones,
           "plans": "one shared descriptor",
           "stochastic_convection": ("device-rng mode, p=1 distance=5 seed=5 (sim_config.gin:37-39): "
-                                    "k_convect_reduce fuses it with the zone reduction") if conv_on else "off"}
+                                    "k_convect_reduce fuses it with the zone reduction") if conv_on else "off",
+          "zone_means": args.zone_means}
   return env, None, desc
 
 

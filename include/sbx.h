@@ -304,6 +304,7 @@ int sbx_host_free(void* p);
 #define SBX_OPT_PIPELINE_CHUNKS 1 /* resident Jacobi path: shares of the batch a step is pipelined over (1 = one launch per kernel) */
 #define SBX_OPT_L2_PREFETCH_DISTANCE 2 /* resident Jacobi path: the CTA of building b prefetches building b + value into L2 (0 = off; default = CTAs in flight) */
 #define SBX_OPT_HOST_SHARES 3 /* sbx_step_host, resident path: shares of the batch stepped one after the other so that a share's device->host copy overlaps the next shares' kernels (0 = the library's choice: 2 for >= 2 MB of outputs, else 1) */
+#define SBX_OPT_NUMPY_MEANS 4 /* 1: zone and grid means summed in the order of the reference's np.mean (float32 pairwise sums over each room's raster-ordered CVs, building.py:845-871) instead of exact integer sums: bit-identical means, hence bit-identical free-running rollouts; TF-Jacobi solver only; costs one more read of the field per step */
 int sbx_set_option(sbx_handle h, int option, int64_t value);
 
 /* Stochastic convection (stochastic_convection_simulator.py:62-145), device-RNG mode: applied

@@ -21,6 +21,7 @@ REWARD_REGRET, REWARD_ENERGY_CARBON = 0, 1
 OPT_PIPELINE_CHUNKS = 1
 OPT_L2_PREFETCH_DISTANCE = 2
 OPT_HOST_SHARES = 3
+OPT_NUMPY_MEANS = 4
 OK = 0
 MAX_ACTIONS = 3
 MAX_HIST_BINS = 32

@@ -19,6 +19,7 @@
 #include <stdlib.h>
 #include <string.h>
 
+#include <algorithm>
 #include <functional>
 #include <new>
 #include <string>
@@ -28,6 +29,7 @@
 #include "sbx_kernels.cuh"
 #include "sbx_resident2.cuh"
 #include "sbx_resident3.cuh"
+#include "sbx_pairwise.cuh"
 
 using namespace sbx;
 
@@ -115,6 +117,8 @@ struct sbx_env {
   cudaEvent_t ev_share[SBX_MAX_CHUNKS] = {};
   unsigned share_seq = 0;
   int host_shares = 0;           // SBX_OPT_HOST_SHARES (0 = the library's choice)
+  int pw_dirty = 1;              // SBX_OPT_NUMPY_MEANS: the per-plan summation trees need (re)building
+  size_t pw_alloc_leaf = 0, pw_alloc_node = 0, pw_alloc_val = 0;   // capacities allocated so far
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_pre[SBX_MAX_CHUNKS] = {}, ev_solve[SBX_MAX_CHUNKS] = {};
   // sbx_timing_begin / sbx_timing_end: CUDA events around every step and every solve launch
@@ -271,6 +275,7 @@ int launch_check(sbx_handle h, const char* what) {
 
 int launch_zone_reduce(sbx_handle h, cudaStream_t st) {
   const Params& p = h->P;
+  if (p.pw_on) return SBX_OK;          // k_post takes the means of k_pw_combine, not these sums
   CUDA_TRY(h, cudaMemsetAsync(p.zone_sum, 0, sizeof(long long) * (size_t)p.B * (p.Z + 1), st));
   const StreamTiling tl = stream_tiling(p.H, p.W, h->V);
   const unsigned grid = (unsigned)((size_t)tl.tiles * p.B);
@@ -321,7 +326,155 @@ int launch_pre(sbx_handle h, cudaStream_t st) {
   return launch_check(h, "k_pre");
 }
 
+// SBX_OPT_NUMPY_MEANS: NumPy's pairwise summation tree (see sbx_pairwise.cuh) of every zone
+// and of the grid, per plan.  Built on the host from the plan's zone bytes -- a counting sort
+// of the CVs by zone in raster order and a recursion whose shape depends on the counts alone.
+struct PwTree {
+  std::vector<uint2> leaf;                 // {start | flag, length}
+  std::vector<uint2> node;                 // {left, right}: leaf index, or ~(node id) before renumbering
+  std::vector<int> height;                 // of every node
+};
+// returns {reference, height}: reference = leaf index >= 0, or ~(node id) < 0
+static std::pair<int, int> pw_build(PwTree& t, uint32_t start, uint32_t n, uint32_t flag) {
+  if (n <= 128) {
+    t.leaf.push_back(make_uint2(start | flag, n));
+    return {(int)t.leaf.size() - 1, 0};
+  }
+  uint32_t n2 = n / 2;
+  n2 -= n2 % 8;
+  const std::pair<int, int> a = pw_build(t, start, n2, flag), b = pw_build(t, start + n2, n - n2, flag);
+  t.node.push_back(make_uint2((uint32_t)a.first, (uint32_t)b.first));
+  const int hgt = 1 + (a.second > b.second ? a.second : b.second);
+  t.height.push_back(hgt);
+  return {~((int)t.node.size() - 1), hgt};
+}
+
+int build_pairwise_tables(sbx_handle h, cudaStream_t st) {
+  Params& p = h->P;
+  const int Z = p.Z, P = p.n_plans;
+  const size_t n_cv = (size_t)p.H * p.W;
+  const bool idx16 = n_cv <= 65536;
+  std::vector<uint16_t> desc((size_t)P * n_cv);
+  CUDA_TRY(h, cudaMemcpyAsync(desc.data(), p.desc, desc.size() * sizeof(uint16_t), cudaMemcpyDeviceToHost, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));
+  std::vector<unsigned char> zlist((size_t)P * n_cv * (idx16 ? 2 : 4), 0);
+  std::vector<PwTree> trees((size_t)P);
+  std::vector<int32_t> meta((size_t)P * kPwMetaInts, 0);
+  std::vector<int2> root((size_t)P * (Z + 1));
+  std::vector<std::vector<uint2>> ordered((size_t)P);
+  size_t capL = 1, capI = 1, cap = 1;
+  std::vector<uint32_t> cnt((size_t)Z + 1), pos((size_t)Z + 1);
+  for (int pl = 0; pl < P; ++pl) {
+    const uint16_t* d = desc.data() + (size_t)pl * n_cv;
+    std::fill(cnt.begin(), cnt.end(), 0u);
+    for (size_t i = 0; i < n_cv; ++i) {
+      const int z = (d[i] >> SBX_DESC_ZONE_SHIFT) & 0xFF;
+      if (z != SBX_ZONE_NONE && z < Z) ++cnt[(size_t)z];
+    }
+    uint32_t o = 0;
+    for (int z = 0; z < Z; ++z) { pos[(size_t)z] = o; o += cnt[(size_t)z]; }
+    unsigned char* zl = zlist.data() + (size_t)pl * n_cv * (idx16 ? 2 : 4);
+    for (size_t i = 0; i < n_cv; ++i) {
+      const int z = (d[i] >> SBX_DESC_ZONE_SHIFT) & 0xFF;
+      if (z == SBX_ZONE_NONE || z >= Z) continue;
+      const uint32_t k = pos[(size_t)z]++;
+      if (idx16) reinterpret_cast<uint16_t*>(zl)[k] = (uint16_t)i;
+      else reinterpret_cast<uint32_t*>(zl)[k] = (uint32_t)i;
+    }
+    PwTree& t = trees[(size_t)pl];
+    std::vector<int> root_ref((size_t)Z + 1);
+    o = 0;
+    for (int z = 0; z < Z; ++z) {
+      root_ref[(size_t)z] = cnt[(size_t)z] ? pw_build(t, o, cnt[(size_t)z], 0u).first : INT32_MIN;
+      o += cnt[(size_t)z];
+    }
+    root_ref[(size_t)Z] = pw_build(t, 0u, (uint32_t)n_cv, kPwGridFlag).first;
+    // inner nodes grouped by height (a node's children are lower): stable counting sort
+    const int L = (int)t.leaf.size(), I = (int)t.node.size();
+    int n_levels = 0;
+    for (int v : t.height) n_levels = v > n_levels ? v : n_levels;
+    if (n_levels + 4 > kPwMetaInts) return fail(h, SBX_E_INVALID, "summation tree of %d levels", n_levels);
+    std::vector<int> lvl_start((size_t)n_levels + 1, 0), newpos((size_t)I);
+    for (int v : t.height) ++lvl_start[(size_t)v];            // height v -> level v - 1, counted at slot v
+    for (int l = 1; l <= n_levels; ++l) lvl_start[(size_t)l] += lvl_start[(size_t)l - 1];
+    // lvl_start[l] = nodes of height <= l; level l - 1 spans [lvl_start[l - 1], lvl_start[l])
+    std::vector<int> fill_at(lvl_start.begin(), lvl_start.end());
+    for (int i = 0; i < I; ++i) newpos[(size_t)i] = fill_at[(size_t)t.height[(size_t)i] - 1]++;
+    auto value_index = [&](int ref) { return ref >= 0 ? ref : L + newpos[(size_t)~ref]; };
+    std::vector<uint2>& ord = ordered[(size_t)pl];
+    ord.resize((size_t)I);
+    for (int i = 0; i < I; ++i)
+      ord[(size_t)newpos[(size_t)i]] = make_uint2((uint32_t)value_index((int)t.node[(size_t)i].x),
+                                                  (uint32_t)value_index((int)t.node[(size_t)i].y));
+    int32_t* m = meta.data() + (size_t)pl * kPwMetaInts;
+    m[0] = L; m[1] = I; m[2] = n_levels;
+    for (int l = 0; l <= n_levels; ++l) m[3 + l] = lvl_start[(size_t)l];
+    for (int z = 0; z <= Z; ++z) {
+      const int ref = root_ref[(size_t)z];
+      root[(size_t)pl * (Z + 1) + z] = ref == INT32_MIN ? make_int2(-1, 0)
+                                                        : make_int2(value_index(ref), z < Z ? (int)cnt[(size_t)z] : (int)n_cv);
+    }
+    capL = (size_t)L > capL ? (size_t)L : capL;
+    capI = (size_t)I > capI ? (size_t)I : capI;
+    cap = (size_t)(L + I) > cap ? (size_t)(L + I) : cap;
+  }
+  // device tables (allocated once; again only when a new plan set needs more room)
+  if (!p.pw_zlist) {
+    unsigned char* z = nullptr; int32_t* mt = nullptr; int2* rt = nullptr; float* mean = nullptr;
+    if (int rc = dev_alloc<unsigned char>(h, &z, zlist.size())) return rc;
+    if (int rc = dev_alloc<int32_t>(h, &mt, meta.size())) return rc;
+    if (int rc = dev_alloc<int2>(h, &rt, root.size())) return rc;
+    if (int rc = dev_alloc<float>(h, &mean, (size_t)p.B * (Z + 1))) return rc;
+    p.pw_zlist = z; p.pw_meta = mt; p.pw_root = rt; p.pw_mean = mean;
+  }
+  if (capL > h->pw_alloc_leaf) {
+    uint2* lf = nullptr;
+    if (int rc = dev_alloc<uint2>(h, &lf, (size_t)P * capL)) return rc;
+    p.pw_leaf = lf; h->pw_alloc_leaf = capL;
+  }
+  if (capI > h->pw_alloc_node) {
+    uint2* nd = nullptr;
+    if (int rc = dev_alloc<uint2>(h, &nd, (size_t)P * capI)) return rc;
+    p.pw_node = nd; h->pw_alloc_node = capI;
+  }
+  if (cap > h->pw_alloc_val) {
+    float* v = nullptr;
+    if (int rc = dev_alloc<float>(h, &v, (size_t)p.B * cap)) return rc;
+    p.pw_val = v; h->pw_alloc_val = cap;
+  }
+  p.pw_capL = (int)h->pw_alloc_leaf; p.pw_capI = (int)h->pw_alloc_node; p.pw_cap = (int)h->pw_alloc_val;
+  std::vector<uint2> leaf_all((size_t)P * p.pw_capL, make_uint2(0u, 0u)), node_all((size_t)P * p.pw_capI, make_uint2(0u, 0u));
+  for (int pl = 0; pl < P; ++pl) {
+    std::copy(trees[(size_t)pl].leaf.begin(), trees[(size_t)pl].leaf.end(), leaf_all.begin() + (size_t)pl * p.pw_capL);
+    std::copy(ordered[(size_t)pl].begin(), ordered[(size_t)pl].end(), node_all.begin() + (size_t)pl * p.pw_capI);
+  }
+  CUDA_TRY(h, cudaMemcpyAsync(const_cast<void*>(p.pw_zlist), zlist.data(), zlist.size(), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(const_cast<int32_t*>(p.pw_meta), meta.data(), meta.size() * sizeof(int32_t), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(const_cast<int2*>(p.pw_root), root.data(), root.size() * sizeof(int2), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(const_cast<uint2*>(p.pw_leaf), leaf_all.data(), leaf_all.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaMemcpyAsync(const_cast<uint2*>(p.pw_node), node_all.data(), node_all.size() * sizeof(uint2), cudaMemcpyHostToDevice, st));
+  CUDA_TRY(h, cudaStreamSynchronize(st));      // the host vectors go out of scope
+  h->pw_dirty = 0;
+  return SBX_OK;
+}
+
+// zone / grid means of buildings [b_begin, b_end) in NumPy's order, into pw_mean
+int launch_pairwise_means(sbx_handle h, cudaStream_t st) {
+  if (h->pw_dirty) if (int rc = build_pairwise_tables(h, st)) return rc;
+  const Params& p = h->P;
+  const long long lanes = (long long)(p.b_end - p.b_begin) * p.pw_capL * 8;
+  const unsigned grid = (unsigned)((lanes + kPwThreads - 1) / kPwThreads);
+  if ((size_t)p.H * p.W <= 65536) k_pw_leaves<uint16_t><<<grid, kPwThreads, 0, st>>>(p);
+  else k_pw_leaves<uint32_t><<<grid, kPwThreads, 0, st>>>(p);
+  if (int rc = launch_check(h, "k_pw_leaves")) return rc;
+  const unsigned nb = (unsigned)(p.b_end - p.b_begin);
+  if (p.pw_capI <= 2048) k_pw_combine<32><<<(nb + kPwThreads / 32 - 1) / (kPwThreads / 32), kPwThreads, 0, st>>>(p);
+  else k_pw_combine<kPwThreads><<<nb, kPwThreads, 0, st>>>(p);
+  return launch_check(h, "k_pw_combine");
+}
+
 int launch_post(sbx_handle h, cudaStream_t st, int is_reset) {
+  if (h->P.pw_on) if (int rc = launch_pairwise_means(h, st)) return rc;
   const Params& p = h->P;
   const int G = hvac_group(h), bpc = 128 / G;
   const unsigned grid = (unsigned)((p.b_end - p.b_begin + bpc - 1) / bpc);
@@ -1158,7 +1311,7 @@ int sbx_upload(sbx_handle h, int field, const void* src, size_t nbytes) {
   if (field == SBX_F_COMFORT) memcpy(h->h_comfort, src, nbytes);
   if (field == SBX_F_OCC_OBS_ZONE) h->P.occ_obs_per_env = 1;
   if (field == SBX_F_OCC_OBS) h->P.occ_obs_per_env = 0;
-  if (field == SBX_F_PLAN_DESC) h->plans_dirty = 1;
+  if (field == SBX_F_PLAN_DESC) { h->plans_dirty = 1; h->pw_dirty = 1; }
   return SBX_OK;
 }
 
@@ -1378,6 +1531,12 @@ int sbx_set_option(sbx_handle h, int option, int64_t value) {
     case SBX_OPT_L2_PREFETCH_DISTANCE:
       if (value < 0 || value > h->cfg.n_envs) return fail(h, SBX_E_INVALID, "SBX_OPT_L2_PREFETCH_DISTANCE must be in [0, n_envs]");
       h->P.prefetch_dist = (int)value;
+      return SBX_OK;
+    case SBX_OPT_NUMPY_MEANS:
+      if (value != 0 && value != 1) return fail(h, SBX_E_INVALID, "SBX_OPT_NUMPY_MEANS must be 0 or 1");
+      if (value && h->cfg.solver != SBX_SOLVER_TF_JACOBI)
+        return fail(h, SBX_E_INVALID, "SBX_OPT_NUMPY_MEANS follows the fp32 field of the TF-Jacobi solver only");
+      h->P.pw_on = (int)value;
       return SBX_OK;
     default:
       return fail(h, SBX_E_INVALID, "unknown option %d", option);

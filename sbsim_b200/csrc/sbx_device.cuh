@@ -185,6 +185,15 @@ struct Params {
   float* max_delta;          // [B] last completed sweep's max
   long long* zone_sum;       // [B,Z+1] integer sums of round((T - zone_ref[b]) * 2^16); slot Z = whole grid
   float* zone_ref;           // [B] reference temperature of those sums
+  // SBX_OPT_NUMPY_MEANS (sbx_pairwise.cuh): means in NumPy's pairwise summation order
+  int pw_on, pw_capL, pw_capI, pw_cap;
+  const void* pw_zlist;      // [P,H*W] u16 / u32: CVs of zone 0, zone 1, .. in raster order
+  const uint2* pw_leaf;      // [P,capL] {start (| kPwGridFlag), length}
+  const uint2* pw_node;      // [P,capI] {left, right} value indices, grouped by height
+  const int32_t* pw_meta;    // [P,kPwMetaInts]
+  const int2* pw_root;       // [P,Z+1] {value index of the tree's root or -1, CVs}
+  float* pw_val;             // [B,pw_cap] leaf sums, then inner nodes
+  float* pw_mean;            // [B,Z+1] zone means, slot Z = grid mean
   uint8_t* active;           // [B]
   int32_t* n_active;         // [1]
   unsigned long long* sweeps_total;  // [1]

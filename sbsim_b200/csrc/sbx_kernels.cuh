@@ -1890,7 +1890,8 @@ __global__ void __launch_bounds__(128, SBX_HVAC_MIN_CTAS) k_post(const Params p,
   const double ref = (double)p.zone_ref[b];
   for (int zi = lane; zi < Z; zi += G) {
     const int n = ncv[zi];
-    const float m = n > 0 ? (float)(ref + from_fix(zs[zi]) / (double)n) : 0.f;
+    const float m = p.pw_on ? p.pw_mean[(size_t)b * (Z + 1) + zi]
+                            : n > 0 ? (float)(ref + from_fix(zs[zi]) / (double)n) : 0.f;
     zpost[zi] = m;
     zpre[zi] = p.pre_zone_mean[(size_t)b * Z + zi];
     p.zone_mean[(size_t)b * Z + zi] = m;
@@ -1899,7 +1900,8 @@ __global__ void __launch_bounds__(128, SBX_HVAC_MIN_CTAS) k_post(const Params p,
       p.qcv64[(size_t)b * Z + zi] = p.qcv64_next[(size_t)b * Z + zi];
     }
   }
-  const float gmean = (float)(ref + from_fix(zs[Z]) / (double)((size_t)p.H * p.W));
+  const float gmean = p.pw_on ? p.pw_mean[(size_t)b * (Z + 1) + Z]
+                              : (float)(ref + from_fix(zs[Z]) / (double)((size_t)p.H * p.W));
   if (lane == 0) p.global_mean[b] = gmean;
   __syncwarp(amask);
   Carry cy = {0, 0, 0, 0, 0};

@@ -169,7 +169,8 @@ class Environment:
                *,
                device: int = 0,
                kernel_path: int = _lib.PATH_AUTO,
-               metrics_env_indices: Sequence[int] = (0,)):
+               metrics_env_indices: Sequence[int] = (0,),
+               numpy_zone_means: bool = False):
     if discount_factor <= 0 or discount_factor > 1:
       raise ValueError("Discount factor must be in (0,1]")   # environment.py:445-446
     if num_hod_features != 1 or num_dow_features != 1:
@@ -349,6 +350,11 @@ class Environment:
     if info.obs_dim != len(names):
       raise RuntimeError(f"observation size mismatch: library {info.obs_dim}, host {len(names)}")
     self.kernel_path = info.kernel_path
+    # Zone / grid means summed in the order of the reference's np.mean (SBX_OPT_NUMPY_MEANS):
+    # bit-identical to building.py:845-871 instead of the exact integer mean a few ulp away.
+    self.numpy_zone_means = bool(numpy_zone_means)
+    if self.numpy_zone_means:
+      self._handle.set_option(_lib.OPT_NUMPY_MEANS, 1)
     self._upload_static()
     self._upload_tables()
     B, D = b.n_envs, len(names)

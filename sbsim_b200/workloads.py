@@ -122,7 +122,7 @@ def randomized(n_envs: int, seed: int = 2024, n_layouts: int = 1024,
 
 def make_randomized_env(n_envs: int, seed: int = 2024, episode_steps: int = 288,
                         n_layouts: int = 1024, histogram: bool = False, device: int = 0,
-                        kernel_path: int = sbx.PATH_AUTO, start: str = DEFAULT_START,
+                        kernel_path: int = sbx.PATH_AUTO, numpy_zone_means: bool = False, start: str = DEFAULT_START,
                         workload: Optional[RandomizedWorkload] = None,
                         convergence_threshold: float = 0.1, iteration_limit: int = 100
                         ) -> Tuple[sbx.Environment, RandomizedWorkload]:
@@ -143,7 +143,7 @@ def make_randomized_env(n_envs: int, seed: int = 2024, episode_steps: int = 288,
       num_days_in_episode=(episode_steps + 0.5) * 300.0 / 86400.0,
       occupancy_normalization_constant=125.0,
       observation_histogram_reducer=sbx.HistogramReducer(HISTOGRAM) if histogram else None,
-      device=device, kernel_path=kernel_path)
+      device=device, kernel_path=kernel_path, numpy_zone_means=numpy_zone_means)
   return env, wl
 
 
@@ -188,7 +188,7 @@ def calibrated_occupancy(kind: str = "randomized"):
 
 def make_calibrated_env(cal: CalibratedBuilding, n_envs: int, episode_steps: int = 288,
                         histogram: bool = True, device: int = 0,
-                        kernel_path: int = sbx.PATH_AUTO, occupancy: str = "randomized",
+                        kernel_path: int = sbx.PATH_AUTO, numpy_zone_means: bool = False, occupancy: str = "randomized",
                         convection=None) -> sbx.Environment:
   """Configs 1/2: n_envs copies of the calibrated building (one shared descriptor),
   Moffett replay weather, reset_temps.npy, schedule in US/Pacific."""
@@ -207,7 +207,7 @@ def make_calibrated_env(cal: CalibratedBuilding, n_envs: int, episode_steps: int
       num_days_in_episode=(episode_steps + 0.5) * 300.0 / 86400.0,
       occupancy_normalization_constant=125.0,
       observation_histogram_reducer=sbx.HistogramReducer(HISTOGRAM) if histogram else None,
-      time_zone=CALIBRATED_TZ, device=device, kernel_path=kernel_path)
+      time_zone=CALIBRATED_TZ, device=device, kernel_path=kernel_path, numpy_zone_means=numpy_zone_means)
 
 
 def synthetic_office_plan(height: int = 744, width: int = 1004, rooms_y: int = 9,
@@ -221,7 +221,7 @@ def synthetic_office_plan(height: int = 744, width: int = 1004, rooms_y: int = 9
 def make_shared_plan_env(plan: floorplan.CompiledPlan, n_envs: int, episode_steps: int = 288,
                          reset_temp_values=None, initial_temp=294.0, weather=None,
                          histogram: bool = True, device: int = 0,
-                         kernel_path: int = sbx.PATH_AUTO, start: str = DEFAULT_START,
+                         kernel_path: int = sbx.PATH_AUTO, numpy_zone_means: bool = False, start: str = DEFAULT_START,
                          solver: str = "tf_jacobi", iteration_limit: int = 100) -> sbx.Environment:
   """Config 2: n_envs copies of one plan (descriptor shared, L2-resident)."""
   weather = weather or sbx.WeatherController(283.0, 296.0, convection_coefficient=100.0)
@@ -237,4 +237,4 @@ def make_shared_plan_env(plan: floorplan.CompiledPlan, n_envs: int, episode_step
       num_days_in_episode=(episode_steps + 0.5) * 300.0 / 86400.0,
       occupancy_normalization_constant=125.0,
       observation_histogram_reducer=sbx.HistogramReducer(HISTOGRAM) if histogram else None,
-      device=device, kernel_path=kernel_path)
+      device=device, kernel_path=kernel_path, numpy_zone_means=numpy_zone_means)

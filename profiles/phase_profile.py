@@ -5,7 +5,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np, torch
 from sbsim_b200 import workloads
 B = 32768
-env, wl = workloads.make_randomized_env(B, episode_steps=64, histogram=True)
+env, wl = workloads.make_randomized_env(B, episode_steps=64, histogram=True,
+                                        numpy_zone_means=bool(int(os.environ.get("PW", "0"))))   # PW=1: SBX_OPT_NUMPY_MEANS
 dev = torch.device("cuda:0")
 D = env.observation_spec().shape[0]
 obs = torch.zeros(B, D, device=dev); rew = torch.zeros(B, device=dev)
@@ -24,8 +25,8 @@ torch.cuda.synchronize()
 raw = env.handle.download("phase_cycles", (W,)).astype(np.float64)
 cyc = raw[:8]
 names = ["prologue (TMA issued)", "wait TMA load", "sweep 1 (+n3)", "sweeps 2..n", "store issue (+gather)",
-         "zone sums (warp 0)", "barrier after sums"]
-tot = cyc[:7].sum()
+         "zone sums (warp 0) / PW: tables staged", "barrier after sums / PW: + leaf sums", "PW: levels + means"]
+tot = cyc[:8].sum()
 for n, c in zip(names, cyc):
   print(f"{n:28s} {c / (B * K):9.0f} cycles/CTA  {100 * c / tot:5.1f}%")
 print(f"total {tot / (B * K):.0f} cycles/CTA = {tot / (B * K) / 1.965e3:.2f} us at 1.965 GHz")

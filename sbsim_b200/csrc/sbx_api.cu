@@ -118,6 +118,7 @@ struct sbx_env {
   unsigned share_seq = 0;
   int host_shares = 0;           // SBX_OPT_HOST_SHARES (0 = the library's choice)
   int pw_dirty = 1;              // SBX_OPT_NUMPY_MEANS: the per-plan summation trees need (re)building
+  int pw_by_solve = 0;           // this step's solve kernel wrote pw_mean itself
   size_t pw_alloc_leaf = 0, pw_alloc_node = 0, pw_alloc_val = 0;   // capacities allocated so far
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   cudaEvent_t ev_pre[SBX_MAX_CHUNKS] = {}, ev_solve[SBX_MAX_CHUNKS] = {};
@@ -362,7 +363,7 @@ int build_pairwise_tables(sbx_handle h, cudaStream_t st) {
   std::vector<int32_t> meta((size_t)P * kPwMetaInts, 0);
   std::vector<int2> root((size_t)P * (Z + 1));
   std::vector<std::vector<uint2>> ordered((size_t)P);
-  size_t capL = 1, capI = 1, cap = 1;
+  size_t capL = 1, capI = 1, cap = 1, zone_cvs = 0;
   std::vector<uint32_t> cnt((size_t)Z + 1), pos((size_t)Z + 1);
   for (int pl = 0; pl < P; ++pl) {
     const uint16_t* d = desc.data() + (size_t)pl * n_cv;
@@ -373,6 +374,7 @@ int build_pairwise_tables(sbx_handle h, cudaStream_t st) {
     }
     uint32_t o = 0;
     for (int z = 0; z < Z; ++z) { pos[(size_t)z] = o; o += cnt[(size_t)z]; }
+    zone_cvs = o > zone_cvs ? o : zone_cvs;
     unsigned char* zl = zlist.data() + (size_t)pl * n_cv * (idx16 ? 2 : 4);
     for (size_t i = 0; i < n_cv; ++i) {
       const int z = (d[i] >> SBX_DESC_ZONE_SHIFT) & 0xFF;
@@ -421,7 +423,7 @@ int build_pairwise_tables(sbx_handle h, cudaStream_t st) {
   // device tables (allocated once; again only when a new plan set needs more room)
   if (!p.pw_zlist) {
     unsigned char* z = nullptr; int32_t* mt = nullptr; int2* rt = nullptr; float* mean = nullptr;
-    if (int rc = dev_alloc<unsigned char>(h, &z, zlist.size())) return rc;
+    if (int rc = dev_alloc<unsigned char>(h, &z, zlist.size() + 16)) return rc;   // + a bulk copy's rounding
     if (int rc = dev_alloc<int32_t>(h, &mt, meta.size())) return rc;
     if (int rc = dev_alloc<int2>(h, &rt, root.size())) return rc;
     if (int rc = dev_alloc<float>(h, &mean, (size_t)p.B * (Z + 1))) return rc;
@@ -443,6 +445,14 @@ int build_pairwise_tables(sbx_handle h, cudaStream_t st) {
     p.pw_val = v; h->pw_alloc_val = cap;
   }
   p.pw_capL = (int)h->pw_alloc_leaf; p.pw_capI = (int)h->pw_alloc_node; p.pw_cap = (int)h->pw_alloc_val;
+  p.pw_zbytes = (uint32_t)((zone_cvs * (idx16 ? 2 : 4) + 15) & ~(size_t)15);
+  // k_resident_step<4, true> keeps leaf sums, inner nodes, the node table and the level offsets in
+  // its idle temperature plane and indexes CVs with 16 bits
+  // (TMA: 16-byte source alignment per plan), and takes the CV list into its zone-sum list region
+  p.pw_fused = (!getenv("SBX_PW_SEPARATE") &&      // developer switch: k_pw_leaves / k_pw_combine on the resident path too
+                h->path == SBX_PATH_RESIDENT && h->V == 4 && idx16 && n_cv % 8 == 0 &&
+                (size_t)p.pw_zbytes <= (size_t)p.geom.rl_cap * 4 &&
+                ((cap + 1) & ~(size_t)1) + 2 * capI + 2 * capL <= (size_t)p.geom.plane_cv) ? 1 : 0;
   std::vector<uint2> leaf_all((size_t)P * p.pw_capL, make_uint2(0u, 0u)), node_all((size_t)P * p.pw_capI, make_uint2(0u, 0u));
   for (int pl = 0; pl < P; ++pl) {
     std::copy(trees[(size_t)pl].leaf.begin(), trees[(size_t)pl].leaf.end(), leaf_all.begin() + (size_t)pl * p.pw_capL);
@@ -474,7 +484,7 @@ int launch_pairwise_means(sbx_handle h, cudaStream_t st) {
 }
 
 int launch_post(sbx_handle h, cudaStream_t st, int is_reset) {
-  if (h->P.pw_on) if (int rc = launch_pairwise_means(h, st)) return rc;
+  if (h->P.pw_on && !(h->pw_by_solve && !is_reset)) if (int rc = launch_pairwise_means(h, st)) return rc;
   const Params& p = h->P;
   const int G = hvac_group(h), bpc = 128 / G;
   const unsigned grid = (unsigned)((p.b_end - p.b_begin + bpc - 1) / bpc);
@@ -750,7 +760,11 @@ int run_resident(sbx_handle h, cudaStream_t st, bool with_header) {
     if (int rc = launch_check(h, "k_resident_step2")) return rc;
     return timing_record(h, h->t_solve, h->t_solve_used, st);
   }
-  if (h->V == 4) k_resident_step<4><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
+  if (p.pw_on && !p.fd_only && h->pw_dirty) if (int rc = build_pairwise_tables(h, st)) return rc;
+  if (h->V == 4 && p.pw_on && p.pw_fused && !p.fd_only) {
+    k_resident_step<4, true><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
+    h->pw_by_solve = 1;            // launch_post need not take the means again
+  } else if (h->V == 4) k_resident_step<4><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
   else k_resident_step<1><<<grid, kResidentThreads, h->resident_smem, st>>>(p, h->tmap_t);
   h->last_resident_kernel = 1;
   if (int rc = launch_check(h, "k_resident_step")) return rc;
@@ -883,6 +897,7 @@ int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_
   if (int rc = timing_record(h, h->t_step, h->t_step_used, st)) return rc;
   p.conv_perm = nullptr;
   h->conv_pending = 0;
+  h->pw_by_solve = 0;
   // host mirror of Thermostat._previous_timestamp (thermostat.py:147) and of the
   // episode counters (environment.py:1313, 1358-1359)
   h->therm_seen = 1;
@@ -968,7 +983,10 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   }
   if (h->path == SBX_PATH_RESIDENT && c.solver != SBX_SOLVER_GAUSS_SEIDEL) {
     cudaError_t e;
-    if (h->V == 4) e = cudaFuncSetAttribute(k_resident_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    if (h->V == 4) {
+      e = cudaFuncSetAttribute(k_resident_step<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+      if (e == cudaSuccess) e = cudaFuncSetAttribute(k_resident_step<4, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    }
     else e = cudaFuncSetAttribute(k_resident_step<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
     if (e != cudaSuccess) { fail(h, SBX_E_CUDA, "cudaFuncSetAttribute failed: %s", cudaGetErrorString(e)); return bail(SBX_E_CUDA); }
     int nb = 0;

@@ -83,6 +83,9 @@ struct Resident3Geom {
 };
 
 // Everything a kernel needs; passed by value.
+constexpr int kPwMetaInts = 40;            // per plan: {L, I, n_levels, level_start[0 .. n_levels]}
+constexpr uint32_t kPwGridFlag = 0x80000000u;
+
 struct Params {
   ResidentGeom geom;
   Resident2Geom g2;
@@ -187,6 +190,8 @@ struct Params {
   float* zone_ref;           // [B] reference temperature of those sums
   // SBX_OPT_NUMPY_MEANS (sbx_pairwise.cuh): means in NumPy's pairwise summation order
   int pw_on, pw_capL, pw_capI, pw_cap;
+  int pw_fused;              // the tables fit the idle plane of k_resident_step: it takes the means itself
+  uint32_t pw_zbytes;        // bytes of a plan's CV list that hold zone CVs (largest plan, 16-byte multiple)
   const void* pw_zlist;      // [P,H*W] u16 / u32: CVs of zone 0, zone 1, .. in raster order
   const uint2* pw_leaf;      // [P,capL] {start (| kPwGridFlag), length}
   const uint2* pw_node;      // [P,capI] {left, right} value indices, grouped by height

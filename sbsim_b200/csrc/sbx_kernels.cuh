@@ -277,6 +277,8 @@ __host__ inline ResidentGeom resident_geom(int H, int W, int Z, int V) {
   g.plane_cv = H * g.P;
   g.pq_magic = 0xFFFFFFFFu / (unsigned)g.Pq + 1u;
   g.rl_cap = reduce_list_capacity(H * wq, Z);
+  // SBX_OPT_NUMPY_MEANS: the same region takes the plan's raster-ordered zone CV list (u16 per CV)
+  if (V == 4 && H * W <= 65536 && g.rl_cap < (H * W / 2 + 7) / 8 * 8) g.rl_cap = (H * W / 2 + 7) / 8 * 8;
   g.desc_stride = (g.plane_cv + 7) & ~7;
   g.list_stride = (H * wq + 7) & ~7;
   // one tensor-map box per plane (box dims <= 256); otherwise one bulk copy per row
@@ -781,7 +783,10 @@ __device__ __forceinline__ float resident_sweep(const float* __restrict__ in, fl
 #define SBX_PHASE(i) do {} while (0)
 #endif
 
-template <int V>
+// PW: SBX_OPT_NUMPY_MEANS with the tables in reach (Params::pw_fused) -- the zone / grid means
+// are taken here, from the field in shared memory, in NumPy's summation order (sbx_pairwise.cuh)
+// instead of the integer zone sums.
+template <int V, bool PW = false>
 __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Params p, const __grid_constant__ CUtensorMap tmap_t) {
   extern __shared__ __align__(128) unsigned char smem[];
 #ifdef SBX_PROFILE_PHASES
@@ -859,7 +864,16 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   }
 
   // ---- stage 1: zero the zone bins while the copies are in flight ---------------
-  for (int i = tid; i < (Z + 1) * (NW + 1); i += NT) bins[i] = 0;
+  if constexpr (PW) {
+    // no integer bins in this variant: their room takes the plan's tree header (sizes, level
+    // offsets) and roots now, so that the means phase does not start with a global round trip
+    int* s_meta = reinterpret_cast<int*>(bins);
+    if (tid < kPwMetaInts) s_meta[tid] = p.pw_meta[(size_t)plan * kPwMetaInts + tid];
+    int2* s_root = reinterpret_cast<int2*>(s_meta + kPwMetaInts);
+    for (int i = tid; i <= Z; i += NT) s_root[i] = p.pw_root[(size_t)plan * (Z + 1) + i];
+  } else {
+    for (int i = tid; i < (Z + 1) * (NW + 1); i += NT) bins[i] = 0;
+  }
   __syncthreads();
   SBX_PHASE(0);   // launch .. TMA issued
   if constexpr (use_tma) mbar_wait(bar, 0);
@@ -867,7 +881,23 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   const float t_inf = scal[0];
   // the zone-sum list is only needed after the sweeps: fetch it behind them
   const int n_chunks = __float_as_int(scal[5]);
-  if (!p.fd_only && n_chunks > 0) {
+  if constexpr (PW) {
+    // the summation tables of this plan are needed after the sweeps: the raster-ordered CV list
+    // comes into the (otherwise unused) zone-sum list region behind them, the leaf and node
+    // tables into L2
+    if (!p.fd_only) {
+      const int* meta = reinterpret_cast<const int*>(bins);
+      if (tid == 0) {
+        mbar_expect_tx(bar + 1, p.pw_zbytes);
+        tma_load_1d(rlist, reinterpret_cast<const uint16_t*>(p.pw_zlist) + (size_t)plan * n_cv, p.pw_zbytes, bar + 1);
+      }
+      const char* lf = reinterpret_cast<const char*>(p.pw_leaf + (size_t)plan * p.pw_capL);
+      const char* nd = reinterpret_cast<const char*>(p.pw_node + (size_t)plan * p.pw_capI);
+      for (int o = tid * 128; o < meta[0] * 8; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(lf + o));
+      for (int o = tid * 128; o < meta[1] * 8; o += NT * 128) asm volatile("prefetch.global.L2 [%0];" ::"l"(nd + o));
+    }
+  }
+  if (!PW && !p.fd_only && n_chunks > 0) {
     const uint32_t* gR = p.rlist + (size_t)plan * L.rl_cap;
     if constexpr (use_tma) {
       if (tid == 0) {
@@ -982,7 +1012,86 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
   if (lane == 0) wmax[warp] = last_lmax;
   long long* wbins = bins + (size_t)(warp + 1) * (Z + 1);   // warp-private bins
   SBX_PHASE(4);   // convection gather (if any), store issued
-  if (!p.fd_only && n_chunks > 0) {
+  if constexpr (PW) {
+    if (!p.fd_only) {
+      // NumPy's pairwise tree over every room's raster-ordered CVs and over the grid (see
+      // sbx_pairwise.cuh: same leaves, same butterfly, same levels), from the field in `in`;
+      // leaf sums, inner nodes and the node table live in the idle plane `out`.
+      const int* meta = reinterpret_cast<const int*>(bins);
+      const int Lf = meta[0], In = meta[1], n_levels = meta[2];
+      float* vals = out;
+      uint2* s_node = reinterpret_cast<uint2*>(out + ((Lf + In + 1) & ~1));
+      uint2* s_leaf = s_node + In;
+      const uint2* gNode = p.pw_node + (size_t)plan * p.pw_capI;
+      const uint2* gLeaf = p.pw_leaf + (size_t)plan * p.pw_capL;
+      for (int i = tid; i < In; i += NT) s_node[i] = gNode[i];
+      for (int i = tid; i < Lf; i += NT) s_leaf[i] = gLeaf[i];
+      const int* s_lvl = meta + 3;
+      if constexpr (use_tma) mbar_wait(bar + 1, 0);
+      __syncthreads();
+      SBX_PHASE(5);   // PW: tables staged
+      const uint16_t* zl0 = reinterpret_cast<const uint16_t*>(rlist);
+      const unsigned wmagic = 0xFFFFFFFFu / (unsigned)W + 1u;     // i / W for i < 2^16
+      const int pad = P - W;
+      for (int g0 = warp * 4; g0 < Lf; g0 += NT / 8) {            // 8 lanes per leaf, warp-uniform trip count
+        const int g = g0 + (lane >> 3), j = lane & 7;
+        const uint2 lf = g < Lf ? s_leaf[g] : make_uint2(0u, 0u);
+        const int m = (int)lf.y;
+        const int main_n = m >= 8 ? (m & ~7) : 0, tail_n = m - main_n;
+        const uint32_t start = lf.x & ~kPwGridFlag;
+        float v[16], tv = 0.f;
+        if (lf.x & kPwGridFlag) {
+#pragma unroll
+          for (int k = 0; k < 16; ++k) {
+            const uint32_t i = start + (uint32_t)(j + 8 * k);
+            v[k] = j + 8 * k < main_n ? in[i + __umulhi(i, wmagic) * pad] : 0.f;
+          }
+          if (j < tail_n) {
+            const uint32_t i = start + (uint32_t)(main_n + j);
+            tv = in[i + __umulhi(i, wmagic) * pad];
+          }
+        } else {
+          const uint16_t* zl = zl0 + start;
+          uint32_t ix[16], it = 0u;
+#pragma unroll
+          for (int k = 0; k < 16; ++k) ix[k] = j + 8 * k < main_n ? (uint32_t)zl[j + 8 * k] : 0u;
+          if (j < tail_n) it = (uint32_t)zl[main_n + j];
+#pragma unroll
+          for (int k = 0; k < 16; ++k) v[k] = j + 8 * k < main_n ? in[ix[k] + __umulhi(ix[k], wmagic) * pad] : 0.f;
+          if (j < tail_n) tv = in[it + __umulhi(it, wmagic) * pad];
+        }
+        float res = v[0];
+#pragma unroll
+        for (int k = 1; k < 16; ++k)
+          if (j + 8 * k < main_n) res = __fadd_rn(res, v[k]);
+        res = __fadd_rn(res, __shfl_xor_sync(0xffffffffu, res, 1));
+        res = __fadd_rn(res, __shfl_xor_sync(0xffffffffu, res, 2));
+        res = __fadd_rn(res, __shfl_xor_sync(0xffffffffu, res, 4));
+#pragma unroll
+        for (int k = 0; k < 7; ++k) {
+          const float x = __shfl_sync(0xffffffffu, tv, (lane & ~7) + k);
+          if (k < tail_n) res = __fadd_rn(res, x);
+        }
+        if (g < Lf && j == 0) vals[g] = res;
+      }
+      __syncthreads();
+      SBX_PHASE(6);   // PW: leaf sums
+      for (int lv = 0; lv < n_levels; ++lv) {
+        const int i1 = s_lvl[lv + 1];
+        for (int i = s_lvl[lv] + tid; i < i1; i += NT) {
+          const uint2 nd = s_node[i];
+          vals[Lf + i] = __fadd_rn(vals[nd.x], vals[nd.y]);
+        }
+        __syncthreads();
+      }
+      const int2* root = reinterpret_cast<const int2*>(meta + kPwMetaInts);
+      for (int z = tid; z <= Z; z += NT) {
+        const int2 r = root[z];
+        p.pw_mean[(size_t)b * (Z + 1) + z] = r.x >= 0 ? __fdiv_rn(vals[r.x], (float)r.y) : 0.f;
+      }
+      SBX_PHASE(7);   // PW: levels + means
+    }
+  } else if (!p.fd_only && n_chunks > 0) {
     // Zone sums from the zone-grouped list: a warp's 32 entries belong to one zone,
     // so the warp reduces its lanes' integers with exact hardware REDUX and the
     // running sum of zone z lives in a REGISTER of lane z mod 32; shared memory is
@@ -1039,7 +1148,7 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
     p.max_delta[b] = md;
     if (!p.fd_only) atomicAdd(p.sweeps_total, (unsigned long long)k);
   }
-  if (!p.fd_only) {
+  if (!PW && !p.fd_only) {
     // combine the warp-private bins (integer sums: exact, order-free), handed to
     // k_post through zone_sum[b, 0..Z]
     long long* zs = p.zone_sum + (size_t)b * (Z + 1);

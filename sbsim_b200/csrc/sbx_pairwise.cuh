@@ -28,8 +28,7 @@
 
 namespace sbx {
 
-constexpr int kPwMetaInts = 40;            // {L, I, n_levels, level_start[0 .. n_levels]}
-constexpr uint32_t kPwGridFlag = 0x80000000u;
+// kPwMetaInts, kPwGridFlag: sbx_device.cuh (k_resident_step<V, true> walks the same tables)
 constexpr int kPwThreads = 256;
 
 template <typename IDX>

@@ -71,19 +71,28 @@ def _check_means(env, plans, B, H, W):
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("path", ["streaming", "resident"])
-def test_means_are_np_mean_of_the_field_bit_for_bit(path):
+@pytest.mark.parametrize("path", ["streaming", "resident", "resident-separate"])
+def test_means_are_np_mean_of_the_field_bit_for_bit(path, monkeypatch):
+  """resident: k_resident_step<4, true> takes the means itself from the field in shared memory
+  (3 launches per step: k_pre, the solve, k_post); resident-separate (SBX_PW_SEPARATE=1) and
+  streaming: k_pw_leaves + k_pw_combine on the field in global memory."""
+  monkeypatch.delenv("SBX_PW_SEPARATE", raising=False)
+  if path == "resident-separate":
+    monkeypatch.setenv("SBX_PW_SEPARATE", "1")
   B = 6
   wl = workloads.randomized(B, seed=5, n_layouts=B)
   env, _ = workloads.make_randomized_env(
       B, workload=wl, episode_steps=16, histogram=True, numpy_zone_means=True,
-      kernel_path=sbx.PATH_RESIDENT if path == "resident" else sbx.PATH_STREAMING)
+      kernel_path=sbx.PATH_STREAMING if path == "streaming" else sbx.PATH_RESIDENT)
   try:
     env.reset()
     _check_means(env, wl.plans, B, 64, 96)
     rng = np.random.default_rng(9)
-    for _ in range(4):
+    for step in range(4):
+      n0 = env.handle.info().kernel_launches
       env.step(rng.uniform(-1, 1, (B, 2)).astype(np.float32))
+      if path != "streaming" and step > 0:       # the first step also prepares the plans
+        assert env.handle.info().kernel_launches - n0 == (3 if path == "resident" else 5)
       _check_means(env, wl.plans, B, 64, 96)
   finally:
     env.close()

@@ -282,7 +282,12 @@ int sbx_step(sbx_handle h, const float* action, float* obs, float* reward,
 
 /* Same calls with HOST pointers: host->device copy of the actions, the step,
  * device->host copies of the outputs, one synchronisation.  Page-locked caller
- * buffers (sbx_host_alloc) are used directly, pageable ones are staged. */
+ * buffers (sbx_host_alloc) are used directly, pageable ones are staged.
+ * sbx_step_host checks the actions like BoundedActionNormalizer.setpoint_value
+ * (bounded_action_normalizer.py:84-90): a value outside [-1, 1] (tolerance 1e-5)
+ * or NaN returns SBX_E_INVALID ("agent_action: <v> not within bounds [-1.0, 1.0]")
+ * before anything is stepped.  (sbx_step takes device pointers and does not look
+ * at the values: its caller owns the policy's squashing.) */
 int sbx_reset_host(sbx_handle h, float* obs, float* reward, int32_t* step_type,
                    float* discount);
 int sbx_step_host(sbx_handle h, const float* action, float* obs, float* reward,

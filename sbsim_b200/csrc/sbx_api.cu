@@ -849,6 +849,8 @@ int do_step(sbx_handle h, const float* action, float* obs, float* reward, int32_
     if (after_share) if (int rc = after_share(0, p.B)) return rc;
   } else if (jacobi_resident && shares > 1) {
     const int n = shares < p.B ? shares : p.B;
+    // (uneven shares -- a smaller last share, whose copy is the exposed one -- measured the same:
+    // 60 / 70 / 80 % first share: 26.1 / 26.4 / 26.6 M env-steps/s end to end against 26.3 M)
     for (int c = 0; c < n; ++c) {
       p.b_begin = (int)((int64_t)p.B * c / n);
       p.b_end = (int)((int64_t)p.B * (c + 1) / n);
@@ -1447,6 +1449,20 @@ int sbx_step_host(sbx_handle h, const float* action, float* obs, float* reward, 
   const int A = h->cfg.n_actions;
   if (A > 0) {
     if (!action) return fail(h, SBX_E_INVALID, "action is NULL");
+    // BoundedActionNormalizer.setpoint_value (bounded_action_normalizer.py:84-90): an agent
+    // action outside [-1, 1] (tolerance 1e-5) is an error, NaN included; one pass over the batch
+    {
+      const float lim = 1.0f + 1e-5f;
+      const size_t n = B * (size_t)A;
+      int bad = 0;
+      for (size_t i = 0; i < n; ++i) bad |= !(fabsf(action[i]) <= lim);
+      if (bad) {
+        size_t i = 0;
+        while (fabsf(action[i]) <= lim) ++i;
+        return fail(h, SBX_E_INVALID, "agent_action: %.9g not within bounds [-1.0, 1.0] (env %zu, action %zu)",
+                    (double)action[i], i / (size_t)A, i % (size_t)A);
+      }
+    }
     const float* src = action;
     if (!is_pinned(action)) {
       memcpy(h->h_action, action, sizeof(float) * B * A);

@@ -554,12 +554,15 @@ class Environment:
     want = (self.batch_size, len(self._action_names))
     if a.shape != want:
       raise ValueError(f"action shape {a.shape} != {want}")
-    tol = config_lib.ACTION_TOLERANCE
-    # one pass over the batch on the fast path (NaN fails the comparison too)
-    if a.size and not (np.abs(a).max() <= 1.0 + tol):
-      bad = a[(a < -1.0 - tol) | (a > 1.0 + tol) | np.isnan(a)][0]
-      raise ValueError(f"agent_action: {bad} not within bounds [-1.0, 1.0]")  # bounded_action_normalizer.py:84-90
     return a
+
+  @staticmethod
+  def _raise_action_bounds(a: np.ndarray):
+    """bounded_action_normalizer.py:84-90; the range check itself runs inside sbx_step_host (one
+    pass in C before anything is stepped), this formats the reference's error."""
+    tol = config_lib.ACTION_TOLERANCE
+    bad = a[(a < -1.0 - tol) | (a > 1.0 + tol) | np.isnan(a)][0]
+    raise ValueError(f"agent_action: {bad} not within bounds [-1.0, 1.0]")
 
   def step(self, action) -> specs.TimeStep:
     """Environment._step (environment.py:1228-1360) for every env.
@@ -572,11 +575,20 @@ class Environment:
     if self._episode_ended:                   # environment.py:1252-1253
       return self.reset()
     a = self._validate_action(action)
-    self._upload_convection()
-    pa = self._pinned_action.array
-    if a.size:
-      pa[...] = a
-    self._handle.step_host(pa, self._obs, self._reward, self._step_type, self._discount)
+    if self._conv is not None:
+      # the host-drawn convection permutation advances the reference's generators: actions that
+      # will be refused must not get that far
+      tol = config_lib.ACTION_TOLERANCE
+      if a.size and not (np.abs(a).max() <= 1.0 + tol):
+        self._raise_action_bounds(a)
+      self._upload_convection()
+    try:      # pageable actions are staged by the library; it also checks their bounds
+      self._handle.step_host(a if a.size else self._pinned_action.array,
+                             self._obs, self._reward, self._step_type, self._discount)
+    except _lib.SbxLibraryError as e:
+      if "not within bounds" in str(e):
+        self._raise_action_bounds(a)
+      raise
     ended = self._step_count >= self._num_timesteps_in_episode
     self._episode_ended = ended
     if not ended:

@@ -305,6 +305,13 @@ def test_action_out_of_bounds_raises():
     with pytest.raises(ValueError, match="not within bounds"):
       env.step(np.array([[0.0, 1.5], [0.0, 0.0]], dtype=np.float32))
     env.step(np.array([[1.0 + 5e-6, -1.0], [0.0, 0.0]], dtype=np.float32))  # inside the 1e-5 tolerance
+    # the check lives in the C ABI (sbx_step_host): a non-Python caller gets SBX_E_INVALID with the
+    # reference's message, and nothing has been stepped
+    before = env.handle.download("episode", (4,)).copy()
+    bad = np.array([[0.0, np.nan], [0.0, 0.0]], dtype=np.float32)
+    with pytest.raises(_lib.SbxLibraryError, match="not within bounds"):
+      env.handle.step_host(bad, env._obs, env._reward, env._step_type, env._discount)
+    np.testing.assert_array_equal(env.handle.download("episode", (4,)), before)
     with pytest.raises(ValueError, match="action shape"):
       env.step(np.zeros((2, 3), dtype=np.float32))
   finally:

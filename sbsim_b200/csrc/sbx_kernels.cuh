@@ -1076,7 +1076,11 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
       }
       __syncthreads();
       SBX_PHASE(6);   // PW: leaf sums
-      for (int lv = 0; lv < n_levels; ++lv) {
+      // inner nodes height by height: the CTA while a level has more than a warp's worth of
+      // nodes (a level never has more nodes than the one below), then warp 0 alone -- no block
+      // barrier for the upper levels, the roots and the means
+      int lv = 0;
+      for (; lv < n_levels && s_lvl[lv + 1] - s_lvl[lv] > 32; ++lv) {
         const int i1 = s_lvl[lv + 1];
         for (int i = s_lvl[lv] + tid; i < i1; i += NT) {
           const uint2 nd = s_node[i];
@@ -1084,10 +1088,20 @@ __global__ void __launch_bounds__(kResidentThreads, 2) k_resident_step(const Par
         }
         __syncthreads();
       }
-      const int2* root = reinterpret_cast<const int2*>(meta + kPwMetaInts);
-      for (int z = tid; z <= Z; z += NT) {
-        const int2 r = root[z];
-        p.pw_mean[(size_t)b * (Z + 1) + z] = r.x >= 0 ? __fdiv_rn(vals[r.x], (float)r.y) : 0.f;
+      if (warp == 0) {
+        for (; lv < n_levels; ++lv) {
+          const int i = s_lvl[lv] + lane;
+          if (i < s_lvl[lv + 1]) {
+            const uint2 nd = s_node[i];
+            vals[Lf + i] = __fadd_rn(vals[nd.x], vals[nd.y]);
+          }
+          __syncwarp();
+        }
+        const int2* root = reinterpret_cast<const int2*>(meta + kPwMetaInts);
+        for (int z = lane; z <= Z; z += 32) {
+          const int2 r = root[z];
+          p.pw_mean[(size_t)b * (Z + 1) + z] = r.x >= 0 ? __fdiv_rn(vals[r.x], (float)r.y) : 0.f;
+        }
       }
       SBX_PHASE(7);   // PW: levels + means
     }

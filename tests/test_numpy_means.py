@@ -149,6 +149,33 @@ def test_free_running_rollout_against_the_oracle(path):
 
 
 @pytest.mark.gpu
+@pytest.mark.parametrize("path", ["streaming", "resident"])
+@pytest.mark.parametrize("plan_name", ["small_24x34", "odd_23x31", "tf_test_10x9"])
+def test_means_on_shared_plans_with_scalar_vectors(path, plan_name):
+  """One plan for the whole batch; widths that are not a multiple of 4 (one CV per vector,
+  k_resident_step<1>: the resident path runs the separate kernels), with stochastic convection
+  replayed on top for the 24x34 plan (the means are taken after the swaps)."""
+  import scenarios as S
+  plan, bfw = {"small_24x34": (S.small_plan(), 2), "odd_23x31": (S.small_plan(23, 31), 2),
+               "tf_test_10x9": (S.TF_TEST_PLAN, 0)}[plan_name]
+  sc = S.Scenario(floor_plan=plan, buffer_from_walls=bfw, cv_size_cm=20.0,
+                  convection=(0.3, 2, 11) if plan_name == "small_24x34" else None)
+  cp = sc.compiled()
+  B = 3
+  env = S.make_env(sc, n_envs=B, plans=cp, numpy_zone_means=True,
+                   kernel_path=sbx.PATH_RESIDENT if path == "resident" else sbx.PATH_STREAMING)
+  try:
+    env.reset()
+    _check_means(env, cp, B, cp.height, cp.width)
+    rng = np.random.default_rng(2)
+    for _ in range(3):
+      env.step(rng.uniform(-1, 1, (B, 2)).astype(np.float32))
+      _check_means(env, cp, B, cp.height, cp.width)
+  finally:
+    env.close()
+
+
+@pytest.mark.gpu
 def test_means_on_the_calibrated_building():
   """744x1004, 126 zones, one shared plan (u32 CV list, 8192 grid leaves, 13 levels)."""
   cal = workloads.load_calibrated(os.path.join(GOLD, "sb1_calibrated.npz"))

@@ -274,6 +274,10 @@ int launch_check(sbx_handle h, const char* what) {
   return SBX_OK;
 }
 
+static bool step_has_convection(const Params& p) {
+  return !p.fd_only && (p.conv_perm != nullptr || p.conv_p > 0.0);
+}
+
 int launch_zone_reduce(sbx_handle h, cudaStream_t st) {
   const Params& p = h->P;
   if (p.pw_on) return SBX_OK;          // k_post takes the means of k_pw_combine, not these sums
@@ -494,70 +498,64 @@ int launch_post(sbx_handle h, cudaStream_t st, int is_reset) {
   return launch_check(h, "k_post");
 }
 
-template <int V>
+template <int V, int MODE>
 void* sweep_kernel_for(int rows_per_warp) {
   switch (rows_per_warp) {
-    case 8: return (void*)k_sweep<V, 8>;
-    case 16: return (void*)k_sweep<V, 16>;
-    case 32: return (void*)k_sweep<V, 32>;
-    case 48: return (void*)k_sweep<V, 48>;
-    default: return (void*)k_sweep<V, 64>;
+    case 8: return (void*)k_sweep<V, 8, MODE>;
+    case 16: return (void*)k_sweep<V, 16, MODE>;
+    case 32: return (void*)k_sweep<V, 32, MODE>;
+    case 48: return (void*)k_sweep<V, 48, MODE>;
+    default: return (void*)k_sweep<V, 64, MODE>;
   }
 }
+// mode 0: a sweep k >= 2; 1: the first sweep
+void* sweep_kernel(int V, int rows_per_warp, int mode) {
+  if (V == 4) return mode == 0 ? sweep_kernel_for<4, 0>(rows_per_warp) : sweep_kernel_for<4, 1>(rows_per_warp);
+  return mode == 0 ? sweep_kernel_for<1, 0>(rows_per_warp) : sweep_kernel_for<1, 1>(rows_per_warp);
+}
 
-// The sweep loop of the streaming path as a graph: k_loop_begin ->
-// WHILE(handle) { k_sweep(k on the device) -> k_check_loop(sets the handle) }.  Built once per
-// handle and mode; the kernels read everything that changes from step to step from device
-// memory (solve header, active flags, buffer rotation), so the baked-in Params stay valid.
+// The sweep loop of the streaming path as a graph: k_loop_begin -> first sweep -> k_check_loop
+// (sets the handle) -> WHILE(handle) { k_sweep(k on the device) -> k_check_loop(sets the handle) }.
+// Built once per handle and mode (0: a step, 1: solve only); the kernels read everything that changes from step to step from device memory
+// (solve header, active flags, buffer rotation), so the baked-in Params stay valid.
 int build_sweep_graph(sbx_handle h, int which) {
   Params p = h->P;                       // snapshot: fd_only is part of it
   cudaGraph_t g = nullptr;
   cudaError_t e = cudaGraphCreate(&g, 0);
   if (e != cudaSuccess) return fail(h, SBX_E_CUDA, "cudaGraphCreate failed: %s", cudaGetErrorString(e));
-  cudaGraphNode_t prev = nullptr, node = nullptr;
-  const int k_dev = 0;
-  {
-    void* args[] = {&p};
-    cudaKernelNodeParams kp;
-    memset(&kp, 0, sizeof(kp));
-    kp.func = (void*)k_loop_begin; kp.gridDim = dim3((unsigned)((p.B + 255) / 256)); kp.blockDim = dim3(256);
-    kp.kernelParams = args;
-    e = cudaGraphAddKernelNode(&node, g, prev ? &prev : nullptr, prev ? 1 : 0, &kp);
-    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphAddKernelNode failed: %s", cudaGetErrorString(e)); }
-    prev = node;
-  }
+  const StreamTiling tl = stream_tiling(p.H, p.W, h->V);
   cudaGraphConditionalHandle handle;
   e = cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault);
   if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphConditionalHandleCreate failed: %s", cudaGetErrorString(e)); }
+  auto add_kernel = [&](cudaGraph_t where, cudaGraphNode_t* dep, void* func, dim3 grid, dim3 block, void** args,
+                        cudaGraphNode_t* out) -> cudaError_t {
+    cudaKernelNodeParams kp;
+    memset(&kp, 0, sizeof(kp));
+    kp.func = func; kp.gridDim = grid; kp.blockDim = block; kp.kernelParams = args;
+    return cudaGraphAddKernelNode(out, where, dep, dep ? 1 : 0, &kp);
+  };
+  const dim3 sweep_grid((unsigned)((size_t)tl.tiles * p.B));
+  int k_first = 1, k_dev = 0;
+  cudaGraphNode_t n_begin = nullptr, n_first = nullptr, n_check1 = nullptr, n_while = nullptr, n_sweep = nullptr, n_check = nullptr;
+  void* a_begin[] = {&p};
+  void* a_first[] = {&p, &k_first};
+  void* a_check[] = {&p, &handle};
+  void* a_sweep[] = {&p, &k_dev};
+  e = add_kernel(g, nullptr, (void*)k_loop_begin, dim3((unsigned)((p.B + 255) / 256)), dim3(256), a_begin, &n_begin);
+  if (e == cudaSuccess)
+    e = add_kernel(g, &n_begin, sweep_kernel(h->V, tl.rows_per_warp, 1), sweep_grid, dim3(kStreamThreads), a_first, &n_first);
+  if (e == cudaSuccess) e = add_kernel(g, &n_first, (void*)k_check_loop, dim3(1), dim3(1024), a_check, &n_check1);
+  if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphAddKernelNode failed: %s", cudaGetErrorString(e)); }
   cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
   cp.conditional.handle = handle;
   cp.conditional.type = cudaGraphCondTypeWhile;
   cp.conditional.size = 1;
-  e = cudaGraphAddNode(&node, g, &prev, 1, &cp);
+  e = cudaGraphAddNode(&n_while, g, &n_check1, 1, &cp);
   if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "conditional graph node failed: %s", cudaGetErrorString(e)); }
   cudaGraph_t body = cp.conditional.phGraph_out[0];
-  const StreamTiling tl = stream_tiling(p.H, p.W, h->V);
-  cudaGraphNode_t n_sweep = nullptr, n_check = nullptr;
-  {
-    int k_arg = k_dev;
-    void* args[] = {&p, &k_arg};
-    cudaKernelNodeParams kp;
-    memset(&kp, 0, sizeof(kp));
-    kp.func = h->V == 4 ? sweep_kernel_for<4>(tl.rows_per_warp) : sweep_kernel_for<1>(tl.rows_per_warp);
-    kp.gridDim = dim3((unsigned)((size_t)tl.tiles * p.B)); kp.blockDim = dim3(kStreamThreads);
-    kp.kernelParams = args;
-    e = cudaGraphAddKernelNode(&n_sweep, body, nullptr, 0, &kp);
-    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphAddKernelNode(k_sweep) failed: %s", cudaGetErrorString(e)); }
-  }
-  {
-    void* args[] = {&p, &handle};
-    cudaKernelNodeParams kp;
-    memset(&kp, 0, sizeof(kp));
-    kp.func = (void*)k_check_loop; kp.gridDim = dim3(1); kp.blockDim = dim3(1024);
-    kp.kernelParams = args;
-    e = cudaGraphAddKernelNode(&n_check, body, &n_sweep, 1, &kp);
-    if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphAddKernelNode(k_check_loop) failed: %s", cudaGetErrorString(e)); }
-  }
+  e = add_kernel(body, nullptr, sweep_kernel(h->V, tl.rows_per_warp, 0), sweep_grid, dim3(kStreamThreads), a_sweep, &n_sweep);
+  if (e == cudaSuccess) e = add_kernel(body, &n_sweep, (void*)k_check_loop, dim3(1), dim3(1024), a_check, &n_check);
+  if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphAddKernelNode (loop body) failed: %s", cudaGetErrorString(e)); }
   cudaGraphExec_t ex = nullptr;
   e = cudaGraphInstantiate(&ex, g, 0);
   if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphInstantiate failed: %s", cudaGetErrorString(e)); }
@@ -597,20 +595,11 @@ int run_stream_sweeps(sbx_handle h, cudaStream_t st) {
   for (int k = 1; k <= p.iteration_limit; ++k) {
     if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
     {
-#define SBX_SWEEP_CASE(R)                                                          \
-  case R:                                                                          \
-    if (h->V == 4) k_sweep<4, R><<<grid, kStreamThreads, 0, st>>>(p, k);           \
-    else k_sweep<1, R><<<grid, kStreamThreads, 0, st>>>(p, k);                     \
-    break
-      switch (tl.rows_per_warp) {
-        SBX_SWEEP_CASE(8);
-        SBX_SWEEP_CASE(16);
-        SBX_SWEEP_CASE(32);
-        SBX_SWEEP_CASE(48);
-        default:
-          SBX_SWEEP_CASE(64);
-      }
-#undef SBX_SWEEP_CASE
+      Params pk = p;
+      int kk = k;
+      void* args[] = {&pk, &kk};
+      CUDA_TRY(h, cudaLaunchKernel(sweep_kernel(h->V, tl.rows_per_warp, k > 1 ? 0 : 1),
+                                   dim3(grid), dim3(kStreamThreads), args, 0, st));
     }
     if (int rc = launch_check(h, "k_sweep")) return rc;
     if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
@@ -666,9 +655,6 @@ int ensure_v1_buffers(sbx_handle h) {
   return SBX_OK;
 }
 
-static bool step_has_convection(const Params& p) {
-  return !p.fd_only && (p.conv_perm != nullptr || p.conv_p > 0.0);
-}
 
 int prepare_plans(sbx_handle h, cudaStream_t st) {
   Params& p = h->P;

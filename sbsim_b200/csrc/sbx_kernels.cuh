@@ -1425,11 +1425,17 @@ __global__ void k_pack_stream(const Params p) {
 // One Jacobi sweep of every still-active building.  Sweep index k is 1-based.
 // Every class of CV runs the same instruction stream (cv_update_packed): warps that
 // mix interior / wall / boundary / exterior CVs do not diverge.
-template <int V, int R>
+// MODE 0: a sweep k >= 2 (k from the host, or from the device in the graph loop); MODE 1: the
+// first sweep (T_est is T_prev: one load serves both) -- a compile-time split: the sweeps of the
+// loop carry neither the first sweep's branches nor its registers (7.7 instead of 8.1 ms per
+// step's sweeps on 4096 x 744x1004).  (MODE 2, a first sweep that also took the zone sums so that
+// buildings converging with it could skip k_zone_reduce, was measured: the ~55 extra instructions
+// per vector cost the first sweep 2.4 ms and saved 2.9 ms of reduction -- 11.1 -> 10.9 ms; removed.)
+template <int V, int R, int MODE>
 __global__ void __launch_bounds__(kStreamThreads, SBX_SWEEP_MIN_CTAS) k_sweep(const Params p, const int k_arg) {
   __shared__ __align__(16) Combo tab[kNumCombos];
   __shared__ float qcv[kMaxZones + 1];
-  const int k = k_arg > 0 ? k_arg : *p.sweep_k;        // device-driven loop: the sweep index lives on the device
+  const int k = MODE != 0 ? 1 : (k_arg > 0 ? k_arg : *p.sweep_k);   // device-driven loop: the sweep index lives on the device
   const StreamTiling tl = stream_tiling(p.H, p.W, V);
   const int b = blockIdx.x / tl.tiles;
   if (!p.active[b]) return;
@@ -1456,7 +1462,7 @@ __global__ void __launch_bounds__(kStreamThreads, SBX_SWEEP_MIN_CTAS) k_sweep(co
   const int cur = p.cur[b];
   int bi, bo;
   sweep_buffers(cur, k, bi, bo);
-  const bool first = k == 1;            // T_est is T_prev itself: one load serves both
+  constexpr bool first = MODE != 0;     // T_est is T_prev itself: one load serves both
   const float* __restrict__ tin = p.tbuf[bi] + (size_t)b * n_cv;
   const float* __restrict__ tprev = p.tbuf[cur] + (size_t)b * n_cv;
   float* __restrict__ tout = p.tbuf[bo] + (size_t)b * n_cv;

@@ -455,7 +455,7 @@ int build_pairwise_tables(sbx_handle h, cudaStream_t st) {
   // (TMA: 16-byte source alignment per plan), and takes the CV list into its zone-sum list region
   p.pw_fused = (!getenv("SBX_PW_SEPARATE") &&      // developer switch: k_pw_leaves / k_pw_combine on the resident path too
                 h->path == SBX_PATH_RESIDENT && h->V == 4 && idx16 && n_cv % 8 == 0 &&
-                (size_t)p.pw_zbytes <= (size_t)p.geom.rl_cap * 4 &&
+                p.pw_zbytes > 0 && (size_t)p.pw_zbytes <= (size_t)p.geom.rl_cap * 4 &&
                 ((cap + 1) & ~(size_t)1) + 2 * capI + 2 * capL <= (size_t)p.geom.plane_cv) ? 1 : 0;
   std::vector<uint2> leaf_all((size_t)P * p.pw_capL, make_uint2(0u, 0u)), node_all((size_t)P * p.pw_capI, make_uint2(0u, 0u));
   for (int pl = 0; pl < P; ++pl) {

@@ -30,6 +30,7 @@
 #include "sbx_resident2.cuh"
 #include "sbx_resident3.cuh"
 #include "sbx_pairwise.cuh"
+#include "sbx_sweep_tma.cuh"
 
 using namespace sbx;
 
@@ -117,6 +118,8 @@ struct sbx_env {
   cudaEvent_t ev_share[SBX_MAX_CHUNKS] = {};
   unsigned share_seq = 0;
   int host_shares = 0;           // SBX_OPT_HOST_SHARES (0 = the library's choice)
+  int sweep_tma = 0;             // streaming path: k_sweep_tma (TMA-staged tiles) instead of k_sweep
+  SweepTensorMaps sweep_tm;
   int pw_dirty = 1;              // SBX_OPT_NUMPY_MEANS: the per-plan summation trees need (re)building
   int pw_by_solve = 0;           // this step's solve kernel wrote pw_mean itself
   size_t pw_alloc_leaf = 0, pw_alloc_node = 0, pw_alloc_val = 0;   // capacities allocated so far
@@ -508,6 +511,7 @@ void* sweep_kernel_for(int rows_per_warp) {
     default: return (void*)k_sweep<V, 64, MODE>;
   }
 }
+void* sweep_tma_kernel(int mode) { return mode == 0 ? (void*)k_sweep_tma<0> : (void*)k_sweep_tma<1>; }
 // mode 0: a sweep k >= 2; 1: the first sweep
 void* sweep_kernel(int V, int rows_per_warp, int mode) {
   if (V == 4) return mode == 0 ? sweep_kernel_for<4, 0>(rows_per_warp) : sweep_kernel_for<4, 1>(rows_per_warp);
@@ -528,22 +532,24 @@ int build_sweep_graph(sbx_handle h, int which) {
   e = cudaGraphConditionalHandleCreate(&handle, g, 1, cudaGraphCondAssignDefault);
   if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphConditionalHandleCreate failed: %s", cudaGetErrorString(e)); }
   auto add_kernel = [&](cudaGraph_t where, cudaGraphNode_t* dep, void* func, dim3 grid, dim3 block, void** args,
-                        cudaGraphNode_t* out) -> cudaError_t {
+                        cudaGraphNode_t* out, unsigned smem = 0) -> cudaError_t {
     cudaKernelNodeParams kp;
     memset(&kp, 0, sizeof(kp));
-    kp.func = func; kp.gridDim = grid; kp.blockDim = block; kp.kernelParams = args;
+    kp.func = func; kp.gridDim = grid; kp.blockDim = block; kp.kernelParams = args; kp.sharedMemBytes = smem;
     return cudaGraphAddKernelNode(out, where, dep, dep ? 1 : 0, &kp);
   };
+  const bool tma = h->sweep_tma != 0;
   const dim3 sweep_grid((unsigned)((size_t)tl.tiles * p.B));
   int k_first = 1, k_dev = 0;
   cudaGraphNode_t n_begin = nullptr, n_first = nullptr, n_check1 = nullptr, n_while = nullptr, n_sweep = nullptr, n_check = nullptr;
   void* a_begin[] = {&p};
-  void* a_first[] = {&p, &k_first};
+  void* a_first[] = {&p, &k_first, &h->sweep_tm};      // the tensor maps: k_sweep_tma only
   void* a_check[] = {&p, &handle};
-  void* a_sweep[] = {&p, &k_dev};
+  void* a_sweep[] = {&p, &k_dev, &h->sweep_tm};
   e = add_kernel(g, nullptr, (void*)k_loop_begin, dim3((unsigned)((p.B + 255) / 256)), dim3(256), a_begin, &n_begin);
   if (e == cudaSuccess)
-    e = add_kernel(g, &n_begin, sweep_kernel(h->V, tl.rows_per_warp, 1), sweep_grid, dim3(kStreamThreads), a_first, &n_first);
+    e = add_kernel(g, &n_begin, tma ? sweep_tma_kernel(1) : sweep_kernel(h->V, tl.rows_per_warp, 1), sweep_grid,
+                   dim3(kStreamThreads), a_first, &n_first, tma ? (unsigned)sweep_tma_smem(true) : 0u);
   if (e == cudaSuccess) e = add_kernel(g, &n_first, (void*)k_check_loop, dim3(1), dim3(1024), a_check, &n_check1);
   if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphAddKernelNode failed: %s", cudaGetErrorString(e)); }
   cudaGraphNodeParams cp = {cudaGraphNodeTypeConditional};
@@ -553,7 +559,8 @@ int build_sweep_graph(sbx_handle h, int which) {
   e = cudaGraphAddNode(&n_while, g, &n_check1, 1, &cp);
   if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "conditional graph node failed: %s", cudaGetErrorString(e)); }
   cudaGraph_t body = cp.conditional.phGraph_out[0];
-  e = add_kernel(body, nullptr, sweep_kernel(h->V, tl.rows_per_warp, 0), sweep_grid, dim3(kStreamThreads), a_sweep, &n_sweep);
+  e = add_kernel(body, nullptr, tma ? sweep_tma_kernel(0) : sweep_kernel(h->V, tl.rows_per_warp, 0), sweep_grid,
+                 dim3(kStreamThreads), a_sweep, &n_sweep, tma ? (unsigned)sweep_tma_smem(false) : 0u);
   if (e == cudaSuccess) e = add_kernel(body, &n_sweep, (void*)k_check_loop, dim3(1), dim3(1024), a_check, &n_check);
   if (e != cudaSuccess) { cudaGraphDestroy(g); return fail(h, SBX_E_CUDA, "cudaGraphAddKernelNode (loop body) failed: %s", cudaGetErrorString(e)); }
   cudaGraphExec_t ex = nullptr;
@@ -597,9 +604,13 @@ int run_stream_sweeps(sbx_handle h, cudaStream_t st) {
     {
       Params pk = p;
       int kk = k;
-      void* args[] = {&pk, &kk};
-      CUDA_TRY(h, cudaLaunchKernel(sweep_kernel(h->V, tl.rows_per_warp, k > 1 ? 0 : 1),
-                                   dim3(grid), dim3(kStreamThreads), args, 0, st));
+      void* args[] = {&pk, &kk, &h->sweep_tm};
+      if (h->sweep_tma)
+        CUDA_TRY(h, cudaLaunchKernel(sweep_tma_kernel(k > 1 ? 0 : 1), dim3(grid), dim3(kStreamThreads), args,
+                                     sweep_tma_smem(k == 1), st));
+      else
+        CUDA_TRY(h, cudaLaunchKernel(sweep_kernel(h->V, tl.rows_per_warp, k > 1 ? 0 : 1),
+                                     dim3(grid), dim3(kStreamThreads), args, 0, st));
     }
     if (int rc = launch_check(h, "k_sweep")) return rc;
     if (int rc = timing_record(h, h->t_solve, h->t_solve_used, st)) return rc;
@@ -616,7 +627,12 @@ int run_stream_sweeps(sbx_handle h, cudaStream_t st) {
 // Tensor map of the [B, H, W] fp32 temperature field with a [1, H, P] box (P > W:
 // the extra columns are zero-filled on load, clipped on store).  The driver entry
 // point is resolved through the runtime, so libsbx does not link libcuda.
+int make_field_tensor_map(sbx_handle h, CUtensorMap* out, float* base, int B, int H, int W, int box_w, int box_h);
 int make_plane_tensor_map(sbx_handle h, float* base, int B, int H, int W, int P) {
+  return make_field_tensor_map(h, &h->tmap_t, base, B, H, W, P, H);
+}
+int make_field_tensor_map(sbx_handle h, CUtensorMap* out, float* base, int B, int H, int W, int box_w, int box_h) {
+  const int P = box_w;
   typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
                                   const cuuint64_t*, const cuuint32_t*, const cuuint32_t*,
                                   CUtensorMapInterleave, CUtensorMapSwizzle, CUtensorMapL2promotion,
@@ -628,10 +644,10 @@ int make_plane_tensor_map(sbx_handle h, float* base, int B, int H, int W, int P)
     return fail(h, SBX_E_CUDA, "cuTensorMapEncodeTiled is not available from this driver");
   const cuuint64_t gdim[3] = {(cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)B};
   const cuuint64_t gstride[2] = {(cuuint64_t)W * 4, (cuuint64_t)H * W * 4};
-  const cuuint32_t box[3] = {(cuuint32_t)P, (cuuint32_t)H, 1};
+  const cuuint32_t box[3] = {(cuuint32_t)P, (cuuint32_t)box_h, 1};
   const cuuint32_t estride[3] = {1, 1, 1};
   const CUresult r = reinterpret_cast<EncodeTiled>(fn)(
-      &h->tmap_t, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstride, box, estride,
+      out, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, base, gdim, gstride, box, estride,
       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_NONE,
       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) return fail(h, SBX_E_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
@@ -1073,6 +1089,20 @@ int sbx_create(const sbx_config* cfg, int device, sbx_handle* out) {
   memset(&h->tmap_t, 0, sizeof(h->tmap_t));
   if (h->path == SBX_PATH_RESIDENT && p.geom.use_tmap) {
     if (int rc = make_plane_tensor_map(h, p.tbuf[0], (int)B, c.height, c.width, p.geom.P)) return bail(rc);
+  }
+  memset(&h->sweep_tm, 0, sizeof(h->sweep_tm));
+  const char* tma_env = getenv("SBX_SWEEP_TMA");          // SBX_SWEEP_TMA=0: the plain-load k_sweep
+  if (h->path == SBX_PATH_STREAMING && h->V == 4 && c.solver == SBX_SOLVER_TF_JACOBI && !(tma_env && tma_env[0] == '0')) {
+    // TMA-staged sweep (sbx_sweep_tma.cuh): per rotation buffer one tensor map with the haloed
+    // T_est box and one with the T_prev box
+    for (int i = 0; i < 3; ++i) {
+      if (int rc = make_field_tensor_map(h, &h->sweep_tm.in[i], p.tbuf[i], (int)B, c.height, c.width, kTmaBoxW, kTmaChunk + 2)) return bail(rc);
+      if (int rc = make_field_tensor_map(h, &h->sweep_tm.prev[i], p.tbuf[i], (int)B, c.height, c.width, 128, kTmaChunk)) return bail(rc);
+    }
+    cudaError_t e = cudaFuncSetAttribute(k_sweep_tma<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_tma_smem(false));
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(k_sweep_tma<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sweep_tma_smem(true));
+    if (e != cudaSuccess) { fail(h, SBX_E_CUDA, "cudaFuncSetAttribute(k_sweep_tma) failed: %s", cudaGetErrorString(e)); return bail(SBX_E_CUDA); }
+    h->sweep_tma = 1;
   }
   ALLOC(p.cur, uint8_t, B);
   ALLOC(p.zone_mean, float, B * Z);

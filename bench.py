@@ -426,7 +426,7 @@ def _measure(args, torch, dist, rank, local_rank, world, dev, with_cpu):
     kernel = ("%s (the whole diffusion solve of every building; %d launch(es) per "
               "step, one per pipelined share of the batch)" % (kname, tm.n_chunks))
   else:
-    kernel = "k_sweep (one Jacobi sweep of every active building per launch; %.2f launches per step)" % (
+    kernel = "k_sweep_tma / k_sweep (one Jacobi sweep of every active building per launch; %.2f launches per step)" % (
         tm.n_solve_launches / max(tm.n_steps, 1))
   traffic = None
   try:  # DRAM bytes per launch from the committed ncu --set full capture, scaled to this B

@@ -127,8 +127,8 @@ if os.path.exists(f"{SRC}/r02_randomized_v3.ncu-rep"):
 h2, u2, d2 = summarize(f"{SRC}/r02_office.ncu-rep", "profiles/r02_ncu_full_office.txt",
                        "ncu --set full --clock-control none --import-source on, `python bench.py --workload office "
                        "--envs-per-gpu 512` (calibrated sb1 plan 744x1004, 512 copies so that the ~40 replays stay short, "
-                       "device-RNG convection as shipped; host-polled sweep loop, see profiles/capture_r02_office.sh): k_sweep<4>, "
-                       "k_convect_reduce (profiles/capture_r02_office.sh)",
+                       "device-RNG convection as shipped; host-polled sweep loop, see profiles/capture_r02_office.sh): k_sweep_tma "
+                       "(TMA-staged tiles, the default sweep), k_convect_reduce (profiles/capture_r02_office.sh)",
                        "k_sweep")
 for name in ("randomized", "office"):
   rows = list(csv.reader(open(f"{SRC}/r02_launches_{name}.csv")))
@@ -143,7 +143,7 @@ traffic = {
                    "dram_bytes_read": col(h1, u1, d1, "dram__bytes_read.sum", ir),
                    "dram_bytes_write": col(h1, u1, d1, "dram__bytes_write.sum", ir),
                    "source": "profiles/r02_ncu_full_randomized.txt (ncu --set full, 32768 buildings per launch)"},
-    "office": {"kernel": "k_sweep<4>", "launch_envs": 512,
+    "office": {"kernel": "k_sweep_tma<0>", "launch_envs": 512,
                "dram_bytes_read": col(h2, u2, d2, "dram__bytes_read.sum", isw),
                "dram_bytes_write": col(h2, u2, d2, "dram__bytes_write.sum", isw),
                "source": "profiles/r02_ncu_full_office.txt (ncu --set full, 512 buildings per launch, a sweep >= 2: reads "

@@ -96,6 +96,59 @@ def test_resident_kernels_agree_bit_for_bit(resident_kernel):
     env.close()
 
 
+@pytest.mark.parametrize("sweep", ["k_sweep_tma", "k_sweep"])
+@pytest.mark.parametrize("plan_name", ["rand_64x96", "wide_12x320"])
+def test_streaming_sweep_kernels_bit_exact(sweep, plan_name, monkeypatch):
+  """The streaming path has two sweep kernels for 4-CV vectors: k_sweep_tma (TMA-staged tiles,
+  the default) and k_sweep (plain loads, SBX_SWEEP_TMA=0; also what 1-CV vectors run).  Both
+  against the oracle: a solve with per-building ambient / convection / heat input bit for bit,
+  then a free-running rollout whose observations must be IDENTICAL between the two kernels."""
+  monkeypatch.delenv("SBX_SWEEP_TMA", raising=False)
+  if sweep == "k_sweep":
+    monkeypatch.setenv("SBX_SWEEP_TMA", "0")
+  plan, bfw = _plans()[plan_name]
+  sc = S.Scenario(floor_plan=plan, buffer_from_walls=bfw, cv_size_cm=10.0 if "rand" in plan_name else 20.0)
+  cp = sc.compiled()
+  B = 5
+  env = S.make_env(sc, n_envs=B, plans=cp, kernel_path=sbx.PATH_STREAMING)
+  try:
+    env.reset()
+    rng = np.random.default_rng(3)
+    H, W, Z = cp.height, cp.width, env.building.n_zones
+    temp = (rng.uniform(285, 300, (B, H, W))).astype(np.float32)
+    qcv = rng.uniform(-50, 400, (B, Z)).astype(np.float32)
+    ambient = rng.uniform(270, 300, B)
+    conv = rng.uniform(5, 100, B)
+    env.handle.upload("temp", temp)
+    env.handle.upload("q_cv", qcv)
+    env.handle.fd_step(ambient, conv)
+    got = env.handle.download("temp", (B, H, W))
+    sweeps = env.handle.download("n_sweeps", (B,))
+    jac = tf_jacobi.TFJacobi(S.oracle_plan(cp, sc.floor_height_cm), sc.time_step_sec,
+                             sc.convergence_threshold, sc.iteration_limit)
+    for b in range(B):
+      want, n, _, _ = jac.fd_step(temp[b], _dense_q(cp, qcv[b]), ambient[b], conv[b])
+      assert sweeps[b] == n, (b, sweeps[b], n)
+      np.testing.assert_array_equal(got[b], want, err_msg=f"env {b}")
+    # a rollout from a fresh reset: a digest of everything the step returns, compared across the
+    # two parametrizations through a module-level dict
+    env.reset()
+    arng = np.random.default_rng(8)
+    digest = []
+    for _ in range(6):
+      ts = env.step(arng.uniform(-1, 1, (B, 2)).astype(np.float32))
+      digest.append((ts.observation.tobytes(), ts.reward.tobytes(), env.handle.download("temp", (B, H, W)).tobytes()))
+    other = _SWEEP_DIGESTS.setdefault(plan_name, {})
+    other[sweep] = digest
+    if len(other) == 2:
+      assert other["k_sweep_tma"] == other["k_sweep"]
+  finally:
+    env.close()
+
+
+_SWEEP_DIGESTS = {}
+
+
 @pytest.mark.parametrize("path", list(PATHS))
 @pytest.mark.parametrize("plan_name", list(_plans()))
 def test_fd_step_bit_exact(path, plan_name):

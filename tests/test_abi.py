@@ -55,6 +55,11 @@ def test_header_constants_match_binding():
   for name, idx in _lib.DIAG.items():
     assert int(diag["SBX_DIAG_" + name.upper()]) == idx, name
   assert int(diag["SBX_DIAG_N"]) == _lib.DIAG_N
+  # sbx_set_option knobs
+  opts = dict(re.findall(r"#define\s+(SBX_OPT_[A-Z0-9_]+)\s+(\d+)", text))
+  assert len(opts) == 4
+  for name, v in opts.items():
+    assert int(v) == getattr(_lib, name[len("SBX_"):]), name
 
 
 def test_create_fails_loudly_without_cuda_or_with_bad_config():
